@@ -1,0 +1,273 @@
+"""ORACLE -- test infrastructure, not product code.
+
+ctypes front-end shared by the two CPU checkers:
+
+* ``port()``  -> oracle/libgomoku_oracle.so, the plain-C restatement (gomoku_oracle.c)
+* ``ref()``   -> oracle/_ref/libgomoku_ref.so, the reference's own sources compiled by
+                 oracle/Makefile (None when it has not been built)
+
+Both expose the same Python methods so a test can run the same check against either.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm import this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(_HERE, "libgomoku_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libgomoku_ref.so")
+REFERENCE_ROOT = "/root/reference/core/lib"
+
+
+def build(want_ref=True):
+    """Compile the C restatement, and oracle/_ref when /root/reference is present."""
+    subprocess.run(["make", "-s", "-C", _HERE, "port"], check=True)
+    if want_ref and os.path.isdir(REFERENCE_ROOT):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pack_moves(move_lists):
+    """list of move lists -> (int16 moves, int64 starts)"""
+    starts = np.zeros(len(move_lists) + 1, np.int64)
+    for i, m in enumerate(move_lists):
+        starts[i + 1] = starts[i] + len(m)
+    moves = np.zeros(max(int(starts[-1]), 1), np.int16)
+    for i, m in enumerate(move_lists):
+        moves[starts[i]:starts[i + 1]] = m
+    return moves, starts
+
+
+class Oracle:
+    def __init__(self, path, prefix, kind):
+        self.lib = ctypes.CDLL(path)
+        self.prefix = prefix
+        self.kind = kind          # "port" | "reference"
+        self._table = None
+        if prefix == "orc_":
+            self.lib.orc_table_default.restype = ctypes.c_void_p
+            self.lib.orc_table_build.restype = ctypes.c_void_p
+            self._table = ctypes.c_void_p(self.lib.orc_table_default())
+            self._default = self._table
+        for name in ("scan_many", "linescan_batch"):
+            getattr(self.lib, prefix + name).restype = ctypes.c_long
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _which(self, custom):
+        # the port passes a table pointer, the reference harness a selector
+        if self.prefix == "orc_":
+            return self._table if custom else self._default
+        return 1 if custom else 0
+
+    # ---- automaton -------------------------------------------------------------------
+    def build_custom(self, protos, types, scores):
+        n = len(protos)
+        arr = (ctypes.c_char_p * n)(*[p.encode() for p in protos])
+        t = (ctypes.c_int * n)(*types)
+        s = (ctypes.c_int * n)(*scores)
+        if self.prefix == "orc_":
+            self._table = ctypes.c_void_p(self.lib.orc_table_build(arr, t, s, n))
+        else:
+            self.lib.ref_table_build_custom(arr, t, s, n)
+
+    def table(self, custom=False):
+        nb, npat = ctypes.c_int(), ctypes.c_int()
+        self._f("table_sizes")(self._which(custom), ctypes.byref(nb), ctypes.byref(npat))
+        base = np.zeros(nb.value, np.int32)
+        check, fail = base.copy(), base.copy()
+        inv = np.zeros(5, np.int32)
+        self._f("table_arrays")(self._which(custom), _p(base), _p(check), _p(fail), _p(inv))
+        pats = []
+        for i in range(npat.value):
+            s = ctypes.create_string_buffer(8)
+            fav, typ, sc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            self._f("table_pattern")(self._which(custom), i, s, ctypes.byref(fav), ctypes.byref(typ), ctypes.byref(sc))
+            pats.append((s.value.decode(), fav.value, typ.value, sc.value))
+        return {"base": base, "check": check, "fail": fail, "invariants": inv, "patterns": pats}
+
+    def augment(self, protos, types, scores, stage):
+        n = len(protos)
+        arr = (ctypes.c_char_p * n)(*[p.encode() for p in protos])
+        t = (ctypes.c_int * n)(*types)
+        s = (ctypes.c_int * n)(*scores)
+        cap = 12 * n + 1
+        strs = ctypes.create_string_buffer(8 * cap)
+        fav, typ, sc = (np.zeros(cap, np.int32) for _ in range(3))
+        m = self._f("augment")(arr, t, s, n, stage, strs, _p(fav), _p(typ), _p(sc), cap)
+        raw = strs.raw
+        return [(raw[8 * i:8 * i + 8].split(b"\0")[0].decode(), int(fav[i]), int(typ[i]), int(sc[i])) for i in range(m)]
+
+    def scan(self, codes, custom=False, cap=256):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        pids, offs = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n = self._f("scan")(self._which(custom), _p(codes), len(codes), _p(pids), _p(offs), cap)
+        assert n <= cap
+        return list(zip(pids[:n].tolist(), offs[:n].tolist()))
+
+    def scan_many(self, codes, starts, custom=False, cap=None):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        starts = np.ascontiguousarray(starts, np.int64)
+        ns = len(starts) - 1
+        cap = cap or 4 * len(codes) + 16
+        pids, offs = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        counts = np.zeros(ns, np.int32)
+        total = self._f("scan_many")(self._which(custom), _p(codes), _p(starts), ns, _p(pids), _p(offs), _p(counts), ctypes.c_long(cap))
+        assert total <= cap
+        return pids[:total], offs[:total], counts
+
+    # ---- line views -----------------------------------------------------------------
+    def line_view(self, moves, pose, direction):
+        mv = np.ascontiguousarray(moves, np.int16)
+        out = np.zeros(13, np.uint8)
+        self._f("line_view")(_p(mv), len(mv), int(pose), int(direction), _p(out))
+        return out
+
+    def line_map(self, moves):
+        mv = np.ascontiguousarray(moves, np.int16)
+        out = np.zeros(88 * 28, np.uint8)
+        lens = np.zeros(88, np.int32)
+        k = self._f("line_map")(_p(mv), len(mv), _p(out), _p(lens))
+        lines, at = [], 0
+        for ln in lens:
+            lines.append(out[at:at + ln].copy())
+            at += ln
+        assert at == k
+        return lines
+
+    # ---- evaluator ------------------------------------------------------------------
+    def eval_batch(self, moves, starts, want_scores=True):
+        """-> dict(scores[N,4,225] i32, pat_totals[N,2,8] u16, cmp_totals[N,2,3] u16, winner, cur_player, bad)"""
+        moves = np.ascontiguousarray(moves, np.int16)
+        starts = np.ascontiguousarray(starts, np.int64)
+        n = len(starts) - 1
+        scores = np.zeros((n, 4, 225), np.int32) if want_scores else None
+        pt = np.zeros((n, 2, 8), np.uint16)
+        ct = np.zeros((n, 2, 3), np.uint16)
+        win = np.zeros(n, np.int8)
+        cur = np.zeros(n, np.int8)
+        bad = self._f("eval_batch")(_p(moves), _p(starts), n, _p(scores), _p(pt), _p(ct), _p(win), _p(cur))
+        return {"scores": scores, "pat_totals": pt, "cmp_totals": ct, "winner": win, "cur_player": cur, "bad": bad}
+
+    def eval_moves(self, move_list):
+        mv, st = pack_moves([move_list])
+        r = self.eval_batch(mv, st)
+        return {k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in r.items()}
+
+    def eval_flags(self):
+        pf = np.zeros((225, 8), np.uint32)
+        cf = np.zeros((225, 3), np.uint32)
+        den = np.zeros((2, 2, 225), np.int32)
+        self._f("eval_flags")(_p(pf), _p(cf), _p(den))
+        return pf, cf, den
+
+    def linescan_batch(self, moves, starts):
+        moves = np.ascontiguousarray(moves, np.int16)
+        starts = np.ascontiguousarray(starts, np.int64)
+        return self._f("linescan_batch")(_p(moves), _p(starts), len(starts) - 1)
+
+    # ---- board / rollout ------------------------------------------------------------
+    def board_play(self, moves):
+        mv = np.ascontiguousarray(moves, np.int16)
+        out = np.zeros(3, np.int32)
+        self._f("board_play")(_p(mv), len(mv), _p(out))
+        return {"cur_player": int(out[0]), "winner": int(out[1]), "applied": int(out[2])}
+
+    def rollout_injected(self, moves, r_stream):
+        mv = np.ascontiguousarray(moves, np.int16)
+        rs = np.ascontiguousarray(r_stream, np.uint8)
+        n = ctypes.c_int()
+        w = self._f("rollout_injected")(_p(mv), len(mv), _p(rs), len(rs), ctypes.byref(n))
+        return w, n.value
+
+
+class PortOracle(Oracle):
+    """extras only the C restatement has (Philox stream, apply/revert, degenerate counter)"""
+
+    def __init__(self):
+        super().__init__(PORT_SO, "orc_", "port")
+        self.lib.orc_degenerate_compounds.restype = ctypes.c_long
+
+    def philox(self, ctr, key):
+        c = (ctypes.c_uint32 * 4)(*ctr)
+        k = (ctypes.c_uint32 * 2)(*key)
+        o = (ctypes.c_uint32 * 4)()
+        self.lib.orc_philox4x32_10(c, k, o)
+        return list(o)
+
+    def rollout_philox_batch(self, moves, starts, rollouts_per_pos, key, ctr_hi=0, pos_base=0):
+        moves = np.ascontiguousarray(moves, np.int16)
+        starts = np.ascontiguousarray(starts, np.int64)
+        n = len(starts) - 1
+        winners = np.zeros((n, rollouts_per_pos), np.int8)
+        lengths = np.zeros((n, rollouts_per_pos), np.uint8)
+        wdb = np.zeros((n, 3), np.int32)
+        self.lib.orc_rollout_philox_batch(_p(moves), _p(starts), n, rollouts_per_pos, ctypes.c_uint64(key),
+                                          ctypes.c_uint32(ctr_hi), pos_base, _p(winners), _p(lengths), _p(wdb))
+        return winners, lengths, wdb
+
+    def eval_apply_revert(self, moves, n_revert):
+        mv = np.ascontiguousarray(moves, np.int16)
+        scores = np.zeros((4, 225), np.int32)
+        pt = np.zeros((2, 8), np.uint16)
+        ct = np.zeros((2, 3), np.uint16)
+        bad = self.lib.orc_eval_apply_revert(_p(mv), len(mv), n_revert, _p(scores), _p(pt), _p(ct))
+        return {"scores": scores, "pat_totals": pt, "cmp_totals": ct, "bad": bad}
+
+    def eval_scratch_batch(self, moves, starts, lead=1, trail=2, min_len=5):
+        """from-scratch model of the kernel's algorithm (same output dict as eval_batch)"""
+        moves = np.ascontiguousarray(moves, np.int16)
+        starts = np.ascontiguousarray(starts, np.int64)
+        n = len(starts) - 1
+        scores = np.zeros((n, 4, 225), np.int32)
+        pt = np.zeros((n, 2, 8), np.uint16)
+        ct = np.zeros((n, 2, 3), np.uint16)
+        win = np.zeros(n, np.int8)
+        bad = self.lib.orc_eval_scratch_batch(_p(moves), _p(starts), n, lead, trail, min_len, _p(scores), _p(pt), _p(ct), _p(win))
+        return {"scores": scores, "pat_totals": pt, "cmp_totals": ct, "winner": win, "bad": bad}
+
+    def scratch_gate_blocks(self):
+        self.lib.orc_scratch_gate_blocks.restype = ctypes.c_long
+        return self.lib.orc_scratch_gate_blocks()
+
+    def degenerate_compounds(self):
+        return self.lib.orc_degenerate_compounds()
+
+
+class RefOracle(Oracle):
+    def __init__(self):
+        super().__init__(REF_SO, "ref_", "reference")
+
+    def rollout_free(self, moves, n_rollouts):
+        mv = np.ascontiguousarray(moves, np.int16)
+        wdb = np.zeros(3, np.int64)
+        total = np.zeros(1, np.int64)
+        self.lib.ref_rollout_free(_p(mv), len(mv), n_rollouts, _p(wdb), _p(total))
+        return wdb, int(total[0])
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        if not os.path.exists(PORT_SO):
+            build(want_ref=False)
+        _port = PortOracle()
+    return _port
+
+
+def ref():
+    """The compiled reference, or None if oracle/_ref has not been built."""
+    global _ref
+    if _ref is None and os.path.exists(REF_SO):
+        _ref = RefOracle()
+    return _ref
