@@ -1,0 +1,300 @@
+"""gomokuai_b200 -- B200-native hot path of Vigilans/GomokuAI (pattern evaluation + random rollouts).
+
+This module is a thin ctypes binding over the C-ABI in ``include/gomoku_b200.h``
+(``gomokuai_b200/lib/libgomoku_b200.so``, hand-written sm_100a CUDA).  PyTorch is used only to own
+device memory and streams.  There is no CPU fallback: if the shared library is missing, or no
+sm_100 GPU is visible, every compute entry point raises.
+
+Build the library in-tree with ``python -m gomokuai_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgomoku_b200.so")
+
+CELLS = 225
+BOARD_WORDS = 16
+PATTERN_TYPES = ("DeadOne", "LiveOne", "DeadTwo", "LiveTwo", "DeadThree", "LiveThree", "DeadFour", "LiveFour", "Five")
+COMPOUND_TYPES = ("DoubleThree", "FourThree", "DoubleFour")
+SYNTH_KEY = 0x474F4D4F4B5531
+
+
+class GomokuB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+_device = None
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GomokuB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m gomokuai_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.gk_last_error.restype = ctypes.c_char_p
+        L.gk_version.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise GomokuB200Error(f"gk status {status}: {lib().gk_last_error().decode()}")
+
+
+def init(device=None):
+    """Bind this process to one GPU (one process per GPU). Returns the device index."""
+    global _device
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    _check(lib().gk_init(int(device)))
+    _device = int(device)
+    return _device
+
+
+def _require_init():
+    if _device is None:
+        init()
+    return _device
+
+
+def device_info():
+    _require_init()
+    d, sm, maj, mnr = (ctypes.c_int() for _ in range(4))
+    _check(lib().gk_device_info(ctypes.byref(d), ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)))
+    return {"device": d.value, "sm_count": sm.value, "cc": (maj.value, mnr.value)}
+
+
+# ---- tables ------------------------------------------------------------------------------------------
+class Table:
+    """Compiled pattern automaton (``gk_table``). ``Table()`` is the reference's default pattern set."""
+
+    def __init__(self, protos=None, types=None, scores=None):
+        self._h = ctypes.c_void_p()
+        self._owned = protos is not None
+        if protos is None:
+            _check(lib().gk_table_default(ctypes.byref(self._h)))
+        else:
+            n = len(protos)
+            arr = (ctypes.c_char_p * n)(*[p.encode() for p in protos])
+            _check(lib().gk_table_build(arr, (ctypes.c_int * n)(*types), (ctypes.c_int * n)(*scores), n,
+                                        ctypes.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self._h and _lib is not None:
+            _lib.gk_table_free(self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        a, b, c, d = (ctypes.c_int() for _ in range(4))
+        _check(lib().gk_table_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return {"n_states": a.value, "n_patterns": b.value, "trail_pad": c.value, "tape_steps": d.value}
+
+    def pattern(self, i):
+        s = ctypes.create_string_buffer(8)
+        fav, typ, sc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().gk_table_pattern(self._h, int(i), s, ctypes.byref(fav), ctypes.byref(typ), ctypes.byref(sc)))
+        return (s.raw.split(b"\0")[0].decode(), fav.value, typ.value, sc.value)
+
+    def patterns(self):
+        return [self.pattern(i) for i in range(self.info()["n_patterns"])]
+
+    def entries(self):
+        """Flat transition words, shape [n_states, 4] (see csrc/gk_format.h)."""
+        n = self.info()["n_states"]
+        out = np.zeros(n * 4, np.uint32)
+        _check(lib().gk_table_entries(self._h, out.ctypes.data_as(ctypes.c_void_p), out.size))
+        return out.reshape(n, 4)
+
+
+    def flush(self):
+        """Per state: pattern id owed when the input ends there (-1 = none)."""
+        n = self.info()["n_states"]
+        out = np.zeros(n, np.int16)
+        _check(lib().gk_table_flush(self._h, out.ctypes.data_as(ctypes.c_void_p), out.size))
+        return out
+
+
+_default_table = None
+
+
+def default_table():
+    global _default_table
+    if _default_table is None:
+        _default_table = Table()
+    return _default_table
+
+
+# ---- host utilities ------------------------------------------------------------------------------------
+def pack_moves(moves, starts):
+    """Move lists (black first, alternating) -> uint32[n,16] packed boards (numpy, host)."""
+    moves = np.ascontiguousarray(moves, np.int16)
+    starts = np.ascontiguousarray(starts, np.int64)
+    n = len(starts) - 1
+    boards = np.zeros((n, BOARD_WORDS), np.uint32)
+    _check(lib().gk_pack_moves(moves.ctypes.data_as(ctypes.c_void_p), starts.ctypes.data_as(ctypes.c_void_p), n,
+                               boards.ctypes.data_as(ctypes.c_void_p)))
+    return boards
+
+
+def synth_positions(first, n, want_moves=True):
+    """The synthetic random mid-game set of BASELINE.json. Returns (boards[n,16] u32, moves i16, starts i64)."""
+    boards = np.zeros((n, BOARD_WORDS), np.uint32)
+    moves = np.zeros(96 * max(n, 1), np.int16) if want_moves else None
+    starts = np.zeros(n + 1, np.int64) if want_moves else None
+    _check(lib().gk_synth_positions(ctypes.c_int64(first), int(n), boards.ctypes.data_as(ctypes.c_void_p),
+                                    moves.ctypes.data_as(ctypes.c_void_p) if want_moves else None,
+                                    starts.ctypes.data_as(ctypes.c_void_p) if want_moves else None))
+    if want_moves:
+        moves = moves[:int(starts[-1])].copy()
+    return boards, moves, starts
+
+
+def unpack_boards(boards):
+    """uint32[n,16] -> uint8[n,225] cell values (0 empty, 1 black, 2 white)."""
+    boards = np.asarray(boards, np.uint32).reshape(-1, BOARD_WORDS)
+    c = np.arange(CELLS)
+    return ((boards[:, c >> 4] >> ((c & 15) * 2).astype(np.uint32)) & 3).astype(np.uint8)
+
+
+# ---- device entry points (torch tensors on the bound GPU) ---------------------------------------------
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(stream):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _as_board_tensor(boards):
+    torch = _torch()
+    dev = torch.device("cuda", _require_init())
+    if isinstance(boards, np.ndarray):
+        boards = torch.from_numpy(boards.view(np.int32)).to(dev)
+    if boards.dtype != torch.int32 or boards.dim() != 2 or boards.shape[1] != BOARD_WORDS or not boards.is_contiguous():
+        raise GomokuB200Error("boards must be a contiguous int32 tensor of shape [n, 16]")
+    if not boards.is_cuda:
+        boards = boards.to(dev)
+    return boards
+
+
+def eval_batch(boards, table=None, want_scores=True, out=None, stream=None):
+    """Evaluate packed boards on the GPU. Returns dict(scores[n,4,225] i32, pat_totals[n,2,8] i16,
+    cmp_totals[n,2,3] i16, winner[n] i8) of CUDA tensors (totals are uint16 bit patterns in int16)."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    table = table or default_table()
+    n = boards.shape[0]
+    dev = boards.device
+    if out is None:
+        out = {
+            "scores": torch.empty((n, 4, CELLS), dtype=torch.int32, device=dev) if want_scores else None,
+            "pat_totals": torch.empty((n, 2, 8), dtype=torch.int16, device=dev),
+            "cmp_totals": torch.empty((n, 2, 3), dtype=torch.int16, device=dev),
+            "winner": torch.empty((n,), dtype=torch.int8, device=dev),
+        }
+    _check(lib().gk_eval_batch(table.handle, _ptr(boards), n, _ptr(out.get("scores")), _ptr(out["pat_totals"]),
+                               _ptr(out["cmp_totals"]), _ptr(out["winner"]), _stream_ptr(stream)))
+    return out
+
+
+def eval_batch_host(boards, table=None, want_scores=True, out=None):
+    """Same through HOST buffers (numpy arrays or pinned CPU tensors): copies are part of the call."""
+    table = table or default_table()
+    _require_init()
+    b = boards.numpy() if hasattr(boards, "numpy") else boards
+    b = np.ascontiguousarray(b).view(np.uint32).reshape(-1, BOARD_WORDS)
+    n = b.shape[0]
+    if out is None:
+        out = {
+            "scores": np.empty((n, 4, CELLS), np.int32) if want_scores else None,
+            "pat_totals": np.empty((n, 2, 8), np.uint16),
+            "cmp_totals": np.empty((n, 2, 3), np.uint16),
+            "winner": np.empty((n,), np.int8),
+        }
+
+    def hp(x):
+        if x is None:
+            return None
+        return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else x.ctypes.data_as(ctypes.c_void_p)
+
+    _check(lib().gk_eval_batch_host(table.handle, b.ctypes.data_as(ctypes.c_void_p), n, hp(out.get("scores")),
+                                    hp(out["pat_totals"]), hp(out["cmp_totals"]), hp(out["winner"])))
+    return out
+
+
+def rollout_batch(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_base=0, want_trace=False, stream=None):
+    """Random playouts. Returns dict(wdb[n,3] i32 = {white, draw, black}, winners[n,R] i8, lengths[n,R] u8)."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    n = boards.shape[0]
+    dev = boards.device
+    wdb = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    winners = torch.empty((n, rollouts_per_pos), dtype=torch.int8, device=dev) if want_trace else None
+    lengths = torch.empty((n, rollouts_per_pos), dtype=torch.uint8, device=dev) if want_trace else None
+    _check(lib().gk_rollout_batch(_ptr(boards), n, int(rollouts_per_pos), ctypes.c_uint64(key), ctypes.c_uint32(ctr_hi),
+                                  int(pos_base), _ptr(wdb), _ptr(winners), _ptr(lengths), _stream_ptr(stream)))
+    return {"wdb": wdb, "winners": winners, "lengths": lengths}
+
+
+def rollout_batch_host(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_base=0, out=None):
+    _require_init()
+    b = boards.numpy() if hasattr(boards, "numpy") else boards
+    b = np.ascontiguousarray(b).view(np.uint32).reshape(-1, BOARD_WORDS)
+    n = b.shape[0]
+    wdb = out if out is not None else np.empty((n, 3), np.int32)
+    p = ctypes.c_void_p(wdb.data_ptr()) if hasattr(wdb, "data_ptr") else wdb.ctypes.data_as(ctypes.c_void_p)
+    _check(lib().gk_rollout_batch_host(b.ctypes.data_as(ctypes.c_void_p), n, int(rollouts_per_pos), ctypes.c_uint64(key),
+                                       ctypes.c_uint32(ctr_hi), int(pos_base), p))
+    return wdb
+
+
+def rollout_injected(boards, r_stream, stream=None):
+    """Playouts driven by an explicit start-index stream r_stream[n, R, stride] (uint8, values 0..224)."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    n = boards.shape[0]
+    if isinstance(r_stream, np.ndarray):
+        r_stream = torch.from_numpy(np.ascontiguousarray(r_stream, np.uint8)).to(boards.device)
+    if r_stream.dim() != 3 or r_stream.shape[0] != n or r_stream.dtype != torch.uint8 or not r_stream.is_contiguous():
+        raise GomokuB200Error("r_stream must be a contiguous uint8 tensor of shape [n, R, stride]")
+    R, stride = r_stream.shape[1], r_stream.shape[2]
+    winners = torch.empty((n, R), dtype=torch.int8, device=boards.device)
+    lengths = torch.empty((n, R), dtype=torch.uint8, device=boards.device)
+    _check(lib().gk_rollout_injected(_ptr(boards), n, R, _ptr(r_stream), stride, _ptr(winners), _ptr(lengths),
+                                     _stream_ptr(stream)))
+    return {"winners": winners, "lengths": lengths}
+
+
+def scan_batch(codes, starts, table=None, max_per_string=16, stream=None):
+    """PatternSearch::matches for a batch of symbol strings (codes 1..4). Returns (pids, offsets, counts)."""
+    torch = _torch()
+    dev = torch.device("cuda", _require_init())
+    table = table or default_table()
+    codes_t = torch.from_numpy(np.ascontiguousarray(codes, np.uint8)).to(dev)
+    starts_t = torch.from_numpy(np.ascontiguousarray(starts, np.int64)).to(dev)
+    ns = len(starts) - 1
+    pids = torch.full((ns, max_per_string), -1, dtype=torch.int32, device=dev)
+    offs = torch.full((ns, max_per_string), -1, dtype=torch.int32, device=dev)
+    counts = torch.zeros((ns,), dtype=torch.int32, device=dev)
+    _check(lib().gk_scan_batch(table.handle, _ptr(codes_t), _ptr(starts_t), ns, int(max_per_string), _ptr(pids),
+                               _ptr(offs), _ptr(counts), _stream_ptr(stream)))
+    return pids, offs, counts

@@ -1,0 +1,426 @@
+// gk_capi.cu -- the C-ABI of include/gomoku_b200.h: argument checking, table upload,
+// stream plumbing and the chunked host<->device pipelines.  No compute happens here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gomoku_b200.h"
+#include "gk_kernels.h"
+#include "gk_table.h"
+
+struct gk_table {
+    gk::HostTable host;
+    uint32_t* d_trans = nullptr;
+    gk::PatRec* d_patrec = nullptr;
+    uint32_t* d_tape = nullptr;
+    int16_t* d_flush = nullptr;
+    bool is_default = false;
+};
+
+namespace {
+
+thread_local std::string t_error;
+std::mutex g_mutex;
+int g_device = -1, g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
+gk_table* g_default_table = nullptr;
+
+gk_status fail(gk_status code, const std::string& msg) { t_error = msg; return code; }
+gk_status cuda_fail(cudaError_t e, const char* what) {
+    return fail(GK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define GK_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+
+gk_status require_device() {
+    if (g_device < 0) return fail(GK_ERR_NOT_INIT, "gk_init() has not been called");
+    return GK_OK;
+}
+
+gk_status upload(gk_table* t) {
+    const gk::HostTable& h = t->host;
+    GK_CUDA(cudaMalloc(&t->d_trans, h.trans.size() * sizeof(uint32_t)));
+    GK_CUDA(cudaMalloc(&t->d_patrec, h.patrec.size() * sizeof(gk::PatRec)));
+    GK_CUDA(cudaMalloc(&t->d_tape, h.tape.size() * sizeof(uint32_t)));
+    GK_CUDA(cudaMalloc(&t->d_flush, h.flush.size() * sizeof(int16_t)));
+    GK_CUDA(cudaMemcpy(t->d_trans, h.trans.data(), h.trans.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    GK_CUDA(cudaMemcpy(t->d_patrec, h.patrec.data(), h.patrec.size() * sizeof(gk::PatRec), cudaMemcpyHostToDevice));
+    GK_CUDA(cudaMemcpy(t->d_tape, h.tape.data(), h.tape.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    GK_CUDA(cudaMemcpy(t->d_flush, h.flush.data(), h.flush.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    return GK_OK;
+}
+
+// device copies are created lazily so that tables can be compiled and inspected without a GPU
+gk_status ensure_uploaded(const gk_table* ct) {
+    gk_table* t = const_cast<gk_table*>(ct);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (t->d_trans) return GK_OK;
+    return upload(t);
+}
+
+gk::EvalArgs eval_args(const gk_table* t, const uint32_t* boards, long long n, int32_t* scores, uint16_t* pat,
+                       uint16_t* cmp, int8_t* winner) {
+    gk::EvalArgs a{};
+    a.trans = t->d_trans; a.n_states = t->host.n_states;
+    a.patrec = t->d_patrec; a.n_patterns = (int)t->host.patrec.size();
+    a.tape = t->d_tape; a.tape_steps = t->host.tape_steps;
+    a.start_state = (uint32_t)t->host.start_state;
+    a.boards = boards; a.n = n;
+    a.scores = scores; a.pat_totals = pat; a.cmp_totals = cmp; a.winner = winner;
+    return a;
+}
+
+// ---- Philox4x32-10 on the host (synthetic position generator only) -----------------------------
+void philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0, n2 = uint32_t(p0 >> 32) ^ c3 ^ k1;
+        c1 = uint32_t(p1); c3 = uint32_t(p0); c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+bool makes_five(const uint8_t* cells, int c, int colour) {
+    const int x0 = c % 15, y0 = c / 15;
+    static const int DX[4] = { 1, 0, 1, 1 }, DY[4] = { 0, 1, 1, -1 };
+    for (int d = 0; d < 4; ++d) {
+        int run = 1;
+        for (int s = -1; s <= 1; s += 2)
+            for (int i = 1; i < 5; ++i) {
+                const int x = x0 + s * i * DX[d], y = y0 + s * i * DY[d];
+                if (x < 0 || x >= 15 || y < 0 || y >= 15 || cells[y * 15 + x] != colour) break;
+                ++run;
+            }
+        if (run >= 5) return true;
+    }
+    return false;
+}
+
+void synth_one(int64_t index, uint32_t* board, int16_t* moves, int* n_moves) {
+    const uint32_t key[2] = { 0x4F4B5531u, 0x00474F4Du };          // 0x474F4D4F4B5531 "GOMOKU1"
+    const uint32_t ilo = uint32_t(index), ihi = uint32_t(uint64_t(index) >> 32);
+    uint32_t w[4];
+    const uint32_t hctr[4] = { 0xffffffffu, 0u, ilo, ihi };
+    philox_host(hctr, key, w);
+    const int target = 16 + int(w[0] % 81u);
+    uint8_t cells[225] = { 0 };
+    int16_t empty[225];
+    for (int i = 0; i < 225; ++i) empty[i] = (int16_t)i;
+    int n_empty = 225, placed = 0;
+    uint32_t draw = 0, block = 0xffffffffu;
+    while (placed < target) {
+        const int colour = (placed & 1) ? 2 : 1;
+        int slot = -1;
+        for (int tries = 0; tries < 64 && slot < 0; ++tries, ++draw) {
+            if ((draw >> 2) != block) {
+                block = draw >> 2;
+                const uint32_t ctr[4] = { block, 1u, ilo, ihi };
+                philox_host(ctr, key, w);
+            }
+            const int k = int((uint64_t(w[draw & 3u]) * uint64_t(n_empty)) >> 32);
+            if (!makes_five(cells, empty[k], colour)) slot = k;    // a stone that completes five-or-more is redrawn
+        }
+        if (slot < 0) break;                                        // 64 redraws all completed a five: stop short
+        const int c = empty[slot];
+        cells[c] = (uint8_t)colour;
+        for (int i = slot; i + 1 < n_empty; ++i) empty[i] = empty[i + 1];   // keep increasing cell order
+        --n_empty;
+        if (moves) moves[placed] = (int16_t)c;
+        ++placed;
+    }
+    for (int i = 0; i < 16; ++i) board[i] = 0;
+    for (int c = 0; c < 225; ++c) board[c >> 4] |= uint32_t(cells[c]) << ((c & 15) * 2);
+    *n_moves = placed;
+}
+
+// ---- pipelined host entry points -----------------------------------------------------------------
+struct Pipe {
+    cudaStream_t stream = nullptr;
+    uint32_t* d_boards = nullptr; int32_t* d_scores = nullptr; uint16_t* d_pat = nullptr; uint16_t* d_cmp = nullptr;
+    int8_t* d_win = nullptr; int32_t* d_wdb = nullptr;
+    int cap = 0;
+};
+constexpr int kPipes = 3;
+Pipe g_pipes[kPipes];
+
+gk_status pipe_reserve(Pipe& p, int chunk) {
+    if (!p.stream) GK_CUDA(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    if (p.cap >= chunk) return GK_OK;
+    cudaFree(p.d_boards); cudaFree(p.d_scores); cudaFree(p.d_pat); cudaFree(p.d_cmp); cudaFree(p.d_win); cudaFree(p.d_wdb);
+    p.cap = 0;
+    GK_CUDA(cudaMalloc(&p.d_boards, size_t(chunk) * 64));
+    GK_CUDA(cudaMalloc(&p.d_scores, size_t(chunk) * 3600));
+    GK_CUDA(cudaMalloc(&p.d_pat, size_t(chunk) * 32));
+    GK_CUDA(cudaMalloc(&p.d_cmp, size_t(chunk) * 12));
+    GK_CUDA(cudaMalloc(&p.d_win, size_t(chunk)));
+    GK_CUDA(cudaMalloc(&p.d_wdb, size_t(chunk) * 12));
+    p.cap = chunk;
+    return GK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gk_version(void) { return "gomoku_b200 0.1 (sm_100a)"; }
+const char* gk_last_error(void) { return t_error.c_str(); }
+
+gk_status gk_init(int device) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GK_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+    if (device < 0 || device >= count) return fail(GK_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop{};
+    GK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GK_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100; this library carries sm_100a code only");
+    GK_CUDA(cudaSetDevice(device));
+    g_device = device; g_sm_count = prop.multiProcessorCount; g_cc_major = prop.major; g_cc_minor = prop.minor;
+    return GK_OK;
+}
+
+gk_status gk_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (Pipe& p : g_pipes) {
+        if (p.stream) cudaStreamDestroy(p.stream);
+        cudaFree(p.d_boards); cudaFree(p.d_scores); cudaFree(p.d_pat); cudaFree(p.d_cmp); cudaFree(p.d_win); cudaFree(p.d_wdb);
+        p = Pipe{};
+    }
+    g_device = -1;
+    return GK_OK;
+}
+
+gk_status gk_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor) {
+    if (gk_status s = require_device()) return s;
+    if (device) *device = g_device;
+    if (sm_count) *sm_count = g_sm_count;
+    if (cc_major) *cc_major = g_cc_major;
+    if (cc_minor) *cc_minor = g_cc_minor;
+    return GK_OK;
+}
+
+// ---- tables ------------------------------------------------------------------------------------
+gk_status gk_table_default(gk_table** out) {
+    if (!out) return fail(GK_ERR_INVALID, "out is null");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_default_table) {
+        gk_table* t = new gk_table;
+        if (!gk::compile_table(gk::default_protos(), t->host)) {
+            const std::string msg = t->host.error;
+            delete t;
+            return fail(GK_ERR_TABLE, msg);
+        }
+        t->is_default = true;
+        g_default_table = t;
+    }
+    *out = g_default_table;
+    return GK_OK;
+}
+
+gk_status gk_table_build(const char* const* protos, const int* types, const int* scores, int n, gk_table** out) {
+    if (!protos || !types || !scores || !out || n <= 0) return fail(GK_ERR_INVALID, "bad arguments");
+    std::vector<gk::Proto> v;
+    for (int i = 0; i < n; ++i) {
+        if (!protos[i]) return fail(GK_ERR_INVALID, "null prototype");
+        v.push_back({ protos[i], types[i], scores[i] });
+    }
+    gk_table* t = new gk_table;
+    if (!gk::compile_table(v, t->host)) {
+        const std::string msg = t->host.error;
+        delete t;
+        return fail(GK_ERR_TABLE, msg);
+    }
+    *out = t;
+    return GK_OK;
+}
+
+gk_status gk_table_free(gk_table* t) {
+    if (!t || t->is_default) return GK_OK;
+    cudaFree(t->d_trans); cudaFree(t->d_patrec); cudaFree(t->d_tape); cudaFree(t->d_flush);
+    delete t;
+    return GK_OK;
+}
+
+gk_status gk_table_info(const gk_table* t, int* n_states, int* n_patterns, int* trail_pad, int* max_steps) {
+    if (!t) return fail(GK_ERR_INVALID, "table is null");
+    if (n_states) *n_states = t->host.n_states;
+    if (n_patterns) *n_patterns = (int)t->host.patterns.size();
+    if (trail_pad) *trail_pad = t->host.trail_pad;
+    if (max_steps) *max_steps = t->host.tape_steps;
+    return GK_OK;
+}
+
+gk_status gk_table_pattern(const gk_table* t, int id, char str8[8], int* favour, int* type, int* score) {
+    if (!t || id < 0 || id >= (int)t->host.patterns.size()) return fail(GK_ERR_INVALID, "pattern id out of range");
+    const gk::PatternInfo& p = t->host.patterns[id];
+    if (str8) { std::memset(str8, 0, 8); std::memcpy(str8, p.str.data(), p.str.size()); }
+    if (favour) *favour = p.favour;
+    if (type) *type = p.type;
+    if (score) *score = p.score;
+    return GK_OK;
+}
+
+gk_status gk_table_entries(const gk_table* t, uint32_t* h_entries, int capacity) {
+    if (!t || !h_entries || capacity < (int)t->host.trans.size()) return fail(GK_ERR_INVALID, "buffer too small");
+    std::memcpy(h_entries, t->host.trans.data(), t->host.trans.size() * sizeof(uint32_t));
+    return GK_OK;
+}
+
+gk_status gk_table_flush(const gk_table* t, int16_t* h_flush, int capacity) {
+    if (!t || !h_flush || capacity < (int)t->host.flush.size()) return fail(GK_ERR_INVALID, "buffer too small");
+    std::memcpy(h_flush, t->host.flush.data(), t->host.flush.size() * sizeof(int16_t));
+    return GK_OK;
+}
+
+// ---- scan ----------------------------------------------------------------------------------------
+gk_status gk_scan_batch(const gk_table* t, const uint8_t* d_codes, const int64_t* d_starts, int n_strings,
+                        int max_per_string, int32_t* d_pids, int32_t* d_offsets, int32_t* d_counts, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (!t || !d_codes || !d_starts || !d_pids || !d_offsets || !d_counts || n_strings < 0 || max_per_string <= 0)
+        return fail(GK_ERR_INVALID, "bad arguments");
+    if (gk_status s = ensure_uploaded(t)) return s;
+    gk::ScanArgs a{ t->d_trans, t->d_flush, d_codes, reinterpret_cast<const long long*>(d_starts), n_strings,
+                    max_per_string, d_pids, d_offsets, d_counts };
+    GK_CUDA(gk::launch_scan(a, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
+// ---- eval ----------------------------------------------------------------------------------------
+gk_status gk_eval_batch(const gk_table* t, const uint32_t* d_boards, int n, int32_t* d_scores, uint16_t* d_pat_totals,
+                        uint16_t* d_cmp_totals, int8_t* d_winner, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (!t || n < 0 || (n > 0 && !d_boards)) return fail(GK_ERR_INVALID, "bad arguments");
+    if (reinterpret_cast<uintptr_t>(d_scores) & 15u) return fail(GK_ERR_INVALID, "d_scores must be 16-byte aligned");
+    if (gk_status s = ensure_uploaded(t)) return s;
+    const gk::EvalArgs a = eval_args(t, d_boards, n, d_scores, d_pat_totals, d_cmp_totals, d_winner);
+    GK_CUDA(gk::launch_eval(a, g_sm_count, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
+gk_status gk_eval_batch_host(const gk_table* t, const uint32_t* h_boards, int n, int32_t* h_scores, uint16_t* h_pat,
+                             uint16_t* h_cmp, int8_t* h_win) {
+    if (gk_status s = require_device()) return s;
+    if (!t || n < 0 || (n > 0 && !h_boards)) return fail(GK_ERR_INVALID, "bad arguments");
+    if (gk_status s = ensure_uploaded(t)) return s;
+    // three chunks in flight: copy-in of chunk k+1 and copy-out of chunk k-1 overlap the kernel of chunk k
+    const int chunk = std::min(n, 16384);
+    if (chunk == 0) return GK_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (Pipe& p : g_pipes) if (gk_status s = pipe_reserve(p, chunk)) return s;
+    int k = 0;
+    for (int at = 0; at < n; at += chunk, ++k) {
+        Pipe& p = g_pipes[k % kPipes];
+        const int m = std::min(chunk, n - at);
+        GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
+        const gk::EvalArgs a = eval_args(t, p.d_boards, m, h_scores ? p.d_scores : nullptr, h_pat ? p.d_pat : nullptr,
+                                         h_cmp ? p.d_cmp : nullptr, h_win ? p.d_win : nullptr);
+        GK_CUDA(gk::launch_eval(a, g_sm_count, p.stream));
+        if (h_scores) GK_CUDA(cudaMemcpyAsync(h_scores + size_t(at) * 900, p.d_scores, size_t(m) * 3600, cudaMemcpyDeviceToHost, p.stream));
+        if (h_pat) GK_CUDA(cudaMemcpyAsync(h_pat + size_t(at) * 16, p.d_pat, size_t(m) * 32, cudaMemcpyDeviceToHost, p.stream));
+        if (h_cmp) GK_CUDA(cudaMemcpyAsync(h_cmp + size_t(at) * 6, p.d_cmp, size_t(m) * 12, cudaMemcpyDeviceToHost, p.stream));
+        if (h_win) GK_CUDA(cudaMemcpyAsync(h_win + at, p.d_win, size_t(m), cudaMemcpyDeviceToHost, p.stream));
+    }
+    for (Pipe& p : g_pipes) GK_CUDA(cudaStreamSynchronize(p.stream));
+    return GK_OK;
+}
+
+// ---- rollouts --------------------------------------------------------------------------------------
+static gk_status rollout_common(const uint32_t* d_boards, int n, int rollouts_per_pos, uint64_t key, uint32_t ctr_hi,
+                                int pos_base, const uint8_t* d_r_stream, int stream_stride, int32_t* d_wdb,
+                                int8_t* d_winners, uint8_t* d_lengths, cudaStream_t stream) {
+    if (n < 0 || rollouts_per_pos <= 0 || (n > 0 && !d_boards)) return fail(GK_ERR_INVALID, "bad arguments");
+    if ((unsigned long long)n * (unsigned long long)rollouts_per_pos >= (1ull << 31))
+        return fail(GK_ERR_INVALID, "n * rollouts_per_pos must be below 2^31 per call");
+    gk::RolloutArgs a{};
+    a.boards = d_boards; a.n = n; a.rollouts_per_pos = rollouts_per_pos;
+    a.key_lo = uint32_t(key); a.key_hi = uint32_t(key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos_base;
+    a.r_stream = d_r_stream; a.stream_stride = stream_stride;
+    a.wdb = d_wdb; a.winners = d_winners; a.lengths = d_lengths;
+    GK_CUDA(gk::launch_rollout(a, g_sm_count, stream));
+    return GK_OK;
+}
+
+gk_status gk_rollout_batch(const uint32_t* d_boards, int n, int rollouts_per_pos, uint64_t philox_key, uint32_t ctr_hi,
+                           int pos_base, int32_t* d_wdb, int8_t* d_winners, uint8_t* d_lengths, void* stream) {
+    if (gk_status s = require_device()) return s;
+    return rollout_common(d_boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, d_wdb, d_winners,
+                          d_lengths, static_cast<cudaStream_t>(stream));
+}
+
+gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_pos, const uint8_t* d_r_stream,
+                              int stream_stride, int8_t* d_winners, uint8_t* d_lengths, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (!d_r_stream || stream_stride <= 0 || stream_stride > 254) return fail(GK_ERR_INVALID, "bad injected stream");
+    return rollout_common(d_boards, n, rollouts_per_pos, 0, 0, 0, d_r_stream, stream_stride, nullptr, d_winners,
+                          d_lengths, static_cast<cudaStream_t>(stream));
+}
+
+gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_per_pos, uint64_t philox_key,
+                                uint32_t ctr_hi, int pos_base, int32_t* h_wdb) {
+    if (gk_status s = require_device()) return s;
+    if (n < 0 || (n > 0 && (!h_boards || !h_wdb))) return fail(GK_ERR_INVALID, "bad arguments");
+    if (n == 0) return GK_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    Pipe& p = g_pipes[0];
+    if (gk_status s = pipe_reserve(p, std::max(n, 1))) return s;
+    GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, p.stream));
+    if (gk_status s = rollout_common(p.d_boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, p.d_wdb,
+                                     nullptr, nullptr, p.stream))
+        return s;
+    GK_CUDA(cudaMemcpyAsync(h_wdb, p.d_wdb, size_t(n) * 12, cudaMemcpyDeviceToHost, p.stream));
+    GK_CUDA(cudaStreamSynchronize(p.stream));
+    return GK_OK;
+}
+
+// ---- host utilities ------------------------------------------------------------------------------------
+gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards) {
+    if (!moves || !starts || !h_boards || n < 0) return fail(GK_ERR_INVALID, "bad arguments");
+    for (int p = 0; p < n; ++p) {
+        uint32_t* b = h_boards + size_t(p) * 16;
+        for (int i = 0; i < 16; ++i) b[i] = 0;
+        int k = 0;
+        for (int64_t i = starts[p]; i < starts[p + 1]; ++i, ++k) {
+            const int c = moves[i];
+            if (c < 0 || c >= 225) return fail(GK_ERR_INVALID, "move out of range");
+            if ((b[c >> 4] >> ((c & 15) * 2)) & 3u) return fail(GK_ERR_INVALID, "cell played twice");
+            b[c >> 4] |= uint32_t((k & 1) ? 2 : 1) << ((c & 15) * 2);
+        }
+    }
+    return GK_OK;
+}
+
+gk_status gk_synth_positions(int64_t first, int n, uint32_t* h_boards, int16_t* h_moves, int64_t* h_starts) {
+    if (!h_boards || n < 0 || (h_moves && !h_starts)) return fail(GK_ERR_INVALID, "bad arguments");
+    std::vector<int> counts(n);
+    const int n_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int w = 0; w < n_threads; ++w)
+        pool.emplace_back([=, &counts]() {
+            for (int i = w; i < n; i += n_threads)
+                synth_one(first + i, h_boards + size_t(i) * 16, h_moves ? h_moves + size_t(i) * 96 : nullptr, &counts[i]);
+        });
+    for (std::thread& th : pool) th.join();
+    if (h_moves) {                                                   // compact the 96-wide rows into one list
+        int64_t at = 0;
+        for (int i = 0; i < n; ++i) {
+            h_starts[i] = at;
+            std::memmove(h_moves + at, h_moves + size_t(i) * 96, size_t(counts[i]) * sizeof(int16_t));
+            at += counts[i];
+        }
+        h_starts[n] = at;
+    }
+    return GK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+// gk_kernels.h -- launch interface between the C-ABI layer and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "gk_format.h"
+
+namespace gk {
+
+struct EvalArgs {
+    const uint32_t* trans; int n_states;       // device copies of the compiled table
+    const PatRec* patrec; int n_patterns;
+    const uint32_t* tape; int tape_steps;
+    uint32_t start_state;
+    const uint32_t* boards; long long n;
+    int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
+};
+size_t eval_smem_bytes(const EvalArgs& a);
+cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream);
+
+struct ScanArgs {
+    const uint32_t* trans; const int16_t* flush;
+    const uint8_t* codes; const long long* starts; int n_strings; int max_per_string;
+    int32_t* pids; int32_t* offsets; int32_t* counts;
+};
+cudaError_t launch_scan(const ScanArgs& a, cudaStream_t stream);
+
+struct RolloutArgs {
+    const uint32_t* boards; int n; int rollouts_per_pos;
+    uint32_t key_lo, key_hi, ctr_hi; int pos_base;
+    const uint8_t* r_stream; int stream_stride;     // non-null: injected start indices instead of Philox
+    int32_t* wdb; int8_t* winners; uint8_t* lengths; // any may be null
+};
+cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stream);
+// number of kernels one launch_rollout call enqueues (wdb clear + rollout)
+int rollout_launches(const RolloutArgs& a);
+
+}  // namespace gk

@@ -1,0 +1,328 @@
+// gk_rollout.cu -- K2 `rollout`: batched random playouts, one thread per rollout.
+//
+// Replaces Default::RandomRollout / Simulate (reference include/algorithms/MonteCarlo.hpp:
+// 37-47,83-88), i.e. per move: Board::getRandomMove (src/Game.cpp:64-73: start index r, then
+// the first empty cell at or after r, cyclically), Board::applyMove (:37-47) and
+// Board::checkGameEnd (:88-136: five-or-more through the new stone, else draw when full).
+//
+// State of one rollout = 72 "line slots" of 32 bits in shared memory, laid out
+// [slot][thread] so that every access of a warp is bank-conflict free whatever slots the
+// lanes touch: 15 rows, 15 columns and the 2 x 21 diagonals of length >= 5, each holding the
+// black stones of that line in bits 0..14 and the white stones in bits 16..30.  A stone is
+// therefore stored four times, and the win test of a move is four independent
+// "read slot, or the bit in, store, m & m>>1 & m>>2 & m>>3 & m>>4" sequences in registers.
+// Legal-move selection works on the row slots plus a 15-bit "row still has an empty cell" mask
+// kept in a register: at most two shared-memory probes per move, no loop.
+//
+// Threads are persistent: a finished lane waits for the next refill point (every kRefill
+// steps, a multiple of 4 so that all lanes draw a fresh Philox4x32-10 block on the same steps),
+// takes the next rollout ticket and re-copies the position's 72-word slot image.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gk_format.h"
+#include "gk_kernels.h"
+
+namespace gk {
+
+namespace {
+
+constexpr int kSlots = 72;
+constexpr int kImageWords = 80;          // 72 slots + meta, 320 B per position
+constexpr int kMetaInfo = 72;            // empties | to_move << 8 | decided << 9 | winner code << 10
+constexpr int kMetaRows = 73;            // rows that still have an empty cell
+constexpr int kThreads = 256;            // per CTA: 256 x 72 x 4 B = 72 KiB of slot state, 3 CTAs per SM
+constexpr int kRefill = 8;               // move steps between refill points (multiple of 4)
+constexpr int kTicketBlock = 256;        // consecutive rollouts a CTA claims at a time
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ bool has_five(uint32_t m) {      // five or more consecutive bits
+    uint32_t t = m & (m >> 1);
+    t &= t >> 2;
+    return (t & (m >> 4)) != 0;
+}
+
+// ---- position -> slot image ------------------------------------------------------------------
+// one warp per position; lane l builds slots l, l+32, l+64
+__global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, uint32_t* __restrict__ images) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const uint32_t* b = boards + (size_t)warp * kBoardWords;
+    uint32_t* img = images + (size_t)warp * kImageWords;
+    uint32_t any_five = 0;                                   // bit 0: black, bit 1: white
+    for (int slot = lane; slot < kSlots; slot += 32) {
+        int cell0, stride, len;
+        if (slot < 15) { cell0 = slot * 15; stride = 1; len = 15; }
+        else if (slot < 30) { cell0 = slot - 15; stride = 15; len = 15; }
+        else if (slot < 51) { const int k = slot - 40; cell0 = k > 0 ? k : -k * 15; stride = 16; len = 15 - (k > 0 ? k : -k); }
+        else { const int s = slot - 47; const int x0 = s < 14 ? s : 14; cell0 = (s - x0) * 15 + x0; stride = 14; len = (s < 15 ? s : 28 - s) + 1; }
+        uint32_t w = 0;
+        for (int i = 0; i < len; ++i) {
+            const int c = cell0 + i * stride;
+            const uint32_t v = (__ldg(b + (c >> 4)) >> ((c & 15) * 2)) & 3u;
+            if (v == 1u) w |= 1u << i;
+            else if (v == 2u) w |= 1u << (16 + i);
+        }
+        img[slot] = w;
+        if (has_five(w & 0x7fffu)) any_five |= 1u;
+        if (has_five(w >> 16)) any_five |= 2u;
+    }
+    any_five = __reduce_or_sync(0xffffffffu, any_five);
+    // rows: empties, stone counts
+    uint32_t blk = 0, wht = 0, rowmask = 0;
+    if (lane < 15) {
+        uint32_t w = 0;
+        for (int i = 0; i < 15; ++i) {
+            const int c = lane * 15 + i;
+            const uint32_t v = (__ldg(b + (c >> 4)) >> ((c & 15) * 2)) & 3u;
+            if (v == 1u) { w |= 1u << i; ++blk; }
+            else if (v == 2u) { w |= 1u << i; ++wht; }
+        }
+        if (w != 0x7fffu) rowmask = 1u << lane;
+    }
+    blk = __reduce_add_sync(0xffffffffu, blk);
+    wht = __reduce_add_sync(0xffffffffu, wht);
+    rowmask = __reduce_or_sync(0xffffffffu, rowmask);
+    if (lane == 0) {
+        const uint32_t empties = kCells - blk - wht;
+        const uint32_t to_move = blk == wht ? 0u : 1u;         // black moves first, Game.h:128; Game.cpp:52
+        const uint32_t decided = (any_five || empties == 0) ? 1u : 0u;
+        const uint32_t wcode = (any_five & 1u) ? 1u : (any_five & 2u) ? 2u : 0u;
+        img[kMetaInfo] = empties | to_move << 8 | decided << 9 | wcode << 10;
+        img[kMetaRows] = rowmask;
+    }
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Lane {
+    uint32_t rowmask;      // rows with at least one empty cell
+    uint32_t empties;
+    uint32_t colour;       // 0 black to move, 1 white
+    uint32_t moves;        // moves played in this rollout
+    uint32_t pos, roll;    // position index (batch-local), rollout index within the position
+};
+
+// One move of an active rollout.  Returns 0 = game goes on, 1 = black won, 2 = white won, 3 = draw.
+__device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */, Lane& L, uint32_t r) {
+    uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
+    uint32_t w = my[y * kThreads];
+    uint32_t avail = ~(w | (w >> 16)) & 0x7fffu & (0xffffffffu << x);
+    if (avail == 0) {                                                            // first empty cell after r: next row that has one
+        uint32_t m = L.rowmask & ~((2u << y) - 1u);
+        if (m == 0) m = L.rowmask;
+        y = __ffs(m) - 1;
+        w = my[y * kThreads];
+        avail = ~(w | (w >> 16)) & 0x7fffu;
+    }
+    x = __ffs(avail) - 1;
+    const uint32_t sh = 16u * L.colour;
+    // row
+    w |= 1u << (x + sh);
+    my[y * kThreads] = w;
+    if (((w | (w >> 16)) & 0x7fffu) == 0x7fffu) L.rowmask &= ~(1u << y);
+    bool five = has_five((w >> sh) & 0x7fffu);
+    // column
+    {
+        uint32_t* p = my + (15u + x) * kThreads;
+        const uint32_t v = *p | (1u << (y + sh));
+        *p = v;
+        five = five || has_five((v >> sh) & 0x7fffu);
+    }
+    // diagonal (+1,+1): x - y = k, k in [-10, 10]
+    {
+        const int k = int(x) - int(y) + 10;
+        if (k >= 0 && k <= 20) {
+            uint32_t* p = my + (30 + k) * kThreads;
+            const uint32_t v = *p | (1u << (min(x, y) + sh));
+            *p = v;
+            five = five || has_five((v >> sh) & 0x7fffu);
+        }
+    }
+    // anti-diagonal (-1,+1): x + y = s, s in [4, 24]
+    {
+        const int s = int(x + y) - 4;
+        if (s >= 0 && s <= 20) {
+            uint32_t* p = my + (51 + s) * kThreads;
+            const uint32_t v = *p | (1u << (min(14u - x, y) + sh));
+            *p = v;
+            five = five || has_five((v >> sh) & 0x7fffu);
+        }
+    }
+    L.moves += 1;
+    L.empties -= 1;
+    uint32_t result = 0;
+    if (five) result = 1u + L.colour;                                            // winner = player of the last stone, Game.cpp:125-128
+    else if (L.empties == 0) result = 3u;                                        // Game.cpp:129-132
+    L.colour ^= 1u;
+    return result;
+}
+
+template <bool kInjected>
+__global__ void __launch_bounds__(kThreads, 3)
+rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
+    extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots][kThreads]
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) s_ticket = 0;
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
+    uint32_t* my = s_slots + threadIdx.x;
+    const uint32_t total = uint32_t(a.n) * uint32_t(a.rollouts_per_pos);
+
+    Lane L{};
+    bool active = false, dead = false;
+    uint32_t acc[3] = { 0, 0, 0 };                                               // white / draw / black of position acc_pos
+    uint32_t acc_pos = 0xffffffffu;
+    uint32_t rnd[4] = { 0, 0, 0, 0 };
+    const uint8_t* inj = nullptr;
+
+    auto finish = [&](uint32_t result) {                                         // result: 1 black, 2 white, 3 draw
+        const int win = result == 1u ? 1 : result == 2u ? -1 : 0;
+        const size_t g = size_t(L.pos) * a.rollouts_per_pos + L.roll;
+        if (a.winners) a.winners[g] = (int8_t)win;
+        if (a.lengths) a.lengths[g] = (uint8_t)L.moves;
+        acc[win + 1] += 1;
+        active = false;
+    };
+    auto flush = [&]() {
+        if (a.wdb && acc_pos != 0xffffffffu) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (acc[i]) atomicAdd(a.wdb + size_t(acc_pos) * 3 + i, int(acc[i]));
+        }
+        acc[0] = acc[1] = acc[2] = 0;
+    };
+
+    for (;;) {
+        // ---- refill point --------------------------------------------------------------------------
+        const bool need = !active && !dead;
+        const uint32_t m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == uint32_t(__ffs(m) - 1)) base = atomicAdd(&s_ticket, uint32_t(__popc(m)));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (need) {
+                const uint32_t t = base + __popc(m & lt);
+                const unsigned long long g64 =
+                    ((unsigned long long)(t / kTicketBlock) * gridDim.x + blockIdx.x) * kTicketBlock + t % kTicketBlock;
+                if (g64 >= total) {
+                    dead = true;
+                } else {
+                    const uint32_t g = uint32_t(g64);
+                    L.pos = g / uint32_t(a.rollouts_per_pos);
+                    L.roll = g - L.pos * uint32_t(a.rollouts_per_pos);
+                    if (L.pos != acc_pos) { flush(); acc_pos = L.pos; }
+                    const uint32_t* img = images + size_t(L.pos) * kImageWords;
+                    const uint32_t info = __ldg(img + kMetaInfo);
+                    L.empties = info & 0xffu;
+                    L.colour = (info >> 8) & 1u;
+                    L.rowmask = __ldg(img + kMetaRows);
+                    L.moves = 0;
+                    if ((info >> 9) & 1u) {                                      // already decided: 0 moves
+                        const uint32_t wc = (info >> 10) & 3u;
+                        active = true;
+                        finish(wc ? wc : 3u);
+                    } else {
+#pragma unroll 8
+                        for (int s = 0; s < kSlots; ++s) my[s * kThreads] = __ldg(img + s);
+                        active = true;
+                        if (kInjected) inj = a.r_stream + size_t(g) * a.stream_stride;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0) {
+            if (__ballot_sync(0xffffffffu, !dead) == 0) break;
+            continue;
+        }
+        // ---- kRefill move steps ------------------------------------------------------------------------
+#pragma unroll 1
+        for (int quad = 0; quad < kRefill / 4; ++quad) {
+            if (!kInjected) {
+                if (active)
+                    philox4x32_10(L.moves >> 2, L.roll, uint32_t(a.pos_base) + L.pos, a.ctr_hi, a.key_lo, a.key_hi, rnd);
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (active) {
+                    uint32_t r;
+                    if (kInjected) {
+                        if (int(L.moves) >= a.stream_stride) {                   // stream exhausted: report length 255, winner 0
+                            L.moves = 255;
+                            finish(3u);
+                            continue;
+                        }
+                        r = inj[L.moves];
+                    } else {
+                        r = __umulhi(rnd[s], uint32_t(kCells));
+                    }
+                    const uint32_t result = play_move(my, L, r);
+                    if (result) finish(result);
+                }
+            }
+        }
+    }
+    flush();
+}
+
+uint32_t* g_images = nullptr;
+size_t g_images_cap = 0;
+
+}  // namespace
+
+int rollout_launches(const RolloutArgs& a) { return a.n > 0 ? 2 : 0; }
+
+cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.n <= 0 || a.rollouts_per_pos <= 0) return cudaSuccess;
+    const size_t need = size_t(a.n) * kImageWords * sizeof(uint32_t);
+    cudaError_t err;
+    if (need > g_images_cap) {                                                   // grow-only scratch owned by the library
+        if (g_images) { err = cudaFree(g_images); if (err != cudaSuccess) return err; }
+        g_images = nullptr; g_images_cap = 0;
+        err = cudaMalloc(&g_images, need);
+        if (err != cudaSuccess) return err;
+        g_images_cap = need;
+    }
+    build_images_kernel<<<(a.n * 32 + 255) / 256, 256, 0, stream>>>(a.boards, a.n, g_images);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    if (a.wdb) {
+        err = cudaMemsetAsync(a.wdb, 0, size_t(a.n) * 3 * sizeof(int32_t), stream);
+        if (err != cudaSuccess) return err;
+    }
+    const size_t smem = size_t(kSlots) * kThreads * sizeof(uint32_t);
+    const unsigned long long total = (unsigned long long)a.n * a.rollouts_per_pos;
+    unsigned long long blocks = (total + kTicketBlock - 1) / kTicketBlock;
+    const unsigned long long resident = (unsigned long long)sm_count * 3;
+    const int grid = int(blocks < resident ? blocks : resident);
+    if (a.r_stream) {
+        err = cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        rollout_kernel<true><<<grid, kThreads, smem, stream>>>(a, g_images);
+    } else {
+        err = cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        rollout_kernel<false><<<grid, kThreads, smem, stream>>>(a, g_images);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace gk

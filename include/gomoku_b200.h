@@ -1,0 +1,142 @@
+/* gomoku_b200.h -- C-ABI of the B200-native hot path of Vigilans/GomokuAI.
+ *
+ * One shared library (gomokuai_b200/lib/libgomoku_b200.so, sm_100a only) replaces, for the
+ * batched case, the reference's pattern evaluator and random-rollout simulator.  Every
+ * entry point below names the reference interface it stands in for (paths relative to
+ * /root/reference/core/lib/).  Signatures carry plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns a gk_status (0 = ok, < 0 = error) and never throws; the text
+ *     of the last error on the calling thread is available from gk_last_error();
+ *   - pointers named d_* are DEVICE pointers on the device given to gk_init(); pointers
+ *     named h_* are HOST pointers (pinned memory makes the *_host calls faster, pageable
+ *     memory is accepted); the caller owns every buffer, the library owns gk_table;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device entry
+ *     points only enqueue work; *_host entry points return after the results are in h_*;
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute call fails
+ *     with GK_ERR_NO_DEVICE.
+ *
+ * Data formats
+ *   board      16 x uint32 per position (64 B): cell c = y*15 + x lives in word c/16,
+ *              bits 2*(c%16)..+1; 0 = empty, 1 = black ('x'), 2 = white ('o'); the 62 unused
+ *              high bits of word 14..15 are ignored.  Black moves first and the players
+ *              alternate (include/Game.h:128, src/Game.cpp:37-47), so the side to move is
+ *              black iff #black == #white.
+ *   scores     int32[4][225] per position = Evaluator::m_scores (include/Pattern.h:219),
+ *              group index g = 2*(favour==Black) + (perspective==Black) (Pattern.h:159-161)
+ *   pat_totals uint16[2][8] per position: [0=White,1=Black][Pattern::Type DeadOne..LiveFour]
+ *              = Evaluator::m_patternDist.back()[type].get(player) (Pattern.h:216, Pattern.cpp:413)
+ *   cmp_totals uint16[2][3] per position: [player][DoubleThree,FourThree,DoubleFour]
+ *              = Evaluator::m_compoundDist.back()[type].get(player) (Pattern.h:217)
+ *   winner     int8 per position: +1 black / -1 white has five-or-more in a row (a Five
+ *              emission, Pattern.cpp:140-145), 0 otherwise
+ *   wdb        int32[3] per position: rollouts won by {white, nobody (draw), black}
+ */
+#ifndef GOMOKU_B200_H_
+#define GOMOKU_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int gk_status;
+enum {
+    GK_OK = 0,
+    GK_ERR_INVALID = -1,     /* bad argument */
+    GK_ERR_NO_DEVICE = -2,   /* no sm_100 device / library built without a matching cubin */
+    GK_ERR_CUDA = -3,        /* CUDA runtime error, see gk_last_error() */
+    GK_ERR_TABLE = -4,       /* prototypes cannot be compiled to the flat table */
+    GK_ERR_NOT_INIT = -5,    /* gk_init() has not been called on this process */
+    GK_ERR_NCCL = -6
+};
+
+enum { GK_WIDTH = 15, GK_HEIGHT = 15, GK_CELLS = 225, GK_BOARD_WORDS = 16,
+       GK_SCORE_GROUPS = 4, GK_PATTERN_TYPES = 8, GK_COMPOUND_TYPES = 3 };
+
+typedef struct gk_table gk_table;
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+gk_status gk_init(int device);                      /* binds the process to one GPU (one process per GPU) */
+gk_status gk_shutdown(void);
+const char* gk_last_error(void);
+gk_status gk_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor);
+const char* gk_version(void);
+
+/* ---- pattern automaton --------------------------------------------------------------
+ * Replaces the static `PatternSearch Evaluator::Patterns` (src/Pattern.cpp:554-596) and
+ * AhoCorasickBuilder::build (src/utils/ACAutomata.cpp:15-23).  The prototypes go through the
+ * same reverse / colour-flip / boundary augmentation and ordering, and the resulting goto /
+ * fail / output behaviour (including the emission-on-fail-landing and invariant-run rules
+ * of PatternSearch::generator::operator++, src/Pattern.cpp:33-56) is compiled into one flat
+ * (state, symbol) -> {next, up to 2 emissions} table that lives in shared memory on the GPU. */
+gk_status gk_table_default(gk_table** out);         /* the reference's 41 prototypes; cached, do not free */
+gk_status gk_table_build(const char* const* protos, const int* types, const int* scores, int n,
+                         gk_table** out);           /* protos: "+xxxxx" / "-_oooo_" ... as Pattern.cpp:14-18 */
+gk_status gk_table_free(gk_table* table);
+gk_status gk_table_info(const gk_table* table, int* n_states, int* n_patterns, int* trail_pad, int* max_steps);
+gk_status gk_table_pattern(const gk_table* table, int id, char str8[8], int* favour, int* type, int* score);
+/* flat transition words (n_states*4 uint32, see gk_format.h) -- for inspection and tests */
+gk_status gk_table_entries(const gk_table* table, uint32_t* h_entries, int capacity);
+/* per state: pattern id still owed if the input ends in that state (a run of five-or-more that
+ * reaches the end of the string, Pattern.cpp:40-45,54), else -1; n_states int16 */
+gk_status gk_table_flush(const gk_table* table, int16_t* h_flush, int capacity);
+
+/* PatternSearch::execute / matches (src/Pattern.cpp:64-74) for a batch of symbol strings:
+ * string i = d_codes[d_starts[i] .. d_starts[i+1]) with symbols 1..4 (EncodeCharset,
+ * include/Mapping.h:40-48).  Emissions (pattern id, end offset) of string i are written to
+ * d_pids/d_offsets[i*max_per_string ..]; d_counts[i] receives the number found (which may
+ * exceed max_per_string; only that many are stored). */
+gk_status gk_scan_batch(const gk_table* table, const uint8_t* d_codes, const int64_t* d_starts, int n_strings,
+                        int max_per_string, int32_t* d_pids, int32_t* d_offsets, int32_t* d_counts, void* stream);
+
+/* ---- board evaluation ---------------------------------------------------------------
+ * Replaces, for a batch of positions, Evaluator::syncWithBoard / applyMove (src/Pattern.cpp:
+ * 306-369) followed by reading m_scores, m_patternDist.back(), m_compoundDist.back() and the
+ * winner.  Any output pointer may be NULL.  d_scores must be 16-byte aligned. */
+gk_status gk_eval_batch(const gk_table* table, const uint32_t* d_boards, int n,
+                        int32_t* d_scores, uint16_t* d_pat_totals, uint16_t* d_cmp_totals, int8_t* d_winner,
+                        void* stream);
+gk_status gk_eval_batch_host(const gk_table* table, const uint32_t* h_boards, int n,
+                             int32_t* h_scores, uint16_t* h_pat_totals, uint16_t* h_cmp_totals, int8_t* h_winner);
+
+/* ---- random rollouts ----------------------------------------------------------------
+ * Replaces Default::RandomRollout / Default::Simulate (include/algorithms/MonteCarlo.hpp:
+ * 37-47,83-88) and RandomPolicy::averagedSimulate (include/policies/Random.h:22-35) for
+ * `rollouts_per_pos` independent playouts from each of n positions: every move draws a start
+ * index r in [0,225) and plays the first empty cell at or after r, cyclically
+ * (Board::getRandomMove, src/Game.cpp:64-73); the game ends on five-or-more in a row through
+ * the last stone or on a full board (Board::checkGameEnd, src/Game.cpp:88-136).
+ * A position that is already decided (five on board) or full plays 0 moves.
+ *
+ * Randomness: Philox4x32-10, key = philox_key; move k of rollout j of position (pos_base+i)
+ * uses word (k & 3) of philox(counter = {k >> 2, j, pos_base + i, ctr_hi}); r = mulhi32(word, 225).
+ * Results therefore do not depend on how positions or rollouts are split across GPUs.
+ * d_winners / d_lengths (nullable) receive per-rollout outcome (+1/-1/0) and move count. */
+gk_status gk_rollout_batch(const uint32_t* d_boards, int n, int rollouts_per_pos,
+                           uint64_t philox_key, uint32_t ctr_hi, int pos_base,
+                           int32_t* d_wdb, int8_t* d_winners, uint8_t* d_lengths, void* stream);
+gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_per_pos,
+                                uint64_t philox_key, uint32_t ctr_hi, int pos_base, int32_t* h_wdb);
+/* Same loop, but move k of rollout j of position i takes r = d_r_stream[(i*rollouts_per_pos + j)
+ * * stream_stride + k] (values 0..224) -- the injected-stream protocol used to compare bit-exactly
+ * with the reference's Board on any external stream (e.g. its own mt19937 draws).  A rollout
+ * that needs more than stream_stride draws reports length 255 and winner 0. */
+gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_pos,
+                              const uint8_t* d_r_stream, int stream_stride,
+                              int8_t* d_winners, uint8_t* d_lengths, void* stream);
+
+/* ---- host utilities (no GPU needed) ------------------------------------------------- */
+/* move lists (black first, alternating; position i = moves[starts[i]..starts[i+1])) -> packed boards */
+gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards);
+/* The synthetic "random mid-game" set of BASELINE.json / SURVEY.md section 8(d): position
+ * (first + i) has 16 + (h mod 81) stones, black first, alternating, each on a uniformly random
+ * empty cell, a stone that would complete five-or-more is redrawn; Philox4x32-10 keyed
+ * 0x474F4D4F4B5531.  Writes packed boards and (optionally) the move lists: h_moves must hold
+ * 96*n entries, h_starts n+1. */
+gk_status gk_synth_positions(int64_t first, int n, uint32_t* h_boards, int16_t* h_moves, int64_t* h_starts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOMOKU_B200_H_ */
