@@ -1,0 +1,142 @@
+"""K2 `rollout` through the C-ABI against the oracle: bit-exact winner and length under injected
+start-index streams; statistical agreement with the reference's own RNG path.  Needs a B200."""
+import numpy as np
+import pytest
+
+from conftest import random_positions
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def test_philox_stream_bit_exact(gpu, port):
+    import torch
+    n, R = 256, 64
+    boards, moves, starts = gpu.synth_positions(0, n)
+    wn, ln, wdb = port.rollout_philox_batch(moves, starts, R, gpu.SYNTH_KEY)
+    r = gpu.rollout_batch(boards, R, want_trace=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(_np(r["winners"]), wn)
+    assert np.array_equal(_np(r["lengths"]), ln)
+    assert np.array_equal(_np(r["wdb"]), wdb)
+    assert 30 < ln.mean() < 80
+
+
+def test_philox_stream_other_key_ctr_and_base(gpu, port):
+    import torch
+    boards, moves, starts = gpu.synth_positions(1000, 40)
+    wn, ln, wdb = port.rollout_philox_batch(moves, starts, 33, 0x1234567890ABCDEF, ctr_hi=7, pos_base=500)
+    r = gpu.rollout_batch(boards, 33, key=0x1234567890ABCDEF, ctr_hi=7, pos_base=500, want_trace=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(_np(r["winners"]), wn) and np.array_equal(_np(r["lengths"]), ln)
+    assert np.array_equal(_np(r["wdb"]), wdb)
+
+
+def test_committed_reference_outcomes(gpu, ref_outputs):
+    import torch
+    g = ref_outputs["rollout_philox"]
+    for case in g["cases"]:
+        mv = ref_outputs["eval"][case["name"]]["moves"]
+        m, st = po.pack_moves([mv])
+        r = gpu.rollout_batch(gpu.pack_moves(m, st), 16, key=g["key"], ctr_hi=g["ctr_hi"], pos_base=case["position_index"], want_trace=True)
+        torch.cuda.synchronize()
+        assert _np(r["winners"])[0].tolist() == [o[0] for o in case["outcomes"]], case["name"]
+        assert _np(r["lengths"])[0].tolist() == [o[1] for o in case["outcomes"]], case["name"]
+    for ex in ref_outputs["rollout_explicit"]:
+        m, st = po.pack_moves([ex["moves"]])
+        r = gpu.rollout_injected(gpu.pack_moves(m, st), np.array(ex["r"], np.uint8).reshape(1, 1, -1))
+        torch.cuda.synchronize()
+        assert int(_np(r["winners"])[0, 0]) == ex["winner"] and int(_np(r["lengths"])[0, 0]) == ex["length"]
+
+
+def test_explicit_injected_streams_bit_exact(gpu, port):
+    import torch
+    rng = np.random.default_rng(4)
+    lists = random_positions(31, 96, lo=0, hi=100)
+    lists = [l for l in lists if port.board_play(l)["cur_player"] != 0][:64]
+    mv, st = po.pack_moves(lists)
+    R, stride = 8, 230
+    rs = rng.integers(0, 225, size=(len(lists), R, stride)).astype(np.uint8)
+    rs[:, 0, :] = 224                                   # always wraps around the end of the board
+    rs[:, 1, :] = 0
+    r = gpu.rollout_injected(gpu.pack_moves(mv, st), rs)
+    torch.cuda.synchronize()
+    for i, l in enumerate(lists):
+        for j in range(R):
+            w, k = port.rollout_injected(l, rs[i, j])
+            assert (int(_np(r["winners"])[i, j]), int(_np(r["lengths"])[i, j])) == (w, k), (i, j)
+
+
+def test_edge_positions(gpu, port, kats):
+    import torch
+    tie = [y * 15 + x for y in kats["tie_row_order"] for x in range(15)]
+    lists = [
+        [],                                                   # empty board: ~100 moves
+        tie[:-1],                                             # one empty cell: exactly one move
+        tie[:-2], tie[:-7],
+        tie,                                                  # full: 0 moves, draw
+        [y * 15 + x for x, y in kats["black_win"]],           # decided: 0 moves
+        [y * 15 + x for x, y in kats["white_win"]],
+    ]
+    mv, st = po.pack_moves(lists)
+    wn, ln, wdb = port.rollout_philox_batch(mv, st, 40, 99)
+    r = gpu.rollout_batch(gpu.pack_moves(mv, st), 40, key=99, want_trace=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(_np(r["winners"]), wn) and np.array_equal(_np(r["lengths"]), ln)
+    assert np.array_equal(_np(r["wdb"]), wdb)
+    assert (ln[4] == 0).all() and (wn[4] == 0).all() and (wn[5] == 1).all() and (wn[6] == -1).all() and (ln[5] == 0).all()
+    assert (ln[1] == 1).all()
+
+
+def test_stream_exhaustion_is_reported(gpu):
+    import torch
+    rs = np.zeros((1, 2, 4), np.uint8)
+    r = gpu.rollout_injected(np.zeros((1, 16), np.uint32), rs)
+    torch.cuda.synchronize()
+    assert _np(r["lengths"]).tolist() == [[255, 255]] and _np(r["winners"]).tolist() == [[0, 0]]
+
+
+def test_full_size_properties_16m_rollouts(gpu, port):
+    """BASELINE config 3 size: 4096 positions x 4096 rollouts."""
+    import torch
+    n, R = 4096, 4096
+    boards, moves, starts = gpu.synth_positions(0, n)
+    bt = torch.from_numpy(boards.view(np.int32)).cuda()
+    a = gpu.rollout_batch(bt, R)["wdb"]
+    torch.cuda.synchronize()
+    assert torch.equal(a.sum(dim=1), torch.full((n,), R, dtype=torch.int64, device=a.device))   # every rollout counted once
+    b = gpu.rollout_batch(bt, R)["wdb"]                                                          # deterministic
+    # partition invariance: positions split across "ranks" with pos_base, as the multi-GPU path does
+    c0 = gpu.rollout_batch(bt[:1000], R, pos_base=0)["wdb"]
+    c1 = gpu.rollout_batch(bt[1000:], R, pos_base=1000)["wdb"]
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a[:1000], c0) and torch.equal(a[1000:], c1)
+    # sampled bit-exact check of whole positions against the oracle
+    sub = [5, 1234, 4095]
+    mv, st = po.pack_moves([moves[starts[i]:starts[i + 1]] for i in sub])
+    for k, i in enumerate(sub):
+        _, _, wdb = port.rollout_philox_batch(mv[st[k]:st[k + 1]], np.array([0, st[k + 1] - st[k]]), R, gpu.SYNTH_KEY, pos_base=i)
+        assert _np(a[i]).tolist() == wdb[0].tolist()
+
+
+def test_win_rates_match_reference_rng_path(gpu, ref):
+    """Free-running agreement with the reference's own mt19937 path (Board::getRandomMove):
+    |p_gpu - p_cpu| <= 4.5 * sqrt(p(1-p)(1/n_g + 1/n_c)) per position."""
+    import torch
+    n, n_c, n_g = 48, 4096, 16384
+    boards, moves, starts = gpu.synth_positions(9000, n)
+    g = _np(gpu.rollout_batch(boards, n_g, key=2024)["wdb"]).astype(np.float64)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for i in range(n):
+        wdb, total = ref.rollout_free(moves[starts[i]:starts[i + 1]], n_c)
+        pg, pc = g[i, 2] / n_g, wdb[2] / n_c
+        p = (g[i, 2] + wdb[2]) / (n_g + n_c)
+        tol = 4.5 * np.sqrt(max(p * (1 - p), 1e-4) * (1 / n_g + 1 / n_c))
+        worst = max(worst, abs(pg - pc) / tol)
+        assert abs(pg - pc) <= tol, (i, pg, pc, tol)
+    assert worst > 0.0
