@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (board evals/s and rollouts/s on 15x15).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one pass of the hot path over one batch of synthetic random mid-game positions
+(SURVEY.md 8d): the primary line is BASELINE.json configs[1], K1 `ac_eval` over 1,048,576
+positions per GPU; the `rollouts` object of the same line is configs[2], K2 `rollout`,
+4096 positions x 4096 playouts per GPU.  Ranks take disjoint position ranges and exchange nothing
+on the data path (weak scaling).  Prints ONE JSON line on rank 0.
+
+--impl reference times the reference's own CPU implementation of the same two paths
+(oracle/_ref = the reference's sources compiled unmodified, else the C restatement) on all host
+cores, one process per core, each step a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EVAL_POSITIONS = 1 << 20          # configs[1]
+ROLL_POSITIONS = 4096             # configs[2]
+ROLL_PER_POS = 4096
+EVAL_BYTES_IN, EVAL_BYTES_OUT = 64, 3648       # algorithmic bytes per board
+EVAL_STEPS_ALGO = 1076                          # automaton symbol-steps per board
+FALLBACK_HBM_GBS = 6650.0                       # B200_PROFILING.md, used only without MEASURED_PEAKS.json
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed regions
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None and self._thread is None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation, one process per core
+# ------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, what, moves, starts, extra = args
+    from oracle import pyoracle
+    orc = pyoracle.ref() if kind == "reference" else pyoracle.port()
+    t0 = time.perf_counter()
+    if what == "eval":
+        r = orc.eval_batch(moves, starts, want_scores=False)        # Evaluator::applyMove replay, the reference's algorithm
+        assert r["bad"] == 0
+        units = len(starts) - 1
+    else:
+        units = 0
+        n_roll = extra
+        for i in range(len(starts) - 1):
+            mv = moves[starts[i]:starts[i + 1]]
+            if kind == "reference":
+                orc.rollout_free(mv, n_roll)                          # Board::getRandomMove with its own mt19937
+            else:
+                m, s = pyoracle.pack_moves([mv])
+                orc.rollout_philox_batch(m, s, n_roll, 1, 0, i)
+            units += n_roll
+    return units, time.perf_counter() - t0
+
+
+class CpuArm:
+    def __init__(self):
+        from oracle import pyoracle
+        if pyoracle.ref() is not None:
+            self.kind = "reference"
+        else:
+            pyoracle.port()
+            self.kind = "port"
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.pool = mp.get_context("fork").Pool(self.cores)
+
+    def _slices(self, moves, starts, n):
+        per = (n + self.cores - 1) // self.cores
+        out = []
+        for c in range(self.cores):
+            lo, hi = c * per, min(n, (c + 1) * per)
+            if lo >= hi:
+                break
+            st = starts[lo:hi + 1] - starts[lo]
+            out.append((moves[starts[lo]:starts[hi]], st))
+        return out
+
+    def run(self, what, moves, starts, n, extra=None):
+        """units/s over all cores for one bounded sample (wall clock over the whole pool)."""
+        jobs = [(self.kind, what, m, s, extra) for m, s in self._slices(moves, starts, n)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+        return sum(u for u, _ in res) / wall, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    import gomokuai_b200 as gk                                          # host-only use: the synthetic position generator
+    arm = CpuArm()
+    n_eval = 384 * arm.cores                                             # ~0.25 s of evaluator replay per core and step
+    n_roll_pos, n_roll = 2 * arm.cores, 16384                            # ~0.15 s of rollouts per core and step
+    _, moves, starts = gk.synth_positions(0, max(n_eval, n_roll_pos))
+    ev, ro = [], []
+    for i in range(args.warmup + args.steps):
+        a, _ = arm.run("eval", moves, starts, n_eval)
+        b, _ = arm.run("rollout", moves, starts, n_roll_pos, n_roll)
+        if i >= args.warmup:
+            ev.append(a)
+            ro.append(b)
+    arm.close()
+    value, rvalue = statistics.mean(ev), statistics.mean(ro)
+    sample = f"{n_eval} positions/step replayed through Evaluator::applyMove; {n_roll_pos}x{n_roll} rollouts/step"
+    line = {
+        "impl": "reference", "metric": "board evals/sec (15x15)", "value": value, "unit": "boards/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_eval / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "configs[1]: AC pattern evaluation of synthetic random mid-game 15x15 positions, "
+                               "bounded CPU sample per step", "positions_per_step": n_eval},
+        "cpu_baseline": {"value": value, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": value, "unit": "boards/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "rollouts": {"metric": "rollouts/sec (15x15)", "value": rvalue, "unit": "rollouts/s",
+                     "cpu_baseline": {"value": rvalue, "unit": "rollouts/s", "cores": arm.cores, "kind": arm.kind,
+                                      "sample": f"{n_roll_pos} positions x {n_roll} rollouts per step"},
+                     "e2e": {"value": rvalue, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu summary, if one exists (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import gomokuai_b200 as gk
+
+    arm = CpuArm() if (rank == 0 and world == 1 and not args.no_cpu) else None   # fork the workers before CUDA exists
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    gk.init(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.current_stream()
+    table = gk.default_table()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: each rank owns a disjoint range of the synthetic position set -------------------------
+    n_eval, n_roll = EVAL_POSITIONS, ROLL_POSITIONS
+    h_boards, moves, starts = gk.synth_positions(rank * n_eval, n_eval, want_moves=(rank == 0))
+    d_boards = torch.from_numpy(h_boards.view(np.int32)).to(dev)
+    d_roll = d_boards[:n_roll].contiguous()
+    out = gk.eval_batch(d_boards, table)                               # allocates outputs once
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    sampler = ClockSampler(local_rank)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        sampler.start()
+        for a, b in evs:
+            flush_buf.fill_(1)                                          # L2 flush between timed iterations (untimed)
+            a.record(stream)
+            fn()
+            b.record(stream)
+        barrier()
+        sampler.stop()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)                # max over ranks
+        return float(total.item()) / steps, ms
+
+    # ---- K1: resident inputs ---------------------------------------------------------------------------------
+    eval_ms, eval_each = timed(lambda: gk.eval_batch(d_boards, table, out=out), args.steps, args.warmup)
+    # ---- K2: resident inputs ---------------------------------------------------------------------------------
+    roll_out = {}
+
+    def roll_step():
+        roll_out["r"] = gk.rollout_batch(d_roll, ROLL_PER_POS, pos_base=rank * n_roll)
+    roll_ms, _ = timed(roll_step, args.steps, args.warmup)
+    wdb = roll_out["r"]["wdb"]
+    assert bool((wdb.sum(dim=1) == ROLL_PER_POS).all()), "rollout counts do not add up"
+    mean_len = None
+    if rank == 0:
+        tr = gk.rollout_batch(d_roll[:256], 256, pos_base=0, want_trace=True)
+        torch.cuda.synchronize()
+        mean_len = float(tr["lengths"].float().mean().item())
+
+    # ---- e2e: HOST buffers through the C-ABI, copies inside the timed region ---------------------------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    h_pinned = torch.from_numpy(h_boards.view(np.int32)).pin_memory()
+    h_out = {
+        "scores": torch.empty((n_eval, 4, 225), dtype=torch.int32).pin_memory(),
+        "pat_totals": torch.empty((n_eval, 2, 8), dtype=torch.int16).pin_memory(),
+        "cmp_totals": torch.empty((n_eval, 2, 3), dtype=torch.int16).pin_memory(),
+        "winner": torch.empty((n_eval,), dtype=torch.int8).pin_memory(),
+    }
+    h_wdb = torch.empty((n_roll, 3), dtype=torch.int32).pin_memory()
+
+    def wall(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(dt.item()) / steps
+
+    e2e_eval_s = wall(lambda: gk.eval_batch_host(h_pinned, table, out=h_out), e2e_steps, 1)
+    e2e_roll_s = wall(lambda: gk.rollout_batch_host(h_pinned[:n_roll], ROLL_PER_POS, pos_base=rank * n_roll, out=h_wdb),
+                      e2e_steps, 1)
+    if rank == 0:                                                       # the e2e result is the same data as the device path
+        assert torch.equal(h_out["scores"][:4096], out["scores"][:4096].cpu())
+        assert torch.equal(h_wdb, wdb.cpu())
+
+    clocks = sampler.summary()
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload --------------------------------------
+    cpu_eval = cpu_roll = None
+    if arm is not None:
+        n_c = 1024 * arm.cores
+        v, w = arm.run("eval", moves, starts, n_c)
+        cpu_eval = {"value": v, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind,
+                    "sample": f"first {n_c} of the {n_eval} positions, replayed through Evaluator::applyMove, {w:.1f} s wall"}
+        n_p = 4 * arm.cores
+        v, w = arm.run("rollout", moves, starts, n_p, 32768)
+        cpu_roll = {"value": v, "unit": "rollouts/s", "cores": arm.cores, "kind": arm.kind,
+                    "sample": f"first {n_p} positions x 32768 rollouts, {w:.1f} s wall"}
+        arm.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    eval_value = world * n_eval / (eval_ms * 1e-3)
+    roll_value = world * n_roll * ROLL_PER_POS / (roll_ms * 1e-3)
+    eval_gbs = n_eval * (EVAL_BYTES_IN + EVAL_BYTES_OUT) / (eval_ms * 1e-3) / 1e9
+    line = {
+        "metric": "board evals/sec (15x15)", "value": eval_value, "unit": "boards/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": eval_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batched AC pattern evaluation of 1,048,576 synthetic random mid-game 15x15 "
+                               "positions per GPU, bit-exact scores", "positions_per_gpu": n_eval,
+                   "outputs": "int32 scores[4][225] + u16 totals[2][8] + u16 compounds[2][3] + winner per position",
+                   "l2": "256 MB write between timed iterations; each step also streams 3.9 GB, > L2",
+                   "line_scans_per_sec": eval_value * 72},
+        "clocks": clocks,
+        "e2e": {"value": world * n_eval / e2e_eval_s, "unit": "boards/s", "h2d_bytes_per_step": n_eval * 64,
+                "d2h_bytes_per_step": n_eval * (3600 + 32 + 12 + 1), "ms_per_step": e2e_eval_s * 1e3,
+                "note": "gk_eval_batch_host: pinned host buffers, 3 chunks in flight; the 3.8 GB result copy is PCIe-bound"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": eval_gbs, "peak": peak, "unit": "GB/s", "frac": eval_gbs / peak,
+                     "traffic": ncu_traffic("ac_eval_kernel"), "kernel": "ac_eval_kernel", "peak_source": peak_src,
+                     "algorithmic_bytes_per_board": EVAL_BYTES_IN + EVAL_BYTES_OUT,
+                     "symbol_steps_per_sec": eval_value / world * EVAL_STEPS_ALGO,
+                     "note": "the kernel is integer-issue / shared-memory-latency bound, not HBM bound (SURVEY 8d)"},
+        "cpu_baseline": cpu_eval,
+        "rollouts": {
+            "metric": "rollouts/sec (15x15)", "value": roll_value, "unit": "rollouts/s", "ms_per_step": roll_ms,
+            "config": {"workload": "configs[2]: 4096 positions x 4096 random playouts per GPU (16,777,216 rollouts)",
+                       "mean_rollout_length_moves": mean_len},
+            "moves_per_sec": roll_value * mean_len if mean_len else None,
+            "e2e": {"value": world * n_roll * ROLL_PER_POS / e2e_roll_s, "unit": "rollouts/s",
+                    "h2d_bytes_per_step": n_roll * 64, "d2h_bytes_per_step": n_roll * 12, "ms_per_step": e2e_roll_s * 1e3},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": n_roll * (64 + 12) / (roll_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": n_roll * (64 + 12) / (roll_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("rollout_kernel"),
+                         "kernel": "rollout_kernel",
+                         "note": "compute-bound by construction: 76 algorithmic bytes per position, amortised over 4096 playouts"},
+            "cpu_baseline": cpu_roll,
+        },
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
