@@ -15,9 +15,11 @@
 
 struct gk_table {
     gk::HostTable host;
-    uint32_t* d_trans = nullptr;
+    uint32_t* d_trans = nullptr;       // host-format words (scan kernel)
+    uint32_t* d_dev_trans = nullptr;   // device-format words (eval kernel)
     gk::PatRec* d_patrec = nullptr;
-    uint32_t* d_tape = nullptr;
+    uint16_t* d_tape_src = nullptr;
+    uint16_t* d_tape_info = nullptr;
     int16_t* d_flush = nullptr;
     bool is_default = false;
 };
@@ -44,17 +46,21 @@ gk_status require_device() {
     return GK_OK;
 }
 
+template <class T>
+gk_status to_device(T** dst, const std::vector<T>& src) {
+    GK_CUDA(cudaMalloc(dst, src.size() * sizeof(T)));
+    GK_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return GK_OK;
+}
+
 gk_status upload(gk_table* t) {
     const gk::HostTable& h = t->host;
-    GK_CUDA(cudaMalloc(&t->d_trans, h.trans.size() * sizeof(uint32_t)));
-    GK_CUDA(cudaMalloc(&t->d_patrec, h.patrec.size() * sizeof(gk::PatRec)));
-    GK_CUDA(cudaMalloc(&t->d_tape, h.tape.size() * sizeof(uint32_t)));
-    GK_CUDA(cudaMalloc(&t->d_flush, h.flush.size() * sizeof(int16_t)));
-    GK_CUDA(cudaMemcpy(t->d_trans, h.trans.data(), h.trans.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    GK_CUDA(cudaMemcpy(t->d_patrec, h.patrec.data(), h.patrec.size() * sizeof(gk::PatRec), cudaMemcpyHostToDevice));
-    GK_CUDA(cudaMemcpy(t->d_tape, h.tape.data(), h.tape.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    GK_CUDA(cudaMemcpy(t->d_flush, h.flush.data(), h.flush.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
-    return GK_OK;
+    if (gk_status s = to_device(&t->d_dev_trans, h.dev_trans)) return s;
+    if (gk_status s = to_device(&t->d_patrec, h.patrec)) return s;
+    if (gk_status s = to_device(&t->d_tape_src, h.tape_src)) return s;
+    if (gk_status s = to_device(&t->d_tape_info, h.tape_info)) return s;
+    if (gk_status s = to_device(&t->d_flush, h.flush)) return s;
+    return to_device(&t->d_trans, h.trans);    // last: its presence marks the table as uploaded
 }
 
 // device copies are created lazily so that tables can be compiled and inspected without a GPU
@@ -68,9 +74,9 @@ gk_status ensure_uploaded(const gk_table* ct) {
 gk::EvalArgs eval_args(const gk_table* t, const uint32_t* boards, long long n, int32_t* scores, uint16_t* pat,
                        uint16_t* cmp, int8_t* winner) {
     gk::EvalArgs a{};
-    a.trans = t->d_trans; a.n_states = t->host.n_states;
+    a.trans = t->d_dev_trans; a.n_states = t->host.n_states;
     a.patrec = t->d_patrec; a.n_patterns = (int)t->host.patrec.size();
-    a.tape = t->d_tape; a.tape_steps = t->host.tape_steps;
+    a.tape_src = t->d_tape_src; a.tape_info = t->d_tape_info; a.tape_steps = t->host.tape_steps;
     a.start_state = (uint32_t)t->host.start_state;
     a.boards = boards; a.n = n;
     a.scores = scores; a.pat_totals = pat; a.cmp_totals = cmp; a.winner = winner;
@@ -247,7 +253,8 @@ gk_status gk_table_build(const char* const* protos, const int* types, const int*
 
 gk_status gk_table_free(gk_table* t) {
     if (!t || t->is_default) return GK_OK;
-    cudaFree(t->d_trans); cudaFree(t->d_patrec); cudaFree(t->d_tape); cudaFree(t->d_flush);
+    cudaFree(t->d_trans); cudaFree(t->d_dev_trans); cudaFree(t->d_patrec); cudaFree(t->d_tape_src);
+    cudaFree(t->d_tape_info); cudaFree(t->d_flush);
     delete t;
     return GK_OK;
 }

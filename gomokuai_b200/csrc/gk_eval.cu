@@ -7,11 +7,12 @@
 //   phase 1  stone-density block score (+160 where a player has a stone on a weighted offset of
 //            the 7x7 neighbourhood, Pattern.cpp:236-272,598-609) from 15-bit row masks
 //   phase 2  the Aho-Corasick scan: 32 lanes walk their chains of whole lines in lock step, one
-//            dependent shared-memory table lookup per symbol; emissions are compacted with
-//            ballot/popc into a shared queue
+//            dependent shared-memory table lookup per symbol; emitting (lane, step) pairs are
+//            compacted with ballot/popc into a shared queue
 //   phase 3  emission scatter: lanes take queue entries, add pattern scores to the '_' / '^' cells
 //            (shared-memory atomics), bump totals, set the saturating per-cell flags
-//   phase 4  compounds (double-three / four-three / double-four, Pattern.cpp:418-550) from the flags
+//   phase 4  compounds (double-three / four-three / double-four, Pattern.cpp:418-550) from the flags;
+//            the 13-symbol window rescans of Compound::updateAntis are spread one per lane
 //   phase 5  coalesced 128-bit store of the four 225-cell score maps + totals + winner
 //
 // Bound by integer issue and shared-memory latency, not HBM (64 B in, 3.6 KB out per board).
@@ -27,12 +28,12 @@ namespace gk {
 namespace {
 
 constexpr int kWarpsPerCta = 32;
-constexpr int kQueueCap = 256;                 // words; also reused as the compound list (u16 x 450)
-constexpr int kQueueFlush = kQueueCap - 64;    // one step can add at most 2 x 32 entries
+constexpr int kQueueCap = 256;                 // words; reused as the compound list (u16 x 450)
+constexpr int kQueueFlush = kQueueCap - 32;    // one step adds at most one entry per lane
 constexpr int kScoreWords = 4 * kCells;        // 900
 constexpr int kFlagWords = 2 * kCells + 2;     // 452 (16-byte multiple)
 constexpr int kBoardSmem = 20;                 // 17 words used (cells up to 271 read as pad)
-constexpr int kTotalWords = 24;                // 16 pattern + 6 compound + winner + spare
+constexpr int kTotalWords = 24;                // 16 pattern + 6 compound + spare
 
 struct WarpSmem {
     int scores[kScoreWords];                   // [group][cell]
@@ -49,6 +50,22 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+// 32-bit shared-window addressing for the scan loop (keeps the generic->shared conversion out of it)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t cell_value(const uint32_t* board, uint32_t cell) {
     return (board[cell >> 4] >> ((cell & 15u) * 2u)) & 3u;
 }
@@ -63,38 +80,45 @@ __device__ __forceinline__ uint32_t squeeze_even(uint32_t x) {
     return x;
 }
 
-// phase 3: apply queue[0 .. n) to the accumulators.  Returns winner bits (1 black, 2 white).
-__device__ __forceinline__ uint32_t scatter_emissions(WarpSmem& ws, const PatRec* s_patrec, int n, int lane) {
+// One emission of pattern `rec` whose last char sits on virtual cell `vend` of a line with the
+// given direction (Updater::updatePatterns, Pattern.cpp:138-165).  Returns winner bits.
+__device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, const PatRec rec, int vend, uint32_t dir) {
+    const uint32_t type = pr_type(rec.w0), black = pr_black(rec.w0);
+    if (type == kTypeFive) return black ? 1u : 2u;                              // :140-145
+    atomicAdd(&ws.totals[black * 8 + type], 1u);                                // :147
+    const int score = dir >= 2 ? int(rec.w1 >> 16) : int(rec.w1 & 0xffffu);     // :151-152
+    const int stride = dir_stride(dir);
+    int* self = ws.scores + black * 3 * kCells;                                 // Group(f, f)
+    int* rival = ws.scores + (black + 1) * kCells;                              // Group(f, -f)
+    const uint32_t cclass = pr_cclass(rec.w0);
+    const uint32_t lo = 1u << (cclass * 8 - 8 + dir * 2);                       // only used when cclass != 0
+    uint32_t cells = rec.w0;
+    for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) {
+        const int cell = vend - int(cells & 7u) * stride;
+        atomicAdd(&rival[cell], score);                                         // '_' and '^', :158-161
+        if (cells & 8u) {
+            atomicAdd(&self[cell], score);
+            if (cclass) {                                                       // Record::set: 00 -> 01 -> 11, :395-400
+                uint32_t* word = &ws.flags[cell * 2 + black];
+                if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
+            }
+        }
+    }
+    return 0;
+}
+
+// phase 3: apply queue[0 .. n) to the accumulators.
+__device__ __noinline__ uint32_t scatter_emissions(WarpSmem& ws, const PatRec* s_patrec, const uint16_t* s_info,
+                                                   int n, int lane) {
     uint32_t win = 0;
     for (int i = lane; i < n; i += 32) {
         const uint32_t ent = ws.queue[i];
-        const PatRec rec = s_patrec[ent & 0x1ffu];
-        const int vend = (ent >> 9) & 0x1ff;
-        const uint32_t dir = (ent >> 18) & 3u;
-        const uint32_t type = pr_type(rec.w0), black = pr_black(rec.w0);
-        if (type == kTypeFive) { win |= black ? 1u : 2u; continue; }          // Pattern.cpp:140-145
-        atomicAdd(&ws.totals[black * 8 + type], 1u);                          // :147
-        const int score = dir >= 2 ? int(rec.w1 >> 16) : int(rec.w1 & 0xffffu);   // :151-152
-        const int stride = dir_stride(dir);
-        int* self = ws.scores + black * 3 * kCells;                          // Group(f, f)
-        int* rival = ws.scores + (black + 1) * kCells;                       // Group(f, -f)
-        const uint32_t cclass = pr_cclass(rec.w0);
-        uint32_t kinds = pr_kinds(rec.w0);
-        while (kinds) {
-            const int j = (__ffs(kinds) - 1) >> 1;
-            const uint32_t kind = (kinds >> (2 * j)) & 3u;
-            kinds &= ~(3u << (2 * j));
-            const int cell = vend - j * stride;
-            atomicAdd(&rival[cell], score);                                  // '_' and '^', :158-161
-            if (kind == 1u) {
-                atomicAdd(&self[cell], score);
-                if (cclass) {                                                // Record::set saturating 00 -> 01 -> 11, :395-400
-                    uint32_t* word = &ws.flags[cell * 2 + black];
-                    const uint32_t lo = 1u << ((cclass - 1) * 8 + dir * 2);
-                    if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
-                }
-            }
-        }
+        const uint32_t inf = s_info[(ent >> 2) & 0x7ffu];                       // index = step * 32 + lane
+        const uint32_t dir = inf >> 9;
+        const int vcell = inf & 0x1ff, stride = dir_stride(dir);
+        win |= apply_emission(ws, s_patrec[dw_pid(ent, 0)], vcell - int(dw_prev(ent, 0)) * stride, dir);
+        const uint32_t p1 = dw_pid(ent, 1);
+        if (p1 != kDevNoPid) win |= apply_emission(ws, s_patrec[p1], vcell - int(dw_prev(ent, 1)) * stride, dir);
     }
     return win;
 }
@@ -105,72 +129,84 @@ __device__ __forceinline__ uint32_t scatter_emissions(WarpSmem& ws, const PatRec
 __device__ __forceinline__ void anti_cells(WarpSmem& ws, const uint32_t* s_trans, const PatRec* s_patrec,
                                            int cell, uint32_t dir, uint32_t cclass, int* rival) {
     const int cx = cell % kWidth, cy = cell / kWidth;
-    const int dx = dir == 1 ? 0 : dir == 3 ? -1 : 1, dy = dir == 0 ? 0 : 1;
     const int stride = dir_stride(dir);
-    uint32_t st = 0;
+    // steps i in [lo, hi] of the window are on the board, the rest reads as '?'
+    int before, after;                                                          // cells available towards -/+ along the line
+    if (dir == 0) { before = cx; after = kWidth - 1 - cx; }
+    else if (dir == 1) { before = cy; after = kHeight - 1 - cy; }
+    else if (dir == 2) { before = min(cx, cy); after = kWidth - 1 - max(cx, cy); }
+    else { before = min(kWidth - 1 - cx, cy); after = min(cx, kHeight - 1 - cy); }
+    const int lo = 6 - min(before, 6), hi = 6 + min(after, 6);
+    uint32_t row = 0;                                                           // word index of the current state's row
+#pragma unroll 1
     for (int i = 0; i < 13; ++i) {
-        const int x = cx + dx * (i - 6), y = cy + dy * (i - 6);
-        uint32_t sym = kSymPad;
-        if (x >= 0 && x < kWidth && y >= 0 && y < kHeight) sym = (cell_value(ws.board, y * kWidth + x) - 1u) & 3u;
-        const uint32_t tw = s_trans[st * 4 + sym];
-        st = tw_next(tw);
-        const uint32_t ne = tw_nemit(tw);
-        for (uint32_t k = 0; k < ne; ++k) {
-            const uint32_t em = tw_emit(tw, k);
-            const PatRec rec = s_patrec[em_pid(em)];
-            const int off = i - int(em_prev(em)) - 6;                       // position of `cell` counted from the pattern's end
+        uint32_t v = 3u;
+        if (i >= lo && i <= hi) v = cell_value(ws.board, cell + (i - 6) * stride);
+        const uint32_t tw = s_trans[row + v];
+        row = (tw & kDevNextMask) >> 2;
+        if (tw >= kDevEmitFloor) continue;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t pid = dw_pid(tw, k);
+            if (pid == kDevNoPid) break;
+            const PatRec rec = s_patrec[pid];
+            const int off = i - int(dw_prev(tw, k)) - 6;                        // `cell` is the off-th char from the pattern's end
             if (pr_cclass(rec.w0) != cclass || off < 0 || off >= int(pr_len(rec.w0))) continue;   // HasCovered, :22-25
-            uint32_t kinds = pr_kinds(rec.w0);
-            if (((kinds >> (2 * off)) & 3u) != 1u) continue;                 // `cell` must sit on a '_'
-            kinds &= ~(3u << (2 * off));
-            while (kinds) {
-                const int j = (__ffs(kinds) - 1) >> 1;
-                kinds &= ~(3u << (2 * j));
-                atomicAdd(&rival[cell + (off - j) * stride], 600);
+            bool on_key = false;                                                // `cell` must sit on a '_'
+            uint32_t cells = rec.w0;
+            for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) on_key = on_key || (cells & 15u) == (8u | uint32_t(off));
+            if (!on_key) continue;
+            cells = rec.w0;
+            for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) {
+                const int j = int(cells & 7u);
+                if (j != off) atomicAdd(&rival[cell + (off - j) * stride], 600);
             }
-            return;                                                          // only the first such pattern, :540
+            return;                                                             // only the first such pattern, :540
         }
     }
 }
 
-// phase 4 for one (cell, player) whose flags passed Compound::Test.
-__device__ __forceinline__ void compound_at(WarpSmem& ws, const uint32_t* s_trans, const PatRec* s_patrec, uint32_t idx) {
+// Compound::locate + updateCritical for one (cell, player) whose flags passed Compound::Test
+// (Pattern.cpp:440-518).  Returns the two updateAntis tasks in t0 / t1 (0 = none):
+// cell | black << 8 | dir << 9 | class << 11 | 1 << 13.
+__device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t idx, uint32_t& t0, uint32_t& t1) {
     const uint32_t f = ws.flags[idx];
     const int cell = idx >> 1;
     const uint32_t black = idx & 1u;
-    // Compound::locate, Pattern.cpp:440-486.  states: S0 0, L2 1, LD3 2, To33 3, To43 4, To44 5
+    // states: S0 0, L2 1, LD3 2, To33 3, To43 4, To44 5
     int state = 0, l3 = 0, ncomp = 0;
     bool triple = false;
-    uint32_t adir[2] = { 0, 0 }, aclass[2] = { 0, 0 };
+    uint32_t first = 0, second = 0;
 #pragma unroll
     for (uint32_t dir = 0; dir < 4; ++dir) {
         const uint32_t c1 = (f >> (dir * 2)) & 3u, c2 = (f >> (8 + dir * 2)) & 3u, c3 = (f >> (16 + dir * 2)) & 3u;
-        const uint32_t cls = c1 ? 1u : c2 ? 2u : c3 ? 3u : 0u;              // LiveThree > DeadThree > LiveTwo
+        const uint32_t cls = c1 ? 1u : c2 ? 2u : c3 ? 3u : 0u;                  // LiveThree > DeadThree > LiveTwo
         if (!cls) continue;
         const uint32_t bits = cls == 1u ? c1 : cls == 2u ? c2 : c3;
         const int count = bits == 3u ? 2 : 1, cond = cls == 3u ? 1 : 2;
         l3 += cls == 1u;
-        for (int i = 0; i < count; ++i) {
-            if (ncomp < 2) { adir[ncomp] = dir; aclass[ncomp] = cls; }
-            ++ncomp;
-            int offset;
-            if (state == 0) offset = 0;
-            else if (state <= 2) offset = 1;
-            else { triple = true; offset = state == 5 ? -cond : -1; }
-            state += cond + offset;
+        const uint32_t task = uint32_t(cell) | black << 8 | dir << 9 | cls << 11 | 1u << 13;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i < count) {
+                if (ncomp == 0) first = task;
+                else if (ncomp == 1) second = task;
+                ++ncomp;
+                int offset;
+                if (state == 0) offset = 0;
+                else if (state <= 2) offset = 1;
+                else { triple = true; offset = state == 5 ? -cond : -1; }
+                state += cond + offset;
+            }
         }
     }
+    t0 = t1 = 0;
     const int type = state - 3;
-    if (type < 0) return;   // cannot happen for flags that passed Test unless one line holds an L3 and two lower-class patterns on the same cell
-    int* self = ws.scores + black * 3 * kCells;
-    int* rival = ws.scores + (black + 1) * kCells;
-    atomicAdd(&self[cell], 600 * ncomp);                                     // updateCritical, :515-518
-    atomicAdd(&rival[cell], 600 * ncomp);
-    atomicAdd(&ws.totals[16 + black * 3 + type], 1u);                        // one compound, :505-508
-    if (!triple && l3 == 0) {                                                // exactly two components here
-        anti_cells(ws, s_trans, s_patrec, cell, adir[0], aclass[0], rival);
-        anti_cells(ws, s_trans, s_patrec, cell, adir[1], aclass[1], rival);
-    }
+    if (type < 0) return;   // needs an L3 plus two lower-class patterns on one cell of one line: excluded by exhaustive line enumeration (tests)
+    atomicAdd(&ws.scores[black * 3 * kCells + cell], 600 * ncomp);              // updateCritical, :515-518
+    atomicAdd(&ws.scores[(black + 1) * kCells + cell], 600 * ncomp);
+    atomicAdd(&ws.totals[16 + black * 3 + type], 1u);                           // one compound, :505-508
+    if (!triple && l3 == 0) { t0 = first; t1 = second; }                        // exactly two components here, :500-502
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
@@ -178,17 +214,21 @@ ac_eval_kernel(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_trans = reinterpret_cast<uint32_t*>(smem_raw);
     PatRec* s_patrec = reinterpret_cast<PatRec*>(s_trans + ((a.n_states * 4 + 3) & ~3));
-    uint32_t* s_tape = reinterpret_cast<uint32_t*>(s_patrec + ((a.n_patterns + 1) & ~1));
-    WarpSmem* s_warps = reinterpret_cast<WarpSmem*>(s_tape + a.tape_steps * 32);
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(s_patrec + ((a.n_patterns + 1) & ~1));
+    uint16_t* s_info = s_src + a.tape_steps * 32;
+    WarpSmem* s_warps = reinterpret_cast<WarpSmem*>(s_info + a.tape_steps * 32);
 
     for (int i = threadIdx.x; i < a.n_states * 4; i += blockDim.x) s_trans[i] = a.trans[i];
     for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
-    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) s_tape[i] = a.tape[i];
+    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) { s_src[i] = a.tape_src[i]; s_info[i] = a.tape_info[i]; }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem& ws = s_warps[warp];
     const uint32_t lt = lanemask_lt();
+    const uint32_t board_addr = smem_addr(ws.board), trans_addr = smem_addr(s_trans);
+    const uint32_t queue_addr = smem_addr(ws.queue), src_addr = smem_addr(s_src + lane);
+    const uint32_t start_tw = a.start_state << 4;                          // a word whose "next" field is the start state
 
     for (long long b = (long long)blockIdx.x * kWarpsPerCta + warp; b < a.n; b += (long long)gridDim.x * kWarpsPerCta) {
         // ---- phase 0 ---------------------------------------------------------------------------
@@ -238,42 +278,35 @@ ac_eval_kernel(EvalArgs a) {
         __syncwarp();
 
         // ---- phase 2: scan -------------------------------------------------------------------------
-        uint32_t st = a.start_state, win = 0;
-        int qn = 0;
-        for (int t = 0; t < a.tape_steps; ++t) {
-            const uint32_t e = s_tape[t * 32 + lane];
-            const uint32_t sym = (cell_value(ws.board, tp_src(e)) - 1u) & 3u;
-            if (e & kTapeStart) st = a.start_state;
-            const uint32_t tw = s_trans[st * 4 + sym];
-            st = tw_next(tw);
-            const uint32_t ne = tw_nemit(tw);
-            const uint32_t m1 = __ballot_sync(0xffffffffu, ne != 0);
-            if (m1) {
-                const uint32_t vcell = tp_vcell(e), dirbits = e & (3u << 18);
-                const uint32_t stride = (e >> 21) & 31u;
-                if (ne) {
-                    const uint32_t em = tw_emit(tw, 0);
-                    ws.queue[qn + __popc(m1 & lt)] = em_pid(em) | ((vcell - em_prev(em) * stride) << 9) | dirbits;
-                }
-                qn += __popc(m1);
-                const uint32_t m2 = __ballot_sync(0xffffffffu, ne > 1);
-                if (m2) {
-                    if (ne > 1) {
-                        const uint32_t em = tw_emit(tw, 1);
-                        ws.queue[qn + __popc(m2 & lt)] = em_pid(em) | ((vcell - em_prev(em) * stride) << 9) | dirbits;
+        // per step: tape entry -> board word -> 2-bit cell value * 4 -> transition word; the only
+        // state-dependent chain is  LDS word, LOP3 (word & 0x3ff0 | value * 4), LDS word.
+        uint32_t tw = start_tw, win = 0;
+        uint32_t qaddr = queue_addr;                                        // shared address of the next free queue word
+        uint32_t src = src_addr;
+        uint32_t tag = uint32_t(lane) << 2;                                 // (step * 32 + lane) << 2
+        for (int t = 0; t < a.tape_steps; t += 2) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u, src += 64, tag += 32u << 2) {
+                const uint32_t e = lds_u16(src);
+                const uint32_t w = lds_u32(board_addr + (e & 0x7cu));
+                const uint32_t v4 = __funnelshift_r(w, w, e >> 8) & 0xcu;   // cell value * 4
+                tw = lds_u32(trans_addr + ((tw & kDevNextMask) | v4));
+                const bool emits = tw < kDevEmitFloor;
+                const uint32_t m = __ballot_sync(0xffffffffu, emits);
+                if (m) {
+                    if (emits) sts_u32(qaddr + 4u * __popc(m & lt), (tw & kDevEmitMask) | tag);
+                    qaddr += 4u * __popc(m);
+                    if (qaddr > queue_addr + 4u * kQueueFlush) {
+                        __syncwarp();
+                        win |= scatter_emissions(ws, s_patrec, s_info, int(qaddr - queue_addr) >> 2, lane);
+                        __syncwarp();
+                        qaddr = queue_addr;
                     }
-                    qn += __popc(m2);
-                }
-                if (qn > kQueueFlush) {
-                    __syncwarp();
-                    win |= scatter_emissions(ws, s_patrec, qn, lane);
-                    __syncwarp();
-                    qn = 0;
                 }
             }
         }
         __syncwarp();
-        win |= scatter_emissions(ws, s_patrec, qn, lane);
+        win |= scatter_emissions(ws, s_patrec, s_info, int(qaddr - queue_addr) >> 2, lane);
         __syncwarp();
 
         // ---- phase 4: compounds ----------------------------------------------------------------------
@@ -295,15 +328,32 @@ ac_eval_kernel(EvalArgs a) {
                 }
             }
             __syncwarp();
-            for (int i = lane; i < cn; i += 32) compound_at(ws, s_trans, s_patrec, clist[i]);
+            for (int base = 0; base < cn; base += 32) {                             // warp-uniform trip count
+                uint32_t t0 = 0, t1 = 0;
+                if (base + lane < cn) compound_at(ws, clist[base + lane], t0, t1);
+                // spread the window rescans: task s = 2 * (rank of the owning lane) + which
+                const uint32_t owners = __ballot_sync(0xffffffffu, t0 != 0);
+                const int ntask = 2 * __popc(owners);
+                for (int s0 = 0; s0 < ntask; s0 += 32) {
+                    const int s = s0 + lane;
+                    const int owner = s < ntask ? int(__fns(owners, 0, (s >> 1) + 1)) : 0;
+                    const uint32_t ta = __shfl_sync(0xffffffffu, t0, owner), tb = __shfl_sync(0xffffffffu, t1, owner);
+                    const uint32_t task = (s & 1) ? tb : ta;
+                    if (s < ntask) {
+                        const uint32_t black = (task >> 8) & 1u;
+                        anti_cells(ws, s_trans, s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
+                                   ws.scores + (black + 1) * kCells);
+                    }
+                }
+            }
         }
         __syncwarp();
 
         // ---- phase 5: output --------------------------------------------------------------------------
         if (a.scores) {
-            const int4* src = reinterpret_cast<const int4*>(ws.scores);
+            const int4* s4 = reinterpret_cast<const int4*>(ws.scores);
             int4* dst = reinterpret_cast<int4*>(a.scores + b * kScoreWords);
-            for (int i = lane; i < kScoreWords / 4; i += 32) dst[i] = src[i];
+            for (int i = lane; i < kScoreWords / 4; i += 32) dst[i] = s4[i];
         }
         if (a.pat_totals && lane < 16) a.pat_totals[b * 16 + lane] = (uint16_t)ws.totals[lane];
         if (a.cmp_totals && lane < 6) a.cmp_totals[b * 6 + lane] = (uint16_t)ws.totals[16 + lane];
@@ -344,7 +394,7 @@ __global__ void scan_strings_kernel(ScanArgs a) {
 
 size_t eval_smem_bytes(const EvalArgs& a) {
     return size_t((a.n_states * 4 + 3) & ~3) * 4 + size_t((a.n_patterns + 1) & ~1) * sizeof(PatRec) +
-           size_t(a.tape_steps) * 32 * 4 + size_t(kWarpsPerCta) * sizeof(WarpSmem);
+           size_t(a.tape_steps) * 32 * 2 * sizeof(uint16_t) + size_t(kWarpsPerCta) * sizeof(WarpSmem);
 }
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {

@@ -34,39 +34,60 @@ GK_HD inline uint32_t tw_emit(uint32_t w, int k) { return (w >> (12 + 10 * k)) &
 GK_HD inline uint32_t em_pid(uint32_t e) { return e & 0x1ffu; }
 GK_HD inline uint32_t em_prev(uint32_t e) { return (e >> 9) & 1u; }
 
-// ---- pattern record: 2 words per pattern --------------------------------------------------
-//   w0 [ 0,14) cell kinds, 2 bits per pattern char counted FROM THE END (j = 0 is the last
-//              char): 0 = not scored, 1 = '_' (scored for both perspectives + flag),
-//              2 = '^' (scored for the rival's perspective only)
-//      [14,18) Pattern::Type (0..8, 8 = Five)
-//      [18]    favour is black
-//      [19,22) length (5..7)
-//      [22,24) compound class: 0 none, 1 LiveThree, 2 DeadThree, 3 LiveTwo
+// ======================= device-side encodings (what the kernels read) ==========================
+// The host words above are the documented, inspectable form (gk_table_entries).  The copies
+// uploaded to the GPU are re-encoded so that the scan loop needs as few integer ops as possible.
+//
+// ---- device transition word: D[state * 4 + v], v = raw 2-bit cell value (0 empty, 1 black,
+//      2 white, 3 off-board pad), i.e. the columns are permuted so no symbol mapping is needed.
+//      The fields are placed so that the scan loop's dependent chain is "LDS, one LOP3, LDS":
+//   [ 0]    emission 0 is "at previous symbol"
+//   [ 1]    emission 1 is "at previous symbol"
+//   [ 2, 4) zero
+//   [ 4,14) next state, i.e. (word & 0x3ff0) is the BYTE offset of the next state's row
+//   [14,23) emission 1 pattern id, 0x1ff = none
+//   [23,32) emission 0 pattern id, 0x1ff = none  (so: word >= kDevEmitFloor  <=>  no emission)
+// Bits [2,14) are replaced by (step * 32 + lane) when the word is pushed to the emission queue.
+constexpr uint32_t kDevNoPid = 0x1ffu;
+constexpr uint32_t kDevEmitFloor = kDevNoPid << 23;
+constexpr uint32_t kDevNextMask = 0x3ff0u;
+constexpr uint32_t kDevEmitMask = 0xffffc003u;    // the bits of a device word that describe its emissions
+GK_HD inline int sym_to_value(int sym) { return (sym + 1) & 3; }   // table symbol index -> raw cell value
+GK_HD inline uint32_t dw_pid(uint32_t w, int k) { return (w >> (23 - 9 * k)) & 0x1ffu; }
+GK_HD inline uint32_t dw_prev(uint32_t w, int k) { return (w >> k) & 1u; }
+
+// ---- device pattern record: 2 words per pattern ---------------------------------------------------
+//   w0 [ 0,16) up to four scored cells, one nibble each: bits 0..2 = j (cell is the j-th char from
+//              the END of the pattern), bit 3 = 1 for '_' (scored for both perspectives + flag),
+//              0 for '^' (rival's perspective only)
+//      [16,19) number of scored cells (0..4)
+//      [19,23) Pattern::Type (0..8, 8 = Five)
+//      [23]    favour is black
+//      [24,27) length (5..7)
+//      [27,29) compound class: 0 none, 1 LiveThree, 2 DeadThree, 3 LiveTwo
 //   w1 [ 0,16) score on rows/columns, [16,32) score on diagonals (= int(1.2 * score))
 struct PatRec { uint32_t w0, w1; };
-GK_HD inline uint32_t pr_kinds(uint32_t w0) { return w0 & 0x3fffu; }
-GK_HD inline uint32_t pr_type(uint32_t w0) { return (w0 >> 14) & 15u; }
-GK_HD inline uint32_t pr_black(uint32_t w0) { return (w0 >> 18) & 1u; }
-GK_HD inline uint32_t pr_len(uint32_t w0) { return (w0 >> 19) & 7u; }
-GK_HD inline uint32_t pr_cclass(uint32_t w0) { return (w0 >> 22) & 3u; }
+GK_HD inline uint32_t pr_ncells(uint32_t w0) { return (w0 >> 16) & 7u; }
+GK_HD inline uint32_t pr_type(uint32_t w0) { return (w0 >> 19) & 15u; }
+GK_HD inline uint32_t pr_black(uint32_t w0) { return (w0 >> 23) & 1u; }
+GK_HD inline uint32_t pr_len(uint32_t w0) { return (w0 >> 24) & 7u; }
+GK_HD inline uint32_t pr_cclass(uint32_t w0) { return (w0 >> 27) & 3u; }
 constexpr int kTypeFive = 8;
 
-// ---- scan tape: tape[step * 32 + lane] ------------------------------------------------------
+// ---- scan tape ---------------------------------------------------------------------------------------
 // One warp evaluates one board; lane L walks a fixed chain of whole lines, one symbol per step.
-//   [ 0, 9) source cell of this step's symbol: 0..224 = board cell, >= 225 = a pad cell (value 3)
-//   [ 9,18) virtual cell of this step on its line (cell0 + index * stride, may run past 224 on
-//           the trailing pads); an emission ending here covers cells vcell - j * stride
-//   [18,20) direction of the line: 0 row, 1 column, 2 diagonal (+1,+1), 3 anti-diagonal (-1,+1)
-//   [20]    first symbol of a line: the automaton restarts from the state reached after one
-//           leading '?'
-//   [21,26) cell stride of the line (1, 15, 16 or 14)
-constexpr uint32_t kTapeStart = 1u << 20;
+// Every line is followed by trail_pad (>= 2) pad symbols; two pads take ANY state to the state
+// "one '?' read from the root" (checked by the table compiler), which is also where a line has
+// to start, so the chain needs no explicit restart between lines.
+//   src[step * 32 + lane]  (uint16)  where this step's symbol lives in the warp's board copy:
+//        [0,7)  byte offset of the 32-bit board word (cell >> 4) * 4; pads read cell 225 (value 3)
+//        [8,13) rotate-right amount that brings the cell's 2 bits to bits 2..3: (2*(cell & 15) + 30) & 31
+//   info[step * 32 + lane] (uint16)  only read when the step emitted:
+//        [0,9)  virtual cell of this step on its line (cell0 + index * stride; runs past 224 on pads)
+//        [9,11) direction: 0 row, 1 column, 2 diagonal (+1,+1), 3 anti-diagonal (-1,+1)
 constexpr int kPadCell = 225;                     // any cell index in [225, 272) reads as pad
-GK_HD inline uint32_t tp_src(uint32_t e) { return e & 0x1ffu; }
-GK_HD inline uint32_t tp_vcell(uint32_t e) { return (e >> 9) & 0x1ffu; }
-GK_HD inline uint32_t tp_dir(uint32_t e) { return (e >> 18) & 3u; }
 GK_HD inline int dir_stride(int dir) { return dir == 0 ? 1 : dir == 1 ? 15 : dir == 2 ? 16 : 14; }
 
-// ---- emission queue entry (kernel internal) ---------------------------------------------------
-//   [0,9) pattern id, [9,18) virtual END cell, [18,20) direction
+// ---- emission queue entry (kernel internal) -----------------------------------------------------------
+//   a device transition word with bits [2,13) replaced by step * 32 + lane
 }  // namespace gk

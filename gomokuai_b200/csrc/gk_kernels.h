@@ -10,9 +10,9 @@
 namespace gk {
 
 struct EvalArgs {
-    const uint32_t* trans; int n_states;       // device copies of the compiled table
+    const uint32_t* trans; int n_states;       // device copies of the compiled table, device encodings (gk_format.h)
     const PatRec* patrec; int n_patterns;
-    const uint32_t* tape; int tape_steps;
+    const uint16_t* tape_src; const uint16_t* tape_info; int tape_steps;
     uint32_t start_state;
     const uint32_t* boards; long long n;
     int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
@@ -21,7 +21,7 @@ size_t eval_smem_bytes(const EvalArgs& a);
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream);
 
 struct ScanArgs {
-    const uint32_t* trans; const int16_t* flush;
+    const uint32_t* trans; const int16_t* flush;   // host-format transition words (symbol-indexed)
     const uint8_t* codes; const long long* starts; int n_strings; int max_per_string;
     int32_t* pids; int32_t* offsets; int32_t* counts;
 };

@@ -235,20 +235,26 @@ FlatStep simulate(const SlotAutomaton& a, int s, bool in_run, int code) {
     }
 }
 
-PatRec make_patrec(const PatternInfo& p) {
+// device pattern record (gk_format.h); false if the pattern scores more than four cells
+bool make_patrec(const PatternInfo& p, PatRec& out) {
     uint32_t w0 = 0;
+    int n = 0;
     const int len = static_cast<int>(p.str.size());
     for (int j = 0; j < len; ++j) {
         const char ch = p.str[len - 1 - j];
-        w0 |= static_cast<uint32_t>(ch == '_' ? 1 : ch == '^' ? 2 : 0) << (2 * j);
+        if (ch != '_' && ch != '^') continue;
+        if (n == 4) return false;
+        w0 |= static_cast<uint32_t>(j | (ch == '_' ? 8 : 0)) << (4 * n++);
     }
-    w0 |= static_cast<uint32_t>(p.type) << 14;
-    w0 |= static_cast<uint32_t>(p.favour == 1) << 18;
-    w0 |= static_cast<uint32_t>(len) << 19;
+    w0 |= static_cast<uint32_t>(n) << 16;
+    w0 |= static_cast<uint32_t>(p.type) << 19;
+    w0 |= static_cast<uint32_t>(p.favour == 1) << 23;
+    w0 |= static_cast<uint32_t>(len) << 24;
     const int cclass = p.type == 5 ? 1 : p.type == 4 ? 2 : p.type == 3 ? 3 : 0;   // CompTypes, Pattern.cpp:420-422
-    w0 |= static_cast<uint32_t>(cclass) << 22;
+    w0 |= static_cast<uint32_t>(cclass) << 27;
     const int diag = static_cast<int>(1 * 1.2 * p.score);     // Pattern.cpp:151-152 with delta = +1
-    return { w0, static_cast<uint32_t>(p.score) | static_cast<uint32_t>(diag) << 16 };
+    out = { w0, static_cast<uint32_t>(p.score) | static_cast<uint32_t>(diag) << 16 };
+    return true;
 }
 
 struct Line { int cell0, stride, len, dir; };
@@ -280,19 +286,20 @@ void build_tape(HostTable& t) {
         lane[best].push_back(li);
         load[best] += lines[li].len + t.trail_pad;
     }
-    t.tape_steps = *std::max_element(load.begin(), load.end());
-    const uint32_t filler = kPadCell | (kPadCell << 9);        // a '?' that belongs to no line
-    t.tape.assign(static_cast<size_t>(t.tape_steps) * 32, filler);
+    t.tape_steps = (*std::max_element(load.begin(), load.end()) + 1) & ~1;   // the kernel unrolls by two
+    const auto src_of = [](int cell) {
+        return static_cast<uint16_t>(((cell >> 4) * 4) | (((2 * (cell & 15) + 30) & 31) << 8));
+    };
+    t.tape_src.assign(static_cast<size_t>(t.tape_steps) * 32, src_of(kPadCell));   // filler: a pad that belongs to no line
+    t.tape_info.assign(static_cast<size_t>(t.tape_steps) * 32, 0);
     for (int l = 0; l < 32; ++l) {
         int step = 0;
         for (int li : lane[l]) {
             const Line& L = lines[li];
             for (int i = 0; i < L.len + t.trail_pad; ++i, ++step) {
-                const uint32_t vcell = static_cast<uint32_t>(L.cell0 + i * L.stride);
-                const uint32_t src = i < L.len ? vcell : static_cast<uint32_t>(kPadCell);
-                t.tape[static_cast<size_t>(step) * 32 + l] =
-                    src | vcell << 9 | static_cast<uint32_t>(L.dir) << 18 | (i == 0 ? kTapeStart : 0u) |
-                    static_cast<uint32_t>(L.stride) << 21;
+                const int vcell = L.cell0 + i * L.stride;
+                t.tape_src[static_cast<size_t>(step) * 32 + l] = src_of(i < L.len ? vcell : kPadCell);
+                t.tape_info[static_cast<size_t>(step) * 32 + l] = static_cast<uint16_t>(vcell | L.dir << 9);
             }
         }
     }
@@ -367,7 +374,12 @@ bool compile_table(const std::vector<Proto>& protos, HostTable& t) {
             t.trans[static_cast<size_t>(id) * 4 + sym_from_refcode(code)] = w;
         }
     }
-    for (const PatternInfo& p : t.patterns) t.patrec.push_back(make_patrec(p));
+    for (const PatternInfo& p : t.patterns) {
+        PatRec rec;
+        if (!make_patrec(p, rec)) { t.error = "pattern '" + p.str + "' scores more than four cells"; return false; }
+        t.patrec.push_back(rec);
+    }
+    if (static_cast<int>(t.patterns.size()) >= static_cast<int>(kDevNoPid)) { t.error = "pattern id 511 is reserved"; return false; }
 
     // A board line is "?", cells, "?..." : after the leading pad the automaton must sit in a
     // state that further pads do not move, so the kernel can start every line there ...
@@ -395,8 +407,27 @@ bool compile_table(const std::vector<Proto>& protos, HostTable& t) {
             if (any) last_emitting = k;
         }
         if (last_emitting >= 16) { t.error = "trailing board edge never stops emitting"; return false; }
-        t.trail_pad = std::max(last_emitting, 1);
+        t.trail_pad = std::max(last_emitting, 2);
+        // trail_pad pads must also leave every state in start_state: that is what lets the kernel run the
+        // lines of a lane back to back without restarting the automaton.
+        std::iota(cur.begin(), cur.end(), 0);
+        for (int k = 0; k < t.trail_pad; ++k)
+            for (int& s : cur) s = static_cast<int>(tw_next(t.trans[static_cast<size_t>(s) * 4 + kSymPad]));
+        for (int s : cur)
+            if (s != t.start_state) { t.error = "board edge does not reset the automaton"; return false; }
     }
+    t.dev_trans.assign(t.trans.size(), 0);
+    for (int id = 0; id < t.n_states; ++id)
+        for (int sym = 0; sym < 4; ++sym) {
+            const uint32_t w = t.trans[static_cast<size_t>(id) * 4 + sym];
+            uint32_t d = tw_next(w) << 4;
+            for (int k = 0; k < 2; ++k) {
+                const bool has = k < static_cast<int>(tw_nemit(w));
+                d |= (has ? em_pid(tw_emit(w, k)) : kDevNoPid) << (23 - 9 * k);
+                d |= (has ? em_prev(tw_emit(w, k)) : 0u) << k;
+            }
+            t.dev_trans[static_cast<size_t>(id) * 4 + sym_to_value(sym)] = d;
+        }
     // How many symbols until the state forgets where it started (0: it never does).  Informational:
     // it bounds the context an emission can depend on.
     {

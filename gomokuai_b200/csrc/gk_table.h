@@ -17,11 +17,14 @@ struct HostTable {
     int n_states = 0;                    // dense ids, 0 = root
     std::vector<uint32_t> trans;         // n_states * 4 transition words (gk_format.h)
     std::vector<int16_t> flush;          // per state: pattern id emitted if the input ends here, else -1
-    std::vector<PatRec> patrec;
     int start_state = 0;                 // state after the single leading '?' of a board line
-    int trail_pad = 0;                   // trailing '?' symbols after which no state can emit any more
-    int tape_steps = 0;                  // scan steps per board (longest lane chain)
-    std::vector<uint32_t> tape;          // tape_steps * 32 words
+    int trail_pad = 0;                   // trailing '?' symbols after which no state can emit any more (>= 2)
+    int tape_steps = 0;                  // scan steps per board (longest lane chain, even)
+    // device encodings (gk_format.h)
+    std::vector<uint32_t> dev_trans;     // n_states * 4, indexed by raw cell value
+    std::vector<PatRec> patrec;
+    std::vector<uint16_t> tape_src;      // tape_steps * 32
+    std::vector<uint16_t> tape_info;     // tape_steps * 32
     int sync_depth = 0;                  // symbols after which the state no longer depends on the start state (0 = not synchronizing)
     std::string error;
 };
@@ -31,9 +34,5 @@ const std::vector<Proto>& default_protos();
 
 // Returns false and fills out.error when the prototypes cannot be represented.
 bool compile_table(const std::vector<Proto>& protos, HostTable& out);
-
-// Host-side walk of the flat table over one symbol string (codes 1..4).  Used by the table
-// self-checks and by gk_scan on tiny inputs in tests; the batched path is the CUDA kernel.
-void scan_host(const HostTable& t, const uint8_t* codes, int n, std::vector<std::pair<int, int>>& out);
 
 }  // namespace gk
