@@ -39,5 +39,33 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(CSRC, "host")
+HOST_SOURCES = ["module.cpp", "mcts.cpp", "root_parallel.cpp"]
+HOST_HEADERS = ["game.h", "mcts.h", "root_parallel.h"]
+
+
+def ext_path():
+    import sysconfig
+    return os.path.join(HERE, "CorePyExt" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pyext(force=False):
+    """Compile the pybind11 module CorePyExt (host C++17 mirror of Board / Policy / MCTS) against the library."""
+    import sysconfig
+    import pybind11
+    out = ext_path()
+    deps = [os.path.join(HOST, f) for f in HOST_SOURCES + HOST_HEADERS] + [LIB]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-fvisibility=hidden",
+           "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+           *[os.path.join(HOST, f) for f in HOST_SOURCES], "-o", out,
+           "-L" + LIB_DIR, "-lgomoku_b200", "-Wl,-rpath,$ORIGIN/lib", "-lpthread"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_pyext(force="--force" in sys.argv))

@@ -1,0 +1,229 @@
+// mcts.cpp -- see mcts.h.  Semantics follow SURVEY.md Appendix A.6 and the cited reference lines.
+#include "mcts.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <random>
+#include <stdexcept>
+#include <string>
+
+#include "../../../include/gomoku_b200.h"
+
+namespace gomoku {
+
+// ---- Policy (MCTS.cpp:18-58) ---------------------------------------------------------------------------
+Policy::Policy(SelectFunc f1, ExpandFunc f2, EvalFunc f3, UpdateFunc f4, double c_puct)
+    : select(f1 ? f1 : [this](const Node* node) { return Default::Select(this, node); }),
+      expand(f2 ? f2 : [this](Node* node, Board& board, const Probs& probs) { return Default::Expand(this, node, board, probs); }),
+      simulate(f3 ? f3 : [this](Board& board) { return Default::Simulate(this, board); }),
+      backPropogate(f4 ? f4 : [this](Node* node, Board& board, double value) { Default::BackPropogate(this, node, board, value); }),
+      c_puct(c_puct) {}
+
+std::unique_ptr<Node> Policy::createNode(Node* parent, Position pose, Player player, float value, float prob) {
+    return std::make_unique<Node>(parent, pose, player, value, prob);
+}
+void Policy::prepare(Board& board) { m_initActs = board.m_moveRecord.size(); }
+void Policy::cleanup(Board& board) { board.revertMove(board.m_moveRecord.size() - m_initActs); }
+Player Policy::applyMove(Board& board, Position move) { return board.applyMove(move, false); }   // no victory check inside the tree
+Player Policy::revertMove(Board& board, std::size_t count) { return board.revertMove(count); }
+bool Policy::checkGameEnd(Board& board) { return board.checkGameEnd(); }
+
+// ---- default algorithms (MonteCarlo.hpp) ---------------------------------------------------------------
+double Default::PUCB(const Node* node, double c_puct) {                                 // :23-28
+    const double P = node->action_prob, N = static_cast<double>(node->parent->node_visits), n = static_cast<double>(node->node_visits + 1);
+    return c_puct * P * std::sqrt(N) / n;
+}
+
+Probs Default::UniformProbs(const Board& board) {                                       // :50-55
+    Probs p(BOARD_SIZE, 0.0f);
+    const float each = 1.0f / static_cast<float>(board.moveCounts(Player::None));
+    for (int i = 0; i < BOARD_SIZE; ++i) if (board.cell(i) == 0) p[i] = each;
+    return p;
+}
+
+Node* Default::Select(Policy* policy, const Node* node) {                               // :57-68, ties -> lowest index
+    std::size_t best = 0;
+    double best_score = -1.0;
+    for (std::size_t i = 0; i < node->children.size(); ++i) {
+        const Node* child = node->children[i].get();
+        const double score = child->state_value + PUCB(child, policy->c_puct);
+        if (score > best_score) { best_score = score; best = i; }
+    }
+    return node->children[best].get();
+}
+
+std::size_t Default::Expand(Policy* policy, Node* node, Board& board, const Probs& probs, bool extraCheck) {   // :71-80
+    node->children.reserve(probs.size());
+    for (int i = 0; i < BOARD_SIZE; ++i)
+        if (probs[i] != 0.0f && (!extraCheck || board.checkMove(i)))
+            node->children.emplace_back(policy->createNode(node, i, -node->player, 0.0f, probs[i]));
+    return node->children.size();
+}
+
+// The reference needs no device set-up call; a drop-in user of Board / MCTS should not either:
+// bind the process to a GPU (LOCAL_RANK, default 0) the first time a GPU slot runs.
+void ensure_gpu() {
+    int device = -1;
+    if (gk_device_info(&device, nullptr, nullptr, nullptr) == GK_OK) return;
+    const char* lr = std::getenv("LOCAL_RANK");
+    if (gk_init(lr ? std::atoi(lr) : 0) != GK_OK) throw std::runtime_error(std::string("gk_init: ") + gk_last_error());
+}
+
+float Default::GpuRolloutValue(const Board& board, int rollouts) {
+    ensure_gpu();
+    static std::atomic<int> call_counter{ 0 };         // a fresh Philox "position" per call: independent streams
+    std::uint32_t packed[16];
+    std::int32_t wdb[3] = { 0, 0, 0 };
+    board.pack(packed);
+    const int base = call_counter.fetch_add(1) & 0x3fffffff;
+    if (gk_rollout_batch_host(packed, 1, rollouts, 0x4D435453ull /* "MCTS" */, 0x5eedu, base, wdb) != GK_OK)
+        throw std::runtime_error(std::string("gk_rollout_batch_host: ") + gk_last_error());
+    const float black_value = static_cast<float>(wdb[2] - wdb[0]) / static_cast<float>(rollouts);
+    return CalcScore(board.m_curPlayer, black_value);
+}
+
+Policy::EvalResult Default::Simulate(Policy*, Board& board) {                           // :83-88, one random game
+    return { GpuRolloutValue(board, 1), UniformProbs(board) };
+}
+
+void Default::BackPropogate(Policy*, Node* node, Board&, double value) {                // :90-95
+    float v = static_cast<float>(value);
+    for (; node != nullptr; node = node->parent, v = -v) {
+        node->node_visits += 1;
+        node->state_value += (v - node->state_value) / static_cast<float>(node->node_visits);
+    }
+}
+
+void Default::AddNoise(Node* node, float alpha, float epsilon) {                        // :97-108, Statistical.hpp:29-34
+    if (node->children.empty()) return;
+    static thread_local std::mt19937 engine{ std::random_device{}() };
+    std::gamma_distribution<float> gamma(alpha, 1.0f);
+    std::vector<float> noise(node->children.size());
+    double norm2 = 0.0;
+    for (std::size_t i = 0; i < noise.size(); ++i) {
+        noise[i] = node->children[i]->action_prob != 0.0f ? gamma(engine) : 0.0f;
+        norm2 += double(noise[i]) * noise[i];
+    }
+    const float inv = norm2 > 0.0 ? static_cast<float>(1.0 / std::sqrt(norm2)) : 0.0f;    // Eigen normalized() = L2
+    for (std::size_t i = 0; i < noise.size(); ++i)
+        node->children[i]->action_prob = node->children[i]->action_prob * (1 - epsilon) + epsilon * noise[i] * inv;
+}
+
+// ---- RandomPolicy (policies/Random.h) --------------------------------------------------------------------
+RandomPolicy::RandomPolicy(double c_puct, std::size_t c_rollouts)
+    : Policy(nullptr, nullptr, [this](Board& board) { return averagedSimulate(board); }, nullptr, c_puct), c_rollouts(c_rollouts) {}
+
+Policy::EvalResult RandomPolicy::averagedSimulate(Board& board) {                      // Random.h:22-35; the board is left untouched
+    return { Default::GpuRolloutValue(board, static_cast<int>(c_rollouts)), Default::UniformProbs(board) };
+}
+
+// ---- MCTS (MCTS.cpp:60-198) ---------------------------------------------------------------------------------
+static Node* updateRoot(MCTS& mcts, std::unique_ptr<Node>&& next) {
+    mcts.m_root = std::move(next);
+    mcts.m_root->parent = nullptr;
+    return mcts.m_root.get();
+}
+
+MCTS::MCTS(milliseconds c_duration, Position last_move, Player last_player, std::shared_ptr<Policy> policy)
+    : m_policy(policy ? policy : std::make_shared<RandomPolicy>()),
+      m_root(m_policy->createNode(nullptr, last_move, last_player, 0.0f, 1.0f)),
+      m_size(1), m_iterations(0), m_duration(c_duration), c_constraint(Constraint::Duration) {}
+
+MCTS::MCTS(std::size_t c_iterations, Position last_move, Player last_player, std::shared_ptr<Policy> policy)
+    : m_policy(policy ? policy : std::make_shared<RandomPolicy>()),
+      m_root(m_policy->createNode(nullptr, last_move, last_player, 0.0f, 1.0f)),
+      m_size(1), m_iterations(c_iterations), m_duration(0), c_constraint(Constraint::Iterations) {}
+
+Position MCTS::getAction(Board& board) {
+    runPlayouts(board);
+    return stepForward()->position;
+}
+
+Probs TempBasedProbs(const Probs& logits, float temperature) {                          // Statistical.hpp:37-42
+    const float eps = std::numeric_limits<float>::epsilon();
+    std::vector<double> t(logits.size());
+    double mx = -std::numeric_limits<double>::infinity();
+    for (std::size_t i = 0; i < t.size(); ++i) { t[i] = double(std::log(logits[i] + eps) / temperature); mx = std::max(mx, t[i]); }
+    double sum = 0.0;
+    for (double& v : t) { v = std::exp(v - mx); sum += v; }
+    Probs out(logits.size());
+    for (std::size_t i = 0; i < t.size(); ++i) { const float p = static_cast<float>(t[i] / sum); out[i] = p > eps ? p : 0.0f; }
+    return out;
+}
+
+Policy::EvalResult MCTS::evalState(Board& board) {                                      // MCTS.cpp:104-117 (the debug print is dropped)
+    runPlayouts(board);
+    Probs visits(BOARD_SIZE, 0.0f);
+    double norm2 = 0.0;
+    for (auto& node : m_root->children) { visits[node->position] = static_cast<float>(node->node_visits); norm2 += double(node->node_visits) * node->node_visits; }
+    const float inv = norm2 > 0.0 ? static_cast<float>(1.0 / std::sqrt(norm2)) : 0.0f;
+    for (float& v : visits) { v *= inv; if (v != 0.0f) v += 1.0f; }
+    return { m_root->state_value, TempBasedProbs(visits, board.m_moveRecord.size() < 15 ? 1.0f : 1e-2f) };
+}
+
+void MCTS::syncWithBoard(Board& board) {                                                // MCTS.cpp:119-125
+    auto iter = std::find_if(board.m_moveRecord.begin(), board.m_moveRecord.end(),
+                             [this](Position p) { return p.id == m_root->position.id; });
+    for (iter = (iter == board.m_moveRecord.end() ? board.m_moveRecord.begin() : iter + 1); iter != board.m_moveRecord.end(); ++iter)
+        stepForward(*iter);
+}
+
+Node* MCTS::stepForward() {                                                             // most visited child becomes the root
+    auto iter = std::max_element(m_root->children.begin(), m_root->children.end(),
+                                 [](auto&& l, auto&& r) { return l->node_visits < r->node_visits; });
+    return iter != m_root->children.end() ? updateRoot(*this, std::move(*iter)) : m_root.get();
+}
+
+Node* MCTS::stepForward(Position next_move) {                                           // MCTS.cpp:136-147
+    auto iter = std::find_if(m_root->children.begin(), m_root->children.end(),
+                             [next_move](auto&& node) { return node->position.id == next_move.id; });
+    if (iter == m_root->children.end())
+        iter = m_root->children.emplace(m_root->children.end(), m_policy->createNode(nullptr, next_move, -m_root->player, 0.0f, 1.0f));
+    return updateRoot(*this, std::move(*iter));
+}
+
+void MCTS::reset() {                                                                    // MCTS.cpp:149-156
+    m_root = m_policy->createNode(nullptr, Position(-1), Player::White, 0.0f, 1.0f);
+    m_size = 1;
+}
+
+std::size_t MCTS::playout(Board& board) {                                               // MCTS.cpp:158-177
+    Node* node = m_root.get();
+    while (!node->isLeaf()) {
+        node = m_policy->select(node);
+        m_policy->applyMove(board, node->position);
+    }
+    double node_value;
+    std::size_t expand_size;
+    if (!m_policy->checkGameEnd(board)) {
+        auto [state_value, action_probs] = m_policy->simulate(board);   // value for the player to move
+        expand_size = m_policy->expand(node, board, action_probs);
+        node_value = -state_value;                                       // the node stores the view of who moved INTO it
+    } else {
+        expand_size = 0;
+        node_value = CalcScore(node->player, board.m_winner);
+    }
+    m_policy->backPropogate(node, board, node_value);
+    m_policy->revertMove(board, board.m_moveRecord.size() - m_policy->m_initActs);
+    return expand_size;
+}
+
+void MCTS::runPlayouts(Board& board) {                                                  // MCTS.cpp:179-198
+    const auto start = std::chrono::system_clock::now();
+    syncWithBoard(board);
+    Default::AddNoise(m_root.get());
+    m_policy->prepare(board);
+    if (c_constraint == Constraint::Duration) {
+        m_iterations = 0;
+        for (auto end = start; end - start < m_duration; end = std::chrono::system_clock::now(), ++m_iterations) m_size += playout(board);
+    } else {
+        for (std::size_t i = 0; i < m_iterations; ++i) m_size += playout(board);
+        m_duration = std::chrono::duration_cast<milliseconds>(std::chrono::system_clock::now() - start);
+    }
+    m_policy->cleanup(board);
+}
+
+}  // namespace gomoku

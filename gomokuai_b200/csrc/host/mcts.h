@@ -1,0 +1,125 @@
+// mcts.h -- host-side mirror of the reference's search layer (include/MCTS.h, src/MCTS.cpp,
+// include/algorithms/MonteCarlo.hpp, include/policies/Random.h): Node, the Policy plugin (four
+// std::function slots + virtuals), MCTS.  The tree stays on the host; what a slot computes may run
+// on the GPU (RandomPolicy::simulate calls gk_rollout_batch_host).  Probability vectors cross as
+// std::vector<float>(225) where the reference uses Eigen::VectorXf.
+#pragma once
+#include <chrono>
+#include <functional>
+#include <memory>
+#include <tuple>
+#include <vector>
+
+#include "game.h"
+
+namespace gomoku {
+
+using std::chrono::milliseconds;
+using Probs = std::vector<float>;
+
+constexpr double C_PUCT = 5.0;                       // MCTS.h:17-19
+constexpr std::size_t C_ITERATIONS = 10000;
+constexpr milliseconds C_DURATION{ 1000 };
+
+struct Node {                                        // MCTS.h:25-66
+    Node* parent = nullptr;
+    Position position = Position(-1);                // the move that led here ...
+    Player player = Player::None;                    // ... and who played it
+    float state_value = 0.0f;                        // running mean, from `player`'s point of view
+    float action_prob = 0.0f;
+    std::size_t node_visits = 0;
+    std::vector<std::unique_ptr<Node>> children;
+
+    Node() = default;
+    Node(const Node&) = delete;                      // children are uniquely owned (MCTS.h:56-61)
+    Node(Node&&) = default;
+    Node& operator=(Node&&) = default;
+    Node(Node* parent, Position position, Player player, float value, float prob)
+        : parent(parent), position(position), player(player), state_value(value), action_prob(prob) {}
+    bool isLeaf() const { return children.empty(); }
+    bool isFull(const Board& board) const { return children.size() == board.moveCounts(Player::None); }
+};
+
+class Policy {                                       // MCTS.h:69-132
+public:
+    using SelectFunc = std::function<Node*(const Node*)>;
+    using ExpandFunc = std::function<std::size_t(Node*, Board&, const Probs&)>;
+    using EvalResult = std::tuple<float, Probs>;     // value for the player to move, 225 move probabilities (0 on occupied cells)
+    using EvalFunc = std::function<EvalResult(Board&)>;
+    using UpdateFunc = std::function<void(Node*, Board&, double)>;
+
+    SelectFunc select;
+    ExpandFunc expand;
+    EvalFunc simulate;
+    UpdateFunc backPropogate;
+
+    // a null slot takes the default algorithm (MCTS.cpp:18-33)
+    explicit Policy(SelectFunc = nullptr, ExpandFunc = nullptr, EvalFunc = nullptr, UpdateFunc = nullptr, double c_puct = C_PUCT);
+    virtual ~Policy() = default;
+
+    virtual std::unique_ptr<Node> createNode(Node* parent, Position pose, Player player, float value, float prob);
+    virtual void prepare(Board& board);
+    virtual void cleanup(Board& board);
+    virtual Player applyMove(Board& board, Position move);
+    virtual Player revertMove(Board& board, std::size_t count = 1);
+    virtual bool checkGameEnd(Board& board);
+    virtual void reset() {}
+
+    double c_puct;
+    std::size_t m_initActs = 0;
+};
+
+// The default algorithms (MonteCarlo.hpp:13-110).  Simulate plays its random game on the GPU.
+struct Default {
+    static double PUCB(const Node* node, double c_puct);
+    static Probs UniformProbs(const Board& board);
+    static Node* Select(Policy* policy, const Node* node);
+    static std::size_t Expand(Policy* policy, Node* node, Board& board, const Probs& probs, bool extraCheck = true);
+    static Policy::EvalResult Simulate(Policy* policy, Board& board);
+    static void BackPropogate(Policy* policy, Node* node, Board& board, double value);
+    static void AddNoise(Node* node, float alpha = 0.05f, float epsilon = 0.25f);
+    // mean value for the player to move of `rollouts` random playouts from `board`, run by the
+    // rollout kernel (include/gomoku_b200.h: gk_rollout_batch_host); throws std::runtime_error on failure
+    static float GpuRolloutValue(const Board& board, int rollouts);
+};
+
+// RandomPolicy (policies/Random.h:15-35): `c_rollouts` playouts averaged per leaf
+class RandomPolicy : public Policy {
+public:
+    explicit RandomPolicy(double c_puct = C_PUCT, std::size_t c_rollouts = 5);
+    EvalResult averagedSimulate(Board& board);
+    std::size_t c_rollouts;
+};
+
+class MCTS {                                         // MCTS.h:135-180
+public:
+    explicit MCTS(milliseconds c_duration = C_DURATION, Position last_move = -1, Player last_player = Player::White,
+                  std::shared_ptr<Policy> policy = nullptr);
+    explicit MCTS(std::size_t c_iterations, Position last_move = -1, Player last_player = Player::White,
+                  std::shared_ptr<Policy> policy = nullptr);
+
+    Position getAction(Board& board);
+    Policy::EvalResult evalState(Board& board);
+    Node* stepForward();
+    Node* stepForward(Position next_move);
+    void syncWithBoard(Board& board);
+    void reset();
+
+    std::shared_ptr<Policy> m_policy;
+    std::unique_ptr<Node> m_root;
+    std::size_t m_size;
+    std::size_t m_iterations;
+    milliseconds m_duration;
+
+private:
+    std::size_t playout(Board& board);
+    void runPlayouts(Board& board);
+    enum class Constraint { Iterations, Duration } c_constraint;
+};
+
+void ensure_gpu();   // gk_init(LOCAL_RANK or 0) on first use; throws std::runtime_error without a usable GPU
+
+// Statistical helpers used by evalState (algorithms/Statistical.hpp:37-42)
+Probs TempBasedProbs(const Probs& logits, float temperature);
+
+}  // namespace gomoku

@@ -1,0 +1,51 @@
+// root_parallel.h -- root-parallel MCTS driver (BASELINE config 4; new, the reference has no
+// parallel search).  `trees` independent search trees start from the same root position; every
+// round each tree descends to one leaf (PUCB), the leaves of all trees are simulated in
+// ONE gk_rollout_batch call (c_rollouts playouts each, disjoint Philox counters), and the results
+// are backed up.  Trees live in arenas (one contiguous child block per expansion) instead of the
+// reference's make_unique per child (MonteCarlo.hpp:71-80).  The per-root-child statistics are
+// integers, so summing them over trees, ranks and GPUs is order-independent: that sum is the only
+// thing the multi-GPU path exchanges (one allreduce of int64[3][225] per move).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <vector>
+
+#include "game.h"
+
+namespace gomoku {
+
+struct RootParallelConfig {
+    int trees = 256;            // independent trees on this rank
+    int c_rollouts = 5;         // RandomPolicy::c_rollouts (policies/Random.h:15)
+    double c_puct = 5.0;
+    std::uint64_t seed = 1;     // Philox key
+    int replica_base = 0;       // first global tree index of this rank (keeps streams disjoint across ranks)
+    int threads = 0;            // host threads for tree work (0 = hardware concurrency)
+    bool noise = true;          // Dirichlet noise on root priors (Default::AddNoise, MonteCarlo.hpp:97-108)
+};
+
+class RootParallelSearch {
+public:
+    using Stats = std::array<std::int64_t, 3 * BOARD_SIZE>;   // [0] visits, [1] black-won rollouts, [2] white-won rollouts, per root child
+
+    explicit RootParallelSearch(const RootParallelConfig& cfg);
+    ~RootParallelSearch();
+
+    // fresh trees from `root`, `playouts_per_tree` playouts on each; fills stats()
+    void run(const Board& root, int playouts_per_tree);
+
+    const Stats& stats() const { return m_stats; }
+    static Position bestMove(const Stats& stats);             // most visited root child, ties -> lowest cell (MCTS.cpp:129-134)
+
+    double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / inside gk_rollout_batch_host
+    std::int64_t leaves = 0, nodes = 0;
+
+private:
+    struct Impl;
+    Impl* m;
+    RootParallelConfig m_cfg;
+    Stats m_stats{};
+};
+
+}  // namespace gomoku

@@ -1,0 +1,45 @@
+"""Root-parallel MCTS across the GPUs of one box (BASELINE config 4).
+
+Every rank (one process per GPU) runs `trees_per_rank` independent search trees from the same
+root with disjoint Philox streams; leaves are simulated in batches by the rollout kernel.  The
+only exchange is ONE allreduce(sum) of the int64[3][225] root statistics per move
+(torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests); integer counts make the
+result independent of the reduction order.
+"""
+import math
+
+import numpy as np
+
+
+def allreduce_root_stats(stats, group=None):
+    """Sum int64[3,225] root statistics over all ranks. No-op without an initialised process group."""
+    import torch
+    import torch.distributed as dist
+    stats = np.ascontiguousarray(stats, np.int64)
+    if not (dist.is_available() and dist.is_initialized()):
+        return stats
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(stats.copy())
+    if backend == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def best_move(stats):
+    """Most visited root child, ties -> lowest cell (MCTS::stepForward, MCTS.cpp:129-134)."""
+    visits = np.asarray(stats)[0]
+    return int(np.argmax(visits)) if visits.max() > 0 else -1
+
+
+def search(board, playouts_total, trees_per_rank=256, c_rollouts=5, c_puct=5.0, seed=1, noise=True, threads=0, group=None):
+    """One move of root-parallel search. Returns (best cell, merged stats int64[3,225], local RootParallelSearch)."""
+    import torch.distributed as dist
+    from .core import RootParallelSearch
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if (dist.is_available() and dist.is_initialized()) else (0, 1)
+    per_tree = max(1, math.ceil(playouts_total / (world * trees_per_rank)))
+    s = RootParallelSearch(trees=trees_per_rank, c_rollouts=c_rollouts, c_puct=c_puct, seed=seed,
+                           replica_base=rank * trees_per_rank, threads=threads, noise=noise)
+    local = s.run(board, per_tree)
+    merged = allreduce_root_stats(local, group)
+    return best_move(merged), merged, s

@@ -1,0 +1,77 @@
+"""The reference-facing plugin surface with its simulate slot on the GPU: MCTS + RandomPolicy
+(config 1 semantics) and the root-parallel driver (config 4).  Needs a B200."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def core(gpu):
+    from gomokuai_b200 import build
+    build.build_pyext()
+    from gomokuai_b200 import core
+    return core
+
+
+def test_random_policy_mcts_plays_a_legal_move_and_restores_the_board(core):
+    # core/test/unit/mcts_unittest.cpp:14-42 (the reference's disabled invariance test)
+    b = core.Board()
+    for c in (112, 113, 97):
+        b.apply_move(c)
+    snapshot = list(map(int, b.move_record))
+    m = core.MCTS(c_iterations=400, policy=core.RandomPolicy(5.0, 5))
+    q, pi = m.policy.eval_state(b)
+    assert list(map(int, b.move_record)) == snapshot and -1.0 <= q <= 1.0 and abs(sum(pi) - 1.0) < 1e-4
+    move = m.get_action(b)
+    assert list(map(int, b.move_record)) == snapshot and b.check_move(move) and m.iterations == 400
+    assert m.size > 400
+
+
+def test_random_policy_value_tracks_the_rollout_kernel(core, gpu):
+    b = core.Board()
+    for c in (112, 0, 113, 1, 114, 2, 115, 30):        # black to move with an open four: black wins most rollouts
+        b.apply_move(c)
+    vals = [core.RandomPolicy(5.0, 64).eval_state(b)[0] for _ in range(8)]
+    wdb = gpu.rollout_batch(b.packed().reshape(1, 16), 4096)["wdb"].cpu().numpy()[0]
+    expect = (wdb[2] - wdb[0]) / 4096.0                 # side to move is black
+    assert abs(np.mean(vals) - expect) < 0.15 and np.mean(vals) > 0.2
+
+
+def test_root_parallel_search_statistics(core):
+    b = core.Board()
+    for c in (112, 113, 97, 98):
+        b.apply_move(c)
+    s = core.RootParallelSearch(trees=64, c_rollouts=5, seed=7, threads=4)
+    stats = s.run(b, 40)
+    assert stats.shape == (3, 225) and stats.dtype == np.int64
+    assert stats[0].sum() == 64 * (40 - 1)              # the first playout of every tree evaluates the root itself
+    occupied = [112, 113, 97, 98]
+    assert (stats[:, occupied] == 0).all()
+    assert ((stats[1] + stats[2]) <= stats[0] * 5).all()
+    again = core.RootParallelSearch(trees=64, c_rollouts=5, seed=7, threads=2).run(b, 40)
+    assert np.array_equal(stats, again)                 # seeded: independent of the host thread count
+    other = core.RootParallelSearch(trees=64, c_rollouts=5, seed=8).run(b, 40)
+    assert not np.array_equal(stats, other)
+    assert s.leaves == 64 * 40 and s.nodes > 64 * 200
+
+
+def test_root_parallel_search_finds_the_winning_move(core):
+    from gomokuai_b200 import root_parallel as rp
+    b = core.Board()
+    for c in (112, 0, 113, 1, 114, 2, 115, 30):        # black completes five at 111 or 116
+        b.apply_move(c)
+    move, stats, _ = rp.search(b, playouts_total=256 * 60, trees_per_rank=256, c_puct=1.0)
+    assert move in (111, 116)
+    # white to move must block: after black's four is open on both sides every move loses, so just check legality
+    b.apply_move(30 + 15)
+    move, stats, _ = rp.search(b, playouts_total=128 * 20, trees_per_rank=128)
+    assert b.check_move(move)
+
+
+def test_decided_root_returns_empty_statistics(core, kats):
+    b = core.Board()
+    for x, y in kats["black_win"]:
+        b.apply_move(core.Position(x, y))
+    stats = core.RootParallelSearch(trees=8).run(b, 10)
+    assert stats.sum() == 0
