@@ -201,15 +201,29 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch from the committed ncu summary, if one exists (profiles/traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+def ncu_summary(kernel):
+    """Per-launch figures of the committed `ncu --set full` capture of the bench-size launch
+    (profiles/ncu_summary.json: dram bytes, warp instructions, issue-slot utilisation)."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get(kernel)
+            return json.load(open(path)).get(kernel, {})
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
+
+
+def issue_roofline(kernel, launch_ms, sm_mhz, sm_count=148):
+    """Integer-issue roofline (the one that binds): warp instructions of one launch (from the
+    committed ncu capture) / (SMs x 4 schedulers x 1 inst/clk x measured SM clock)."""
+    summ = ncu_summary(kernel)
+    if not summ.get("warp_inst_per_launch") or not sm_mhz:
+        return None
+    peak = sm_count * 4 * sm_mhz * 1e6
+    achieved = summ["warp_inst_per_launch"] / (launch_ms * 1e-3)
+    return {"bound": "int32 issue slots", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s",
+            "frac": achieved / peak, "active_lanes_per_inst": summ.get("threads_per_inst"),
+            "source": "warp instructions per launch from profiles/ncu_summary.json, time and clock measured live"}
 
 
 def run_gpu_arm(args, rank, world, local_rank):
@@ -315,11 +329,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload --------------------------------------
     cpu_eval = cpu_roll = None
     if arm is not None:
-        n_c = 1024 * arm.cores
+        n_c = 6144 * arm.cores                                           # ~4 s per core of evaluator replay
         v, w = arm.run("eval", moves, starts, n_c)
         cpu_eval = {"value": v, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind,
                     "sample": f"first {n_c} of the {n_eval} positions, replayed through Evaluator::applyMove, {w:.1f} s wall"}
-        n_p = 4 * arm.cores
+        n_p = 16 * arm.cores                                             # ~3 s per core of rollouts
         v, w = arm.run("rollout", moves, starts, n_p, 32768)
         cpu_roll = {"value": v, "unit": "rollouts/s", "cores": arm.cores, "kind": arm.kind,
                     "sample": f"first {n_p} positions x 32768 rollouts, {w:.1f} s wall"}
@@ -349,10 +363,11 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "note": "gk_eval_batch_host: pinned host buffers, 3 chunks in flight; the 3.8 GB result copy is PCIe-bound"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": eval_gbs, "peak": peak, "unit": "GB/s", "frac": eval_gbs / peak,
-                     "traffic": ncu_traffic("ac_eval_kernel"), "kernel": "ac_eval_kernel", "peak_source": peak_src,
+                     "traffic": ncu_summary("ac_eval_kernel").get("dram_bytes_per_launch"), "kernel": "ac_eval_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_board": EVAL_BYTES_IN + EVAL_BYTES_OUT,
                      "symbol_steps_per_sec": eval_value / world * EVAL_STEPS_ALGO,
                      "note": "the kernel is integer-issue / shared-memory-latency bound, not HBM bound (SURVEY 8d)"},
+        "roofline_issue": issue_roofline("ac_eval_kernel", eval_ms, clocks.get("sm_mhz")),
         "cpu_baseline": cpu_eval,
         "rollouts": {
             "metric": "rollouts/sec (15x15)", "value": roll_value, "unit": "rollouts/s", "ms_per_step": roll_ms,
@@ -363,9 +378,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                     "h2d_bytes_per_step": n_roll * 64, "d2h_bytes_per_step": n_roll * 12, "ms_per_step": e2e_roll_s * 1e3},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": n_roll * (64 + 12) / (roll_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": n_roll * (64 + 12) / (roll_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("rollout_kernel"),
-                         "kernel": "rollout_kernel",
+                         "frac": n_roll * (64 + 12) / (roll_ms * 1e-3) / 1e9 / peak,
+                         "traffic": ncu_summary("rollout_kernel").get("dram_bytes_per_launch"), "kernel": "rollout_kernel",
                          "note": "compute-bound by construction: 76 algorithmic bytes per position, amortised over 4096 playouts"},
+            "roofline_issue": issue_roofline("rollout_kernel", roll_ms, clocks.get("sm_mhz")),
             "cpu_baseline": cpu_roll,
         },
     }

@@ -27,7 +27,8 @@ namespace gk {
 
 namespace {
 
-constexpr int kWarpsPerCta = 32;
+constexpr int kWarpsPerCta = 32;               // with the default table: 15.9 KB of tables + 32 x 6.5 KB = 223.5 KB of 227 KB
+constexpr size_t kSmemLimit = 227 * 1024;
 constexpr int kQueueCap = 256;                 // words; reused as the compound list (u16 x 450)
 constexpr int kQueueFlush = kQueueCap - 32;    // one step adds at most one entry per lane
 constexpr int kScoreWords = 4 * kCells;        // 900
@@ -126,7 +127,7 @@ __device__ __noinline__ uint32_t scatter_emissions(WarpSmem& ws, const PatRec* s
 // Compound::updateAntis (Pattern.cpp:520-543): rescan the 13-symbol window centred on `cell`
 // from the root state and give +600 (rival's perspective) to the other '_' / '^' cells of the
 // first emission of class `cclass` that has `cell` on a '_'.
-__device__ __forceinline__ void anti_cells(WarpSmem& ws, const uint32_t* s_trans, const PatRec* s_patrec,
+__device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t trans_addr, const PatRec* s_patrec,
                                            int cell, uint32_t dir, uint32_t cclass, int* rival) {
     const int cx = cell % kWidth, cy = cell / kWidth;
     const int stride = dir_stride(dir);
@@ -137,13 +138,18 @@ __device__ __forceinline__ void anti_cells(WarpSmem& ws, const uint32_t* s_trans
     else if (dir == 2) { before = min(cx, cy); after = kWidth - 1 - max(cx, cy); }
     else { before = min(kWidth - 1 - cx, cy); after = min(cx, kHeight - 1 - cy); }
     const int lo = 6 - min(before, 6), hi = 6 + min(after, 6);
-    uint32_t row = 0;                                                           // word index of the current state's row
-#pragma unroll 1
+    // gather the 13 cell values first (independent loads), 2 bits each
+    uint32_t window = 0;
+#pragma unroll
     for (int i = 0; i < 13; ++i) {
         uint32_t v = 3u;
         if (i >= lo && i <= hi) v = cell_value(ws.board, cell + (i - 6) * stride);
-        const uint32_t tw = s_trans[row + v];
-        row = (tw & kDevNextMask) >> 2;
+        window |= v << (2 * i);
+    }
+    uint32_t tw = 0;                                                            // "next" field 0 = root
+#pragma unroll 1
+    for (int i = 0; i < 13; ++i, window >>= 2) {
+        tw = lds_u32(trans_addr + ((tw & kDevNextMask) | ((window & 3u) << 2)));
         if (tw >= kDevEmitFloor) continue;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -226,11 +232,15 @@ ac_eval_kernel(EvalArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem& ws = s_warps[warp];
     const uint32_t lt = lanemask_lt();
-    const uint32_t board_addr = smem_addr(ws.board), trans_addr = smem_addr(s_trans);
-    const uint32_t queue_addr = smem_addr(ws.queue), src_addr = smem_addr(s_src + lane);
+    // shared-window addresses, made opaque so the compiler keeps them in registers instead of
+    // re-deriving them from the CTA's shared base inside the scan loop
+    uint32_t board_addr = smem_addr(ws.board), trans_addr = smem_addr(s_trans);
+    uint32_t queue_addr = smem_addr(ws.queue), src_addr = smem_addr(s_src + lane);
+    asm volatile("" : "+r"(board_addr), "+r"(trans_addr), "+r"(queue_addr), "+r"(src_addr));
     const uint32_t start_tw = a.start_state << 4;                          // a word whose "next" field is the start state
 
-    for (long long b = (long long)blockIdx.x * kWarpsPerCta + warp; b < a.n; b += (long long)gridDim.x * kWarpsPerCta) {
+    const int warps = blockDim.x >> 5;
+    for (long long b = (long long)blockIdx.x * warps + warp; b < a.n; b += (long long)gridDim.x * warps) {
         // ---- phase 0 ---------------------------------------------------------------------------
         uint32_t bw = 0xffffffffu;
         if (lane < kBoardWords) bw = __ldg(a.boards + b * kBoardWords + lane);
@@ -341,7 +351,7 @@ ac_eval_kernel(EvalArgs a) {
                     const uint32_t task = (s & 1) ? tb : ta;
                     if (s < ntask) {
                         const uint32_t black = (task >> 8) & 1u;
-                        anti_cells(ws, s_trans, s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
+                        anti_cells(ws, trans_addr, s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
                                    ws.scores + (black + 1) * kCells);
                     }
                 }
@@ -392,19 +402,31 @@ __global__ void scan_strings_kernel(ScanArgs a) {
 
 }  // namespace
 
-size_t eval_smem_bytes(const EvalArgs& a) {
+static size_t table_smem_bytes(const EvalArgs& a) {
     return size_t((a.n_states * 4 + 3) & ~3) * 4 + size_t((a.n_patterns + 1) & ~1) * sizeof(PatRec) +
-           size_t(a.tape_steps) * 32 * 2 * sizeof(uint16_t) + size_t(kWarpsPerCta) * sizeof(WarpSmem);
+           size_t(a.tape_steps) * 32 * 2 * sizeof(uint16_t);
 }
+
+// warps per CTA: as many as fit beside the tables (32 for the default table; bigger custom tables get fewer)
+static int eval_warps(const EvalArgs& a) {
+    const size_t tables = table_smem_bytes(a);
+    if (tables + sizeof(WarpSmem) > kSmemLimit) return 0;
+    const size_t fit = (kSmemLimit - tables) / sizeof(WarpSmem);
+    return int(fit < size_t(kWarpsPerCta) ? fit : size_t(kWarpsPerCta));
+}
+
+size_t eval_smem_bytes(const EvalArgs& a) { return table_smem_bytes(a) + size_t(eval_warps(a)) * sizeof(WarpSmem); }
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
+    const int warps = eval_warps(a);
+    if (warps == 0) return cudaErrorInvalidConfiguration;                    // table too large for shared memory
     const size_t smem = eval_smem_bytes(a);
     cudaError_t err = cudaFuncSetAttribute(ac_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    const long long want = (a.n + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int grid = (int)(want < sm_count ? want : sm_count);               // persistent: one 32-warp CTA per SM
-    ac_eval_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(a);
+    const long long want = (a.n + warps - 1) / warps;
+    const int grid = (int)(want < sm_count ? want : sm_count);               // persistent: one CTA per SM
+    ac_eval_kernel<<<grid, warps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "gk_format.h"
 #include "gk_kernels.h"
@@ -33,7 +34,7 @@ constexpr int kImageWords = 80;          // 72 slots + meta, 320 B per position
 constexpr int kMetaInfo = 72;            // empties | to_move << 8 | decided << 9 | winner code << 10
 constexpr int kMetaRows = 73;            // rows that still have an empty cell
 constexpr int kThreads = 256;            // per CTA: 256 x 72 x 4 B = 72 KiB of slot state, 3 CTAs per SM
-constexpr int kRefill = 8;               // move steps between refill points (multiple of 4)
+constexpr int kRefillDefault = 8;        // move steps between refill points (multiple of 4)
 constexpr int kTicketBlock = 256;        // consecutive rollouts a CTA claims at a time
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -175,7 +176,7 @@ __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */,
     return result;
 }
 
-template <bool kInjected>
+template <bool kInjected, int kRefill>
 __global__ void __launch_bounds__(kThreads, 3)
 rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots][kThreads]
@@ -313,16 +314,21 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stre
     unsigned long long blocks = (total + kTicketBlock - 1) / kTicketBlock;
     const unsigned long long resident = (unsigned long long)sm_count * 3;
     const int grid = int(blocks < resident ? blocks : resident);
-    if (a.r_stream) {
-        err = cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        rollout_kernel<true><<<grid, kThreads, smem, stream>>>(a, g_images);
-    } else {
-        err = cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        rollout_kernel<false><<<grid, kThreads, smem, stream>>>(a, g_images);
+    int refill = kRefillDefault;
+    if (const char* env = std::getenv("GK_ROLLOUT_REFILL")) refill = std::atoi(env);   // tuning knob (4, 8, 12 or 16)
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, kThreads, smem, stream>>>(a, g_images);
+        return cudaGetLastError();
+    };
+    if (a.r_stream) return launch(rollout_kernel<true, kRefillDefault>);
+    switch (refill) {
+        case 4: return launch(rollout_kernel<false, 4>);
+        case 12: return launch(rollout_kernel<false, 12>);
+        case 16: return launch(rollout_kernel<false, 16>);
+        default: return launch(rollout_kernel<false, kRefillDefault>);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace gk

@@ -1204,3 +1204,124 @@ int orc_eval_scratch_batch(const int16_t* moves, const int64_t* starts, int n_po
     }
     return bad;
 }
+
+/* ======================================================================================
+ * Exhaustive single-line checks behind "incremental replay == from-scratch evaluation"
+ * --------------------------------------------------------------------------------------
+ * The reference updates its state from 13-symbol windows around each move; the CUDA kernel
+ * scans whole lines of the final position.  Because the matcher is not a textbook automaton
+ * (no output links, emissions depend on up to two symbols of left context) the two are equal
+ * only if, for EVERY line content:
+ *   T4  the emissions covering a cell m found in the 13-window around m are exactly (same
+ *       patterns, same positions, same order) those covering m in the scan of the whole line;
+ *   T5  changing cell m does not change any whole-line emission that does not cover m (Five
+ *       emissions excepted: where a run of five-or-more is reported moves with the run's length,
+ *       but a Five only sets the winner and never contributes to scores or totals);
+ * and the compound logic is well defined only if
+ *   T1  no cell has, on one line and for one player, exactly one '_' pattern of a class and
+ *       two or more of a lower-priority class (Compound::locate would yield type -1);
+ *   T2  no cell has three or more '_' patterns of one class on one line (the 2-bit unary
+ *       counters of Record::set would saturate and lose a later removal).
+ * All lines of length 5..max_len over {x, o, blank} are enumerated with the reference's 6/6
+ * padding.  out[0..3] = violations of T1, T2, T4, T5; out[4] = lines, out[5] = emissions,
+ * out[7] = T5-style differences that involve only Five emissions (informational).
+ * T3 (every L3/D3/L2 pattern has >= 2 own stones within distance 3 of each of its '_' cells,
+ * which makes the density gate of updateCompound redundant) is a property of the table:
+ * out[6] = patterns violating it.
+ * ==================================================================================== */
+typedef struct { int pid, end; } em_t;
+
+static int scan_list(const orc_table* tb, const uint8_t* s, int n, em_t* out, int cap) {
+    gen_t g = gen_make(tb, s, n);
+    int c = 0;
+    for (gen_begin(&g); !gen_at_end(&g); gen_next(&g)) {
+        if (c < cap) { out[c].pid = gen_pattern(&g); out[c].end = g.offset; }
+        ++c;
+    }
+    return c;
+}
+static int covers(const orc_table* tb, const em_t* e, int pos) { return e->end >= pos && e->end - pos < tb->pats[e->pid].len; }
+
+int orc_line_theorems(int max_len, long* out) {
+    const orc_table* tb = orc_table_default();
+    memset(out, 0, sizeof(long) * 8);
+    for (int p = 0; p < tb->n_pats; ++p) {                 /* T3 */
+        const pat_t* pt = &tb->pats[p];
+        if (pt->type != T_LIVE3 && pt->type != T_DEAD3 && pt->type != T_LIVE2) continue;
+        char own = pt->favour == P_BLACK ? 'x' : 'o';
+        for (int i = 0; i < pt->len; ++i) {
+            if (pt->str[i] != '_') continue;
+            int near = 0;
+            for (int j = 0; j < pt->len; ++j) if (pt->str[j] == own && abs(i - j) <= 3) ++near;
+            if (near < 2) { out[6] += 1; break; }
+        }
+    }
+    for (int L = 5; L <= max_len; ++L) {
+        long total = 1;
+        for (int i = 0; i < L; ++i) total *= 3;
+        for (long code = 0; code < total; ++code) {
+            uint8_t line[40];
+            int n = 0;
+            long c = code;
+            for (int i = 0; i < 6; ++i) line[n++] = 3;
+            for (int i = 0; i < L; ++i) { int v = (int)(c % 3); c /= 3; line[n++] = (uint8_t)(v == 0 ? 4 : v); }
+            for (int i = 0; i < 6; ++i) line[n++] = 3;
+            em_t full[64];
+            int nf = scan_list(tb, line, n, full, 64);
+            out[4] += 1; out[5] += nf;
+            /* T1 / T2: '_' counts per cell, player, class */
+            int cnt[15][2][3];
+            memset(cnt, 0, sizeof cnt);
+            for (int e = 0; e < nf && e < 64; ++e) {
+                const pat_t* pt = &tb->pats[full[e].pid];
+                int k = pt->type == T_LIVE3 ? 0 : pt->type == T_DEAD3 ? 1 : pt->type == T_LIVE2 ? 2 : -1;
+                if (k < 0) continue;
+                for (int i = 0; i < pt->len; ++i)
+                    if (pt->str[pt->len - 1 - i] == '_') cnt[full[e].end - i - 6][grp1(pt->favour)][k] += 1;
+            }
+            for (int m = 0; m < L; ++m) for (int pg = 0; pg < 2; ++pg) {
+                for (int k = 0; k < 3; ++k) if (cnt[m][pg][k] >= 3) out[1] += 1;
+                for (int k = 0; k < 3; ++k) {
+                    if (cnt[m][pg][k] == 0) continue;
+                    if (cnt[m][pg][k] == 1) for (int k2 = k + 1; k2 < 3; ++k2) if (cnt[m][pg][k2] >= 2) out[0] += 1;
+                    break;
+                }
+            }
+            for (int m = 0; m < L; ++m) {
+                /* T4: window around m (padded index m + 6) vs whole line, emissions covering m, in order */
+                em_t win[32];
+                int nw = scan_list(tb, line + m, ORC_TARGET_LEN, win, 32);
+                int a = 0, b = 0, bad = 0;
+                for (;;) {
+                    while (a < nw && !covers(tb, &win[a], 6)) ++a;
+                    while (b < nf && !covers(tb, &full[b], m + 6)) ++b;
+                    if (a >= nw || b >= nf) { bad = (a < nw) != (b < nf); break; }
+                    if (win[a].pid != full[b].pid || win[a].end + m != full[b].end) { bad = 1; break; }
+                    ++a; ++b;
+                }
+                out[2] += bad;
+                /* T5: change cell m, emissions not covering m must not move */
+                uint8_t keep = line[m + 6];
+                for (int v = 1; v <= 4; ++v) {
+                    if (v == 3 || v == keep) continue;
+                    line[m + 6] = (uint8_t)v;
+                    em_t alt[64];
+                    int na = scan_list(tb, line, n, alt, 64);
+                    for (int five = 0; five < 2; ++five) {           /* pass 0: all but Five, pass 1: Five only */
+                        int i = 0, j = 0, diff = 0;
+                        for (;;) {
+                            while (i < nf && (covers(tb, &full[i], m + 6) || (tb->pats[full[i].pid].type == T_FIVE) != five)) ++i;
+                            while (j < na && (covers(tb, &alt[j], m + 6) || (tb->pats[alt[j].pid].type == T_FIVE) != five)) ++j;
+                            if (i >= nf || j >= na) { diff = (i < nf) != (j < na); break; }
+                            if (full[i].pid != alt[j].pid || full[i].end != alt[j].end) { diff = 1; break; }
+                            ++i; ++j;
+                        }
+                        out[five ? 7 : 3] += diff;
+                    }
+                }
+                line[m + 6] = keep;
+            }
+        }
+    }
+    return 0;
+}

@@ -66,6 +66,9 @@ int orc_eval_scratch_batch(const int16_t* moves, const int64_t* starts, int n_po
                            int32_t* scores, uint16_t* pat_totals, uint16_t* cmp_totals, int8_t* winner);
 long orc_scratch_gate_blocks(void);
 
+/* ---- exhaustive single-line checks (see gomoku_oracle.c) ---- */
+int orc_line_theorems(int max_len, long* out8);
+
 /* ---- board / rollout ---- */
 int orc_board_play(const int16_t* moves, int n_moves, int* out3);
 int orc_rollout_injected(const int16_t* moves, int n_moves, const uint8_t* r_stream, int stream_len,

@@ -199,3 +199,17 @@ def test_philox_known_answer(port):
     # Random123 kat_vectors: philox4x32-10, counter 0 / key 0 and the all-ones vector
     assert port.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert port.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+def test_exhaustive_single_line_theorems(port):
+    """Every line of length 5..10 over {x, o, blank}: the facts that make a from-scratch evaluation of
+    the final position equal to the reference's incremental replay (oracle/gomoku_oracle.c,
+    orc_line_theorems).  The same enumeration up to length 15 (all lines a board can hold) was run
+    once while writing DESIGN.md section 2.2."""
+    import ctypes
+    out = (ctypes.c_long * 8)()
+    port.lib.orc_line_theorems(10, out)
+    t1, t2, t4, t5, lines, emissions, t3, five_moves = list(out)
+    assert lines == sum(3 ** n for n in range(5, 11)) and emissions > 50000
+    assert (t1, t2, t3, t4, t5) == (0, 0, 0, 0, 0)
+    assert five_moves > 0          # Five emissions do move with the run length (they only set the winner)
