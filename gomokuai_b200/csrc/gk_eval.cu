@@ -151,6 +151,7 @@ __device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t trans_addr, co
     for (int i = 0; i < 13; ++i, window >>= 2) {
         tw = lds_u32(trans_addr + ((tw & kDevNextMask) | ((window & 3u) << 2)));
         if (tw >= kDevEmitFloor) continue;
+        if (dw_cclass0(tw) != cclass && dw_pid(tw, 1) == kDevNoPid) continue;   // wrong class, no second emission: cheap reject
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t pid = dw_pid(tw, k);

@@ -43,7 +43,8 @@ GK_HD inline uint32_t em_prev(uint32_t e) { return (e >> 9) & 1u; }
 //      The fields are placed so that the scan loop's dependent chain is "LDS, one LOP3, LDS":
 //   [ 0]    emission 0 is "at previous symbol"
 //   [ 1]    emission 1 is "at previous symbol"
-//   [ 2, 4) zero
+//   [ 2, 4) compound class of emission 0's pattern (0 none, 1 LiveThree, 2 DeadThree, 3 LiveTwo): lets the
+//           13-symbol window rescans skip emissions of the wrong class without loading the pattern record
 //   [ 4,14) next state, i.e. (word & 0x3ff0) is the BYTE offset of the next state's row
 //   [14,23) emission 1 pattern id, 0x1ff = none
 //   [23,32) emission 0 pattern id, 0x1ff = none  (so: word >= kDevEmitFloor  <=>  no emission)
@@ -55,6 +56,7 @@ constexpr uint32_t kDevEmitMask = 0xffffc003u;    // the bits of a device word t
 GK_HD inline int sym_to_value(int sym) { return (sym + 1) & 3; }   // table symbol index -> raw cell value
 GK_HD inline uint32_t dw_pid(uint32_t w, int k) { return (w >> (23 - 9 * k)) & 0x1ffu; }
 GK_HD inline uint32_t dw_prev(uint32_t w, int k) { return (w >> k) & 1u; }
+GK_HD inline uint32_t dw_cclass0(uint32_t w) { return (w >> 2) & 3u; }
 
 // ---- device pattern record: 2 words per pattern ---------------------------------------------------
 //   w0 [ 0,16) up to four scored cells, one nibble each: bits 0..2 = j (cell is the j-th char from

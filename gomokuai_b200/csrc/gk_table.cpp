@@ -426,6 +426,10 @@ bool compile_table(const std::vector<Proto>& protos, HostTable& t) {
                 d |= (has ? em_pid(tw_emit(w, k)) : kDevNoPid) << (23 - 9 * k);
                 d |= (has ? em_prev(tw_emit(w, k)) : 0u) << k;
             }
+            if (tw_nemit(w) > 0) {
+                const int type = t.patterns[em_pid(tw_emit(w, 0))].type;
+                d |= static_cast<uint32_t>(type == 5 ? 1 : type == 4 ? 2 : type == 3 ? 3 : 0) << 2;
+            }
             t.dev_trans[static_cast<size_t>(id) * 4 + sym_to_value(sym)] = d;
         }
     // How many symbols until the state forgets where it started (0: it never does).  Informational:

@@ -1,0 +1,21 @@
+"""Tiny end-to-end run of every kernel (for compute-sanitizer)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gomokuai_b200 as gk
+from oracle import pyoracle as po
+gk.init(0)
+P = po.port()
+boards, moves, starts = gk.synth_positions(0, 600)
+ref = P.eval_batch(moves, starts)
+out = gk.eval_batch(boards); torch.cuda.synchronize()
+assert np.array_equal(out["scores"].cpu().numpy(), ref["scores"])
+wn, ln, wdb = P.rollout_philox_batch(moves[:starts[8]], starts[:9], 40, 5)
+r = gk.rollout_batch(boards[:8], 40, key=5, want_trace=True); torch.cuda.synchronize()
+assert np.array_equal(r["winners"].cpu().numpy(), wn) and np.array_equal(r["wdb"].cpu().numpy(), wdb)
+rs = np.random.default_rng(0).integers(0, 225, size=(8, 3, 230)).astype(np.uint8)
+gk.rollout_injected(boards[:8], rs); torch.cuda.synchronize()
+codes = np.array([3, 4, 1, 1, 1, 4, 2, 3, 3], np.uint8)
+gk.scan_batch(codes, np.array([0, 9], np.int64)); torch.cuda.synchronize()
+print("small ok")
