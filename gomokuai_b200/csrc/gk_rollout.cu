@@ -14,7 +14,7 @@
 // Legal-move selection works on the row slots plus a 15-bit "row still has an empty cell" mask
 // kept in a register: at most two shared-memory probes per move, no loop.
 //
-// Threads are persistent: a finished lane waits for the next refill point (every kRefill
+// Threads are persistent: a finished lane waits for the next refill point (every kRefill = 12
 // steps, a multiple of 4 so that all lanes draw a fresh Philox4x32-10 block on the same steps),
 // takes the next rollout ticket and re-copies the position's 72-word slot image.
 #include <cuda_runtime.h>
@@ -33,8 +33,8 @@ constexpr int kSlots = 72;
 constexpr int kImageWords = 80;          // 72 slots + meta, 320 B per position
 constexpr int kMetaInfo = 72;            // empties | to_move << 8 | decided << 9 | winner code << 10
 constexpr int kMetaRows = 73;            // rows that still have an empty cell
-constexpr int kThreads = 256;            // per CTA: 256 x 72 x 4 B = 72 KiB of slot state, 3 CTAs per SM
-constexpr int kRefillDefault = 8;        // move steps between refill points (multiple of 4)
+constexpr int kThreads = 256;            // per CTA: 256 x 73 x 4 B = 73 KiB of slot state, 3 CTAs per SM
+constexpr int kRefillDefault = 12;       // move steps between refill points (multiple of 4)
 constexpr int kTicketBlock = 256;        // consecutive rollouts a CTA claims at a time
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -121,6 +121,14 @@ struct Lane {
     uint32_t pos, roll;    // position index (batch-local), rollout index within the position
 };
 
+// raw five-in-a-row detector on a whole slot word: bit i of the result is set iff bits i..i+4 are.
+// Bit 15 of a slot is always 0, so runs never leak between the black half and the white half.
+__device__ __forceinline__ uint32_t five_bits(uint32_t v) {
+    uint32_t t = v & (v >> 1);
+    t &= t >> 2;
+    return t & (v >> 4);
+}
+
 // One move of an active rollout.  Returns 0 = game goes on, 1 = black won, 2 = white won, 3 = draw.
 __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */, Lane& L, uint32_t r) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
@@ -139,38 +147,37 @@ __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */,
     w |= 1u << (x + sh);
     my[y * kThreads] = w;
     if (((w | (w >> 16)) & 0x7fffu) == 0x7fffu) L.rowmask &= ~(1u << y);
-    bool five = has_five((w >> sh) & 0x7fffu);
+    uint32_t fives = five_bits(w);
     // column
     {
         uint32_t* p = my + (15u + x) * kThreads;
         const uint32_t v = *p | (1u << (y + sh));
         *p = v;
-        five = five || has_five((v >> sh) & 0x7fffu);
+        fives |= five_bits(v);
     }
-    // diagonal (+1,+1): x - y = k, k in [-10, 10]
+    // diagonal (+1,+1): x - y = k, k in [-10, 10]; cells on shorter diagonals use the scratch slot, where
+    // the same bit is set over and over and can never form a run
     {
-        const int k = int(x) - int(y) + 10;
-        if (k >= 0 && k <= 20) {
-            uint32_t* p = my + (30 + k) * kThreads;
-            const uint32_t v = *p | (1u << (min(x, y) + sh));
-            *p = v;
-            five = five || has_five((v >> sh) & 0x7fffu);
-        }
+        const uint32_t k = x - y + 10u;
+        const bool ok = k <= 20u;
+        uint32_t* p = my + (ok ? 30u + k : uint32_t(kSlots)) * kThreads;
+        const uint32_t v = *p | (1u << ((ok ? min(x, y) : 0u) + sh));
+        *p = v;
+        fives |= five_bits(v);
     }
     // anti-diagonal (-1,+1): x + y = s, s in [4, 24]
     {
-        const int s = int(x + y) - 4;
-        if (s >= 0 && s <= 20) {
-            uint32_t* p = my + (51 + s) * kThreads;
-            const uint32_t v = *p | (1u << (min(14u - x, y) + sh));
-            *p = v;
-            five = five || has_five((v >> sh) & 0x7fffu);
-        }
+        const uint32_t s = x + y - 4u;
+        const bool ok = s <= 20u;
+        uint32_t* p = my + (ok ? 51u + s : uint32_t(kSlots)) * kThreads;
+        const uint32_t v = *p | (1u << ((ok ? min(14u - x, y) : 0u) + sh));
+        *p = v;
+        fives |= five_bits(v);
     }
     L.moves += 1;
     L.empties -= 1;
     uint32_t result = 0;
-    if (five) result = 1u + L.colour;                                            // winner = player of the last stone, Game.cpp:125-128
+    if (fives & (0x7fffu << sh)) result = 1u + L.colour;                         // winner = player of the last stone, Game.cpp:125-128
     else if (L.empties == 0) result = 3u;                                        // Game.cpp:129-132
     L.colour ^= 1u;
     return result;
@@ -179,13 +186,14 @@ __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */,
 template <bool kInjected, int kRefill>
 __global__ void __launch_bounds__(kThreads, 3)
 rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
-    extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots][kThreads]
+    extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots + 1][kThreads]
     __shared__ uint32_t s_ticket;
     if (threadIdx.x == 0) s_ticket = 0;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     uint32_t* my = s_slots + threadIdx.x;
+    my[kSlots * kThreads] = 0;                                                   // scratch slot: must never hold a run
     const uint32_t total = uint32_t(a.n) * uint32_t(a.rollouts_per_pos);
 
     Lane L{};
@@ -309,7 +317,7 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stre
         err = cudaMemsetAsync(a.wdb, 0, size_t(a.n) * 3 * sizeof(int32_t), stream);
         if (err != cudaSuccess) return err;
     }
-    const size_t smem = size_t(kSlots) * kThreads * sizeof(uint32_t);
+    const size_t smem = size_t(kSlots + 1) * kThreads * sizeof(uint32_t);   // + one scratch slot per thread
     const unsigned long long total = (unsigned long long)a.n * a.rollouts_per_pos;
     unsigned long long blocks = (total + kTicketBlock - 1) / kTicketBlock;
     const unsigned long long resident = (unsigned long long)sm_count * 3;
@@ -325,7 +333,7 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stre
     if (a.r_stream) return launch(rollout_kernel<true, kRefillDefault>);
     switch (refill) {
         case 4: return launch(rollout_kernel<false, 4>);
-        case 12: return launch(rollout_kernel<false, 12>);
+        case 8: return launch(rollout_kernel<false, 8>);
         case 16: return launch(rollout_kernel<false, 16>);
         default: return launch(rollout_kernel<false, kRefillDefault>);
     }
