@@ -284,6 +284,34 @@ def rollout_injected(boards, r_stream, stream=None):
     return {"winners": winners, "lengths": lengths}
 
 
+def encode_states_batch(boards, last_moves=None, augment=False, probs=None, stream=None):
+    """Board.encoded_states() for a batch (core/py_ext/src/game_ext.hpp:87-104) and, with augment=True,
+    the 8 rotations / reflections of augment_game_data (network/data_helper.py:36-55).
+    last_moves: int16[n,2] = (last, second-to-last) cell ids, -1 = none.  probs: float32[n,225] (optional).
+    Returns planes uint8[n,V,6,15,15] (V = 8 or 1) and, if probs is given, float32[n,V,225]."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    n, dev, V = boards.shape[0], boards.device, (8 if augment else 1)
+    if last_moves is not None:
+        if isinstance(last_moves, np.ndarray):
+            last_moves = torch.from_numpy(np.ascontiguousarray(last_moves, np.int16))
+        last_moves = last_moves.to(dev).contiguous()
+        if last_moves.dtype != torch.int16 or tuple(last_moves.shape) != (n, 2):
+            raise GomokuB200Error("last_moves must be int16[n, 2]")
+    probs_out = None
+    if probs is not None:
+        if isinstance(probs, np.ndarray):
+            probs = torch.from_numpy(np.ascontiguousarray(probs, np.float32))
+        probs = probs.to(dev).contiguous()
+        if probs.dtype != torch.float32 or tuple(probs.shape) != (n, CELLS):
+            raise GomokuB200Error("probs must be float32[n, 225]")
+        probs_out = torch.empty((n, V, CELLS), dtype=torch.float32, device=dev)
+    planes = torch.empty((n, V, 6, 15, 15), dtype=torch.uint8, device=dev)
+    _check(lib().gk_encode_states_batch(_ptr(boards), _ptr(last_moves), n, int(bool(augment)), _ptr(planes),
+                                        _ptr(probs), _ptr(probs_out), _stream_ptr(stream)))
+    return (planes, probs_out) if probs is not None else planes
+
+
 def scan_batch(codes, starts, table=None, max_per_string=16, stream=None):
     """PatternSearch::matches for a batch of symbol strings (codes 1..4). Returns (pids, offsets, counts)."""
     torch = _torch()

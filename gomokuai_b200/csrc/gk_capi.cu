@@ -390,6 +390,17 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
     return GK_OK;
 }
 
+// ---- feature planes ----------------------------------------------------------------------------------------
+gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last_moves, int n, int augment,
+                                 uint8_t* d_planes, const float* d_probs, float* d_probs_out, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (n < 0 || (n > 0 && (!d_boards || !d_planes)) || (d_probs && !d_probs_out))
+        return fail(GK_ERR_INVALID, "bad arguments");
+    gk::EncodeArgs a{ d_boards, d_last_moves, n, augment ? 1 : 0, d_planes, d_probs, d_probs_out };
+    GK_CUDA(gk::launch_encode(a, g_sm_count, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
 // ---- host utilities ------------------------------------------------------------------------------------
 gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards) {
     if (!moves || !starts || !h_boards || n < 0) return fail(GK_ERR_INVALID, "bad arguments");

@@ -37,4 +37,12 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stre
 // number of kernels one launch_rollout call enqueues (wdb clear + rollout)
 int rollout_launches(const RolloutArgs& a);
 
+struct EncodeArgs {
+    const uint32_t* boards; const int16_t* last_moves;   // last_moves: [n][2] = last, second-to-last (-1 = none); may be null
+    long long n; int augment;                             // augment: 0 = one variant, 1 = the 8 rotations / reflections
+    uint8_t* planes;                                      // [n][variants][6][225]
+    const float* probs; float* probs_out;                 // optional: [n][225] -> [n][variants][225]
+};
+cudaError_t launch_encode(const EncodeArgs& a, int sm_count, cudaStream_t stream);
+
 }  // namespace gk

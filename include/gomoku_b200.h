@@ -126,6 +126,19 @@ gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_
                               const uint8_t* d_r_stream, int stream_stride,
                               int8_t* d_winners, uint8_t* d_lengths, void* stream);
 
+/* ---- self-play feature planes ("next" row f3 of SURVEY.md section 8) ------------------
+ * Replaces Board.encoded_states() of CorePyExt (core/py_ext/src/game_ext.hpp:87-104) for a batch,
+ * and, with augment != 0, augment_game_data's 8 rotations / reflections of the planes
+ * (network/data_helper.py:36-55; order: for i in 0..3: rot90(i), fliplr(rot90(i))).
+ * d_last_moves: int16[n][2] = {last move, second-to-last move} as cell ids, -1 = none; NULL = none.
+ * d_planes: uint8[n][V][6][15][15], V = 8 if augment else 1 (no alignment requirement).
+ * Planes: stones of the side to move, stones of the opponent, empty cells, last move, second-to-last
+ * move (one-hot), all-ones iff black is to move.
+ * d_probs (nullable): float[n][225] move probabilities; d_probs_out: float[n][V][225] receives them
+ * under the same rotations / reflections (augment_game_data's rot_probs / flip_probs). */
+gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last_moves, int n, int augment,
+                                 uint8_t* d_planes, const float* d_probs, float* d_probs_out, void* stream);
+
 /* ---- host utilities (no GPU needed) ------------------------------------------------- */
 /* move lists (black first, alternating; position i = moves[starts[i]..starts[i+1])) -> packed boards */
 gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards);

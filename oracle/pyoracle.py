@@ -187,6 +187,40 @@ class Oracle:
         return w, n.value
 
 
+# ---- self-play feature planes (row f3): numpy restatements --------------------------------------------
+def encoded_states(move_list):
+    """Board.encoded_states() (core/py_ext/src/game_ext.hpp:87-104): uint8[6,15,15] =
+    [stones of the side to move, opponent's stones, empty cells, last move, second-to-last move,
+    all-ones iff black is to move].  Black moves first and players alternate (Game.cpp:37-47)."""
+    cells = np.zeros(225, np.int8)
+    for k, c in enumerate(move_list):
+        cells[c] = 1 if k % 2 == 0 else -1                    # Player::Black = 1, White = -1 (Game.h)
+    cur = 1 if len(move_list) % 2 == 0 else -1
+    out = np.zeros((6, 225), np.uint8)
+    out[0] = cells == cur                                     # :91-93 moveStates(m_curPlayer)
+    out[1] = cells == -cur                                    #        moveStates(-m_curPlayer)
+    out[2] = cells == 0                                       #        moveStates(Player::None)
+    for i in (0, 1):                                          # :94-100 one-hot of the last two moves
+        if len(move_list) > i:
+            out[3 + i, move_list[-1 - i]] = 1
+    out[5] = cur == 1                                         # :101
+    return out.reshape(6, 15, 15)
+
+
+def augment_planes(states, probs):
+    """augment_game_data (network/data_helper.py:36-55) for one sample: the 8 variants in the
+    reference's order -- for i in 0..3: rot90(i), fliplr(rot90(i)).  -> (uint8[8,6,15,15], f32[8,225])"""
+    st, pr = [], []
+    for i in range(4):
+        rs = np.array([np.rot90(plane, i) for plane in states])
+        rp = np.rot90(probs.reshape(15, 15), i)
+        st.append(rs)
+        pr.append(rp.flatten())
+        st.append(np.array([np.fliplr(plane) for plane in rs]))
+        pr.append(np.fliplr(rp).flatten())
+    return np.stack(st), np.stack(pr)
+
+
 class PortOracle(Oracle):
     """extras only the C restatement has (Philox stream, apply/revert, degenerate counter)"""
 
@@ -243,6 +277,12 @@ class PortOracle(Oracle):
 class RefOracle(Oracle):
     def __init__(self):
         super().__init__(REF_SO, "ref_", "reference")
+
+    def encoded_states(self, moves):
+        mv = np.ascontiguousarray(moves, np.int16)
+        out = np.zeros((6, 15, 15), np.uint8)
+        self.lib.ref_encoded_states(_p(mv), len(mv), _p(out))
+        return out
 
     def rollout_free(self, moves, n_rollouts):
         mv = np.ascontiguousarray(moves, np.int16)

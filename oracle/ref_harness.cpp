@@ -6,8 +6,10 @@
 // links them with this file into oracle/_ref/libgomoku_ref.so.  Everything the
 // harness computes is computed by the reference's Board / BoardMap / PatternSearch /
 // Evaluator; the only logic restated here is
-//   * the 4-line loop of Default::RandomRollout (algorithms/MonteCarlo.hpp:37-47) and
-//   * the 4-line probe loop of Board::getRandomMove (Game.cpp:68-71),
+//   * the 4-line loop of Default::RandomRollout (algorithms/MonteCarlo.hpp:37-47),
+//   * the 4-line probe loop of Board::getRandomMove (Game.cpp:68-71) and
+//   * the plane-filling lambda of Board.encoded_states (core/py_ext/src/game_ext.hpp:87-104; the
+//     pybind module itself needs pybind11/eigen.h, i.e. real Eigen),
 // because MonteCarlo.hpp needs float Eigen algebra the shim does not provide and the
 // reference's RNG (`static mt19937 rnd_eng`, Game.cpp:11-12) cannot be seeded or fed
 // from outside.  Private members are reached exactly the way the reference's own unit
@@ -323,6 +325,28 @@ int ref_rollout_free(const int16_t* moves, int n_moves, int n_rollouts, int64_t*
         *total_moves += total;
         b.revertMove((size_t)total);
     }
+    return 0;
+}
+
+// Board.encoded_states() (core/py_ext/src/game_ext.hpp:87-104) over the reference's Board: planes
+// [stones of the side to move, opponent's, empty, last move, second-to-last move, black to move].
+// Moves are replayed without victory checks so that any position can be encoded.
+int ref_encoded_states(const int16_t* moves, int n_moves, uint8_t* out /*6*225*/) {
+    Board b;
+    for (int i = 0; i < n_moves; ++i) b.applyMove(Position(moves[i]), false);
+    int index = 0;
+    for (auto player : { b.m_curPlayer, -b.m_curPlayer, Player::None }) {
+        for (int c = 0; c < BOARD_SIZE; ++c) out[index * BOARD_SIZE + c] = b.moveState(player, c) ? 1 : 0;
+        ++index;
+    }
+    for (int i = 0; i <= 1; ++index, ++i) {
+        std::memset(out + index * BOARD_SIZE, 0, BOARD_SIZE);
+        if ((int)b.m_moveRecord.size() > i) {
+            auto position = *(b.m_moveRecord.rbegin() + i);
+            out[index * BOARD_SIZE + position.y() * WIDTH + position.x()] = 1;
+        }
+    }
+    std::memset(out + index * BOARD_SIZE, b.m_curPlayer == Player::Black, BOARD_SIZE);
     return 0;
 }
 
