@@ -118,6 +118,18 @@ class Table:
         return out.reshape(n, 4)
 
 
+    def device_format(self):
+        """The automaton as the eval kernel reads it (csrc/gk_format.h): dict(next[n_rows,4] u16 row offsets
+        indexed by raw cell value, erec[n_clones] u32, n_clones, root_off, start_off, list_cap, tape_steps)."""
+        info = (ctypes.c_int * 6)()
+        _check(lib().gk_table_device_format(self._h, info, None, 0, None, 0))
+        nxt = np.zeros(info[0] * 4, np.uint16)
+        erec = np.zeros(max(info[1], 1), np.uint32)
+        _check(lib().gk_table_device_format(self._h, info, nxt.ctypes.data_as(ctypes.c_void_p), nxt.size,
+                                            erec.ctypes.data_as(ctypes.c_void_p), erec.size))
+        return {"next": nxt.reshape(-1, 4), "erec": erec[:info[1]], "n_clones": info[1], "root_off": info[2],
+                "start_off": info[3], "list_cap": info[4], "tape_steps": info[5]}
+
     def flush(self):
         """Per state: pattern id owed when the input ends there (-1 = none)."""
         n = self.info()["n_states"]

@@ -16,7 +16,8 @@
 struct gk_table {
     gk::HostTable host;
     uint32_t* d_trans = nullptr;       // host-format words (scan kernel)
-    uint32_t* d_dev_trans = nullptr;   // device-format words (eval kernel)
+    uint16_t* d_next16 = nullptr;      // device-format automaton (eval kernel)
+    uint32_t* d_erec = nullptr;
     gk::PatRec* d_patrec = nullptr;
     uint16_t* d_tape_src = nullptr;
     uint16_t* d_tape_info = nullptr;
@@ -55,7 +56,8 @@ gk_status to_device(T** dst, const std::vector<T>& src) {
 
 gk_status upload(gk_table* t) {
     const gk::HostTable& h = t->host;
-    if (gk_status s = to_device(&t->d_dev_trans, h.dev_trans)) return s;
+    if (gk_status s = to_device(&t->d_next16, h.dev_next)) return s;
+    if (gk_status s = to_device(&t->d_erec, h.dev_erec)) return s;
     if (gk_status s = to_device(&t->d_patrec, h.patrec)) return s;
     if (gk_status s = to_device(&t->d_tape_src, h.tape_src)) return s;
     if (gk_status s = to_device(&t->d_tape_info, h.tape_info)) return s;
@@ -74,10 +76,10 @@ gk_status ensure_uploaded(const gk_table* ct) {
 gk::EvalArgs eval_args(const gk_table* t, const uint32_t* boards, long long n, int32_t* scores, uint16_t* pat,
                        uint16_t* cmp, int8_t* winner) {
     gk::EvalArgs a{};
-    a.trans = t->d_dev_trans; a.n_states = t->host.n_states;
+    a.next16 = t->d_next16; a.erec = t->d_erec; a.n_states = t->host.n_states; a.n_clones = t->host.n_clones;
     a.patrec = t->d_patrec; a.n_patterns = (int)t->host.patrec.size();
     a.tape_src = t->d_tape_src; a.tape_info = t->d_tape_info; a.tape_steps = t->host.tape_steps;
-    a.start_state = (uint32_t)t->host.start_state;
+    a.root_off = t->host.root_off; a.start_off = t->host.start_off; a.list_cap = t->host.list_cap;
     a.boards = boards; a.n = n;
     a.scores = scores; a.pat_totals = pat; a.cmp_totals = cmp; a.winner = winner;
     return a;
@@ -253,7 +255,7 @@ gk_status gk_table_build(const char* const* protos, const int* types, const int*
 
 gk_status gk_table_free(gk_table* t) {
     if (!t || t->is_default) return GK_OK;
-    cudaFree(t->d_trans); cudaFree(t->d_dev_trans); cudaFree(t->d_patrec); cudaFree(t->d_tape_src);
+    cudaFree(t->d_trans); cudaFree(t->d_next16); cudaFree(t->d_erec); cudaFree(t->d_patrec); cudaFree(t->d_tape_src);
     cudaFree(t->d_tape_info); cudaFree(t->d_flush);
     delete t;
     return GK_OK;
@@ -287,6 +289,23 @@ gk_status gk_table_entries(const gk_table* t, uint32_t* h_entries, int capacity)
 gk_status gk_table_flush(const gk_table* t, int16_t* h_flush, int capacity) {
     if (!t || !h_flush || capacity < (int)t->host.flush.size()) return fail(GK_ERR_INVALID, "buffer too small");
     std::memcpy(h_flush, t->host.flush.data(), t->host.flush.size() * sizeof(int16_t));
+    return GK_OK;
+}
+
+gk_status gk_table_device_format(const gk_table* t, int info[6], uint16_t* h_next, int next_capacity, uint32_t* h_erec,
+                                 int erec_capacity) {
+    if (!t || !info) return fail(GK_ERR_INVALID, "bad arguments");
+    const gk::HostTable& h = t->host;
+    info[0] = h.n_clones + h.n_states; info[1] = h.n_clones; info[2] = h.root_off; info[3] = h.start_off;
+    info[4] = h.list_cap; info[5] = h.tape_steps;
+    if (h_next) {
+        if (next_capacity < (int)h.dev_next.size()) return fail(GK_ERR_INVALID, "buffer too small");
+        std::memcpy(h_next, h.dev_next.data(), h.dev_next.size() * sizeof(uint16_t));
+    }
+    if (h_erec) {
+        if (erec_capacity < (int)h.dev_erec.size()) return fail(GK_ERR_INVALID, "buffer too small");
+        std::memcpy(h_erec, h.dev_erec.data(), h.dev_erec.size() * sizeof(uint32_t));
+    }
     return GK_OK;
 }
 

@@ -51,15 +51,18 @@ encode_states_kernel(EncodeArgs a) {
         const int nb = __reduce_add_sync(0xffffffffu, blk), nw = __reduce_add_sync(0xffffffffu, wht);
         const uint32_t mine = nb == nw ? 1u : 2u;
         const int last1 = a.last_moves ? a.last_moves[b * 2] : -1, last2 = a.last_moves ? a.last_moves[b * 2 + 1] : -1;
-        for (int c = lane; c < kCells; c += 32) {
-            const uint32_t word = __shfl_sync(0xffffffffu, w, c >> 4);
+        for (int c0 = 0; c0 < kCells; c0 += 32) {                          // warp-uniform trip count (shuffles inside)
+            const int c = c0 + lane;
+            const uint32_t word = __shfl_sync(0xffffffffu, w, (c >> 4) & 15);
             const uint32_t val = (word >> ((c & 15) * 2)) & 3u;
-            base[c] = val == mine;
-            base[kCells + c] = val == (3u - mine);
-            base[2 * kCells + c] = val == 0u;
-            base[3 * kCells + c] = c == last1;
-            base[4 * kCells + c] = c == last2;
-            base[5 * kCells + c] = mine == 1u;
+            if (c < kCells) {
+                base[c] = val == mine;
+                base[kCells + c] = val == (3u - mine);
+                base[2 * kCells + c] = val == 0u;
+                base[3 * kCells + c] = c == last1;
+                base[4 * kCells + c] = c == last2;
+                base[5 * kCells + c] = mine == 1u;
+            }
         }
         __syncwarp();
         // the position's output range need not be 16-byte aligned (1350 = 84 x 16 + 6): byte-wise head up

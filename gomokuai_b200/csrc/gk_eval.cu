@@ -3,14 +3,19 @@
 // Replaces, for a batch, Evaluator::applyMove replay + read-out of m_scores / totals
 // (reference src/Pattern.cpp:128-302,418-550; semantics restated in SURVEY.md Appendix A).
 //
-//   phase 0  load the 64-byte board, pad cells = 3, clear the warp's shared-memory accumulators
+//   phase 0  load the 64-byte board (one word per lane, kept in registers), clear the warp's
+//            shared-memory accumulators
 //   phase 1  stone-density block score (+160 where a player has a stone on a weighted offset of
 //            the 7x7 neighbourhood, Pattern.cpp:236-272,598-609) from 15-bit row masks
-//   phase 2  the Aho-Corasick scan: 32 lanes walk their chains of whole lines in lock step, one
-//            dependent shared-memory table lookup per symbol; emitting (lane, step) pairs are
-//            compacted with ballot/popc into a shared queue
-//   phase 3  emission scatter: lanes take queue entries, add pattern scores to the '_' / '^' cells
-//            (shared-memory atomics), bump totals, set the saturating per-cell flags
+//   phase 2  the Aho-Corasick scan: 32 lanes walk their chains of whole lines in lock step; per
+//            symbol: tape entry, board word by warp shuffle, rotate, ONE dependent 16-bit table
+//            load.  A step that emitted appends one 16-bit entry to the lane's private list
+//            (predicated store, no votes); the lists cannot overflow (capacity proven by the
+//            table compiler over all boards)
+//   phase 3  emission scatter: the lists are concatenated by a prefix sum and entry i of the
+//            concatenation goes to lane i % 32 (binary search over 32 prefix counts), so the
+//            work is balanced whatever lines the stones sit on; pattern scores go to the '_' / '^'
+//            cells with shared-memory atomics, totals are bumped, saturating per-cell flags set
 //   phase 4  compounds (double-three / four-three / double-four, Pattern.cpp:418-550) from the flags;
 //            the 13-symbol window rescans of Compound::updateAntis are spread one per lane
 //   phase 5  coalesced 128-bit store of the four 225-cell score maps + totals + winner
@@ -27,21 +32,21 @@ namespace gk {
 
 namespace {
 
-constexpr int kWarpsPerCta = 32;               // with the default table: 15.9 KB of tables + 32 x 6.5 KB = 223.5 KB of 227 KB
+constexpr int kWarpsPerCta = 32;
 constexpr size_t kSmemLimit = 227 * 1024;
-constexpr int kQueueCap = 256;                 // words; reused as the compound list (u16 x 450)
-constexpr int kQueueFlush = kQueueCap - 32;    // one step adds at most one entry per lane
 constexpr int kScoreWords = 4 * kCells;        // 900
 constexpr int kFlagWords = 2 * kCells + 2;     // 452 (16-byte multiple)
 constexpr int kBoardSmem = 20;                 // 17 words used (cells up to 271 read as pad)
 constexpr int kTotalWords = 24;                // 16 pattern + 6 compound + spare
+constexpr int kPrefixHalves = 40;              // 33 used: prefix[j] = emissions held by lanes < j
 
+// Per-warp shared-memory block; the emission lists (32 lanes x list_cap uint16) follow it.
 struct WarpSmem {
     int scores[kScoreWords];                   // [group][cell]
     uint32_t flags[kFlagWords];                // [cell][player grp]: 3 classes x 4 dirs x 2-bit unary count
-    uint32_t queue[kQueueCap];
     uint32_t board[kBoardSmem];
     uint32_t totals[kTotalWords];
+    uint16_t prefix[kPrefixHalves];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp block must keep 16-byte alignment");
 
@@ -53,18 +58,13 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 // 32-bit shared-window addressing for the scan loop (keeps the generic->shared conversion out of it)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t v;
     asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" :: "r"(addr), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ uint32_t cell_value(const uint32_t* board, uint32_t cell) {
@@ -108,26 +108,11 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, const PatRec re
     return 0;
 }
 
-// phase 3: apply queue[0 .. n) to the accumulators.
-__device__ __noinline__ uint32_t scatter_emissions(WarpSmem& ws, const PatRec* s_patrec, const uint16_t* s_info,
-                                                   int n, int lane) {
-    uint32_t win = 0;
-    for (int i = lane; i < n; i += 32) {
-        const uint32_t ent = ws.queue[i];
-        const uint32_t inf = s_info[(ent >> 2) & 0x7ffu];                       // index = step * 32 + lane
-        const uint32_t dir = inf >> 9;
-        const int vcell = inf & 0x1ff, stride = dir_stride(dir);
-        win |= apply_emission(ws, s_patrec[dw_pid(ent, 0)], vcell - int(dw_prev(ent, 0)) * stride, dir);
-        const uint32_t p1 = dw_pid(ent, 1);
-        if (p1 != kDevNoPid) win |= apply_emission(ws, s_patrec[p1], vcell - int(dw_prev(ent, 1)) * stride, dir);
-    }
-    return win;
-}
-
 // Compound::updateAntis (Pattern.cpp:520-543): rescan the 13-symbol window centred on `cell`
 // from the root state and give +600 (rival's perspective) to the other '_' / '^' cells of the
 // first emission of class `cclass` that has `cell` on a '_'.
-__device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t trans_addr, const PatRec* s_patrec,
+__device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t next_addr, uint32_t root_off, uint32_t emit_thr,
+                                           const uint32_t* s_erec, const PatRec* s_patrec,
                                            int cell, uint32_t dir, uint32_t cclass, int* rival) {
     const int cx = cell % kWidth, cy = cell / kWidth;
     const int stride = dir_stride(dir);
@@ -138,26 +123,27 @@ __device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t trans_addr, co
     else if (dir == 2) { before = min(cx, cy); after = kWidth - 1 - max(cx, cy); }
     else { before = min(kWidth - 1 - cx, cy); after = min(cx, kHeight - 1 - cy); }
     const int lo = 6 - min(before, 6), hi = 6 + min(after, 6);
-    // gather the 13 cell values first (independent loads), 2 bits each
+    // gather the 13 cell values first (independent loads), value * 2 at bit 2 * i + 1
     uint32_t window = 0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         uint32_t v = 3u;
         if (i >= lo && i <= hi) v = cell_value(ws.board, cell + (i - 6) * stride);
-        window |= v << (2 * i);
+        window |= v << (2 * i + 1);
     }
-    uint32_t tw = 0;                                                            // "next" field 0 = root
+    uint32_t nx = root_off;
 #pragma unroll 1
     for (int i = 0; i < 13; ++i, window >>= 2) {
-        tw = lds_u32(trans_addr + ((tw & kDevNextMask) | ((window & 3u) << 2)));
-        if (tw >= kDevEmitFloor) continue;
-        if (dw_cclass0(tw) != cclass && dw_pid(tw, 1) == kDevNoPid) continue;   // wrong class, no second emission: cheap reject
+        nx = lds_u16(next_addr + nx + (window & 6u));
+        if (nx >= emit_thr) continue;
+        const uint32_t er = s_erec[nx >> 3];
+        if (er_cclass0(er) != cclass && er_pid(er, 1) == kDevNoPid) continue;   // wrong class, no second emission: cheap reject
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const uint32_t pid = dw_pid(tw, k);
+            const uint32_t pid = er_pid(er, k);
             if (pid == kDevNoPid) break;
             const PatRec rec = s_patrec[pid];
-            const int off = i - int(dw_prev(tw, k)) - 6;                        // `cell` is the off-th char from the pattern's end
+            const int off = i - int(er_prev(er, k)) - 6;                        // `cell` is the off-th char from the pattern's end
             if (pr_cclass(rec.w0) != cclass || off < 0 || off >= int(pr_len(rec.w0))) continue;   // HasCovered, :22-25
             bool on_key = false;                                                // `cell` must sit on a '_'
             uint32_t cells = rec.w0;
@@ -216,35 +202,45 @@ __device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t idx, uint32_t
     if (!triple && l3 == 0) { t0 = first; t1 = second; }                        // exactly two components here, :500-502
 }
 
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+__host__ __device__ inline size_t warp_bytes(int list_cap) { return sizeof(WarpSmem) + size_t(list_cap) * 64; }
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
 ac_eval_kernel(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_trans = reinterpret_cast<uint32_t*>(smem_raw);
-    PatRec* s_patrec = reinterpret_cast<PatRec*>(s_trans + ((a.n_states * 4 + 3) & ~3));
-    uint16_t* s_src = reinterpret_cast<uint16_t*>(s_patrec + ((a.n_patterns + 1) & ~1));
-    uint16_t* s_info = s_src + a.tape_steps * 32;
-    WarpSmem* s_warps = reinterpret_cast<WarpSmem*>(s_info + a.tape_steps * 32);
+    const int n_rows = a.n_clones + a.n_states;
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* s_erec = reinterpret_cast<uint32_t*>(smem_raw + align16(size_t(n_rows) * 8));
+    PatRec* s_patrec = reinterpret_cast<PatRec*>(reinterpret_cast<unsigned char*>(s_erec) + align16(size_t(a.n_clones) * 4));
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_patrec) + align16(size_t(a.n_patterns) * sizeof(PatRec)));
+    unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64);
 
-    for (int i = threadIdx.x; i < a.n_states * 4; i += blockDim.x) s_trans[i] = a.trans[i];
+    for (int i = threadIdx.x; i < n_rows * 4; i += blockDim.x) s_next[i] = a.next16[i];
+    for (int i = threadIdx.x; i < a.n_clones; i += blockDim.x) s_erec[i] = a.erec[i];
     for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
-    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) { s_src[i] = a.tape_src[i]; s_info[i] = a.tape_info[i]; }
+    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) s_src[i] = a.tape_src[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem& ws = s_warps[warp];
+    const int cap = a.list_cap;
+    WarpSmem& ws = *reinterpret_cast<WarpSmem*>(s_warps + size_t(warp) * warp_bytes(cap));
+    uint16_t* lists = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(&ws) + sizeof(WarpSmem));   // [lane][cap]
     const uint32_t lt = lanemask_lt();
+    const uint32_t emit_thr = uint32_t(a.n_clones) * 8u;
     // shared-window addresses, made opaque so the compiler keeps them in registers instead of
     // re-deriving them from the CTA's shared base inside the scan loop
-    uint32_t board_addr = smem_addr(ws.board), trans_addr = smem_addr(s_trans);
-    uint32_t queue_addr = smem_addr(ws.queue), src_addr = smem_addr(s_src + lane);
-    asm volatile("" : "+r"(board_addr), "+r"(trans_addr), "+r"(queue_addr), "+r"(src_addr));
-    const uint32_t start_tw = a.start_state << 4;                          // a word whose "next" field is the start state
+    uint32_t next_addr = smem_addr(s_next), src_addr = smem_addr(s_src + lane);
+    uint32_t list_addr = smem_addr(lists + lane * cap);
+    asm volatile("" : "+r"(next_addr), "+r"(src_addr), "+r"(list_addr));
 
     const int warps = blockDim.x >> 5;
     for (long long b = (long long)blockIdx.x * warps + warp; b < a.n; b += (long long)gridDim.x * warps) {
         // ---- phase 0 ---------------------------------------------------------------------------
         uint32_t bw = 0xffffffffu;
-        if (lane < kBoardWords) bw = __ldg(a.boards + b * kBoardWords + lane);
+        if (lane < kBoardWords) {
+            bw = __ldg(a.boards + b * kBoardWords + lane);
+            bw &= ~((bw >> 1) & 0x55555555u);                               // a cell holding the invalid value 3 reads as white
+        }
         if (lane == 14) bw |= 0xfffffffcu;                                  // cells 225.. are pads
         if (lane == 15) bw = 0xffffffffu;
         if (lane < kBoardSmem) ws.board[lane] = bw;
@@ -280,62 +276,83 @@ ac_eval_kernel(EvalArgs a) {
             near &= 0x7fffu & ~occ;
             if (lane >= 30) near = 0;
             int* dst = ws.scores + (pg ? 3 : 0) * kCells + y * kWidth;       // scores(P, P), Pattern.cpp:244,268
-            while (near) {
-                const int x = __ffs(near) - 1;
-                near &= near - 1;
-                dst[x] = 160;
-            }
+#pragma unroll
+            for (int x = 0; x < kWidth; ++x)
+                if (near & (1u << x)) dst[x] = 160;
         }
         __syncwarp();
 
         // ---- phase 2: scan -------------------------------------------------------------------------
-        // per step: tape entry -> board word -> 2-bit cell value * 4 -> transition word; the only
-        // state-dependent chain is  LDS word, LOP3 (word & 0x3ff0 | value * 4), LDS word.
-        uint32_t tw = start_tw, win = 0;
-        uint32_t qaddr = queue_addr;                                        // shared address of the next free queue word
+        // per step: tape entry -> board word (shuffle) -> cell value * 2 -> next row offset.  The only
+        // state-dependent chain is  IADD (offset + value * 2), LDS.U16.
+        uint32_t nx = a.start_off;
+        uint32_t lp = list_addr;                                            // shared address of the lane's next free list slot
         uint32_t src = src_addr;
-        uint32_t tag = uint32_t(lane) << 2;                                 // (step * 32 + lane) << 2
         for (int t = 0; t < a.tape_steps; t += 2) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u, src += 64, tag += 32u << 2) {
+            for (int u = 0; u < 2; ++u, src += 64) {
                 const uint32_t e = lds_u16(src);
-                const uint32_t w = lds_u32(board_addr + (e & 0x7cu));
-                const uint32_t v4 = __funnelshift_r(w, w, e >> 8) & 0xcu;   // cell value * 4
-                tw = lds_u32(trans_addr + ((tw & kDevNextMask) | v4));
-                const bool emits = tw < kDevEmitFloor;
-                const uint32_t m = __ballot_sync(0xffffffffu, emits);
-                if (m) {
-                    if (emits) sts_u32(qaddr + 4u * __popc(m & lt), (tw & kDevEmitMask) | tag);
-                    qaddr += 4u * __popc(m);
-                    if (qaddr > queue_addr + 4u * kQueueFlush) {
-                        __syncwarp();
-                        win |= scatter_emissions(ws, s_patrec, s_info, int(qaddr - queue_addr) >> 2, lane);
-                        __syncwarp();
-                        qaddr = queue_addr;
-                    }
+                const uint32_t w = __shfl_sync(0xffffffffu, bw, e);         // source lane = e & 31 = board word index
+                const uint32_t v2 = __funnelshift_r(w, w, e >> 8) & 6u;     // cell value * 2
+                nx = lds_u16(next_addr + nx + v2);
+                if (nx < emit_thr) {
+                    sts_u16(lp, nx * 8u + uint32_t(t + u));                 // clone id << 6 | step
+                    lp += 2;
                 }
             }
         }
-        __syncwarp();
-        win |= scatter_emissions(ws, s_patrec, s_info, int(qaddr - queue_addr) >> 2, lane);
+        // ---- phase 3: balanced scatter ----------------------------------------------------------------
+        uint32_t win = 0;
+        {
+            uint32_t incl = (lp - list_addr) >> 1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            ws.prefix[lane + 1] = (uint16_t)incl;
+            if (lane == 0) ws.prefix[0] = 0;
+            const int total = int(__shfl_sync(0xffffffffu, incl, 31));
+            __syncwarp();
+            for (int i = lane; i < total; i += 32) {
+                int j = ws.prefix[16] <= i ? 16 : 0;                            // owner lane: prefix[j] <= i < prefix[j + 1]
+                if (ws.prefix[j + 8] <= i) j += 8;
+                if (ws.prefix[j + 4] <= i) j += 4;
+                if (ws.prefix[j + 2] <= i) j += 2;
+                if (ws.prefix[j + 1] <= i) j += 1;
+                const uint32_t ent = lists[j * cap + (i - int(ws.prefix[j]))];
+                const uint32_t er = s_erec[ent >> 6];
+                const uint32_t inf = __ldg(a.tape_info + (ent & 63u) * 32u + uint32_t(j));
+                const uint32_t dir = inf >> 9;
+                const int vcell = inf & 0x1ff, stride = dir_stride(dir);
+                win |= apply_emission(ws, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir);
+                const uint32_t p1 = er_pid(er, 1);
+                if (p1 != kDevNoPid) win |= apply_emission(ws, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir);
+            }
+        }
         __syncwarp();
 
         // ---- phase 4: compounds ----------------------------------------------------------------------
         {
-            unsigned short* clist = reinterpret_cast<unsigned short*>(ws.queue);
+            unsigned short* clist = lists;                                          // the emission lists are dead now (32 * cap >= 450)
             int cn = 0;
-            for (int r = 0; r < (2 * kCells + 31) / 32; ++r) {
-                const int idx = r * 32 + lane;
-                bool hit = false;
-                if (idx < 2 * kCells) {
-                    const uint32_t f = ws.flags[idx];
-                    const uint32_t bits = (f | (f >> 8) | (f >> 16)) & 0xffu;       // Compound::Test, Pattern.cpp:424-433
-                    hit = (bits & (bits - 1)) != 0;
+            const uint2* f2 = reinterpret_cast<const uint2*>(ws.flags);             // one cell: white word, black word
+            for (int r = 0; r < (kCells + 31) / 32; ++r) {
+                const int cell = r * 32 + lane;
+                uint32_t hits = 0;
+                if (cell < kCells) {
+                    const uint2 f = f2[cell];
+                    const uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu;   // Compound::Test, Pattern.cpp:424-433
+                    const uint32_t bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
+                    hits = ((bw0 & (bw0 - 1)) != 0 ? 1u : 0u) | ((bw1 & (bw1 - 1)) != 0 ? 2u : 0u);
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    if (hit) clist[cn + __popc(m & lt)] = (unsigned short)idx;
-                    cn += __popc(m);
+                const uint32_t m = __ballot_sync(0xffffffffu, hits != 0);
+                if (m) {                                                            // rare: a few cells per board
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, hits & 1u), m1 = __ballot_sync(0xffffffffu, hits & 2u);
+                    if (hits & 1u) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
+                    cn += __popc(m0);
+                    if (hits & 2u) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
+                    cn += __popc(m1);
                 }
             }
             __syncwarp();
@@ -352,8 +369,8 @@ ac_eval_kernel(EvalArgs a) {
                     const uint32_t task = (s & 1) ? tb : ta;
                     if (s < ntask) {
                         const uint32_t black = (task >> 8) & 1u;
-                        anti_cells(ws, trans_addr, s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
-                                   ws.scores + (black + 1) * kCells);
+                        anti_cells(ws, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, int(task & 0xffu),
+                                   (task >> 9) & 3u, (task >> 11) & 3u, ws.scores + (black + 1) * kCells);
                     }
                 }
             }
@@ -404,24 +421,25 @@ __global__ void scan_strings_kernel(ScanArgs a) {
 }  // namespace
 
 static size_t table_smem_bytes(const EvalArgs& a) {
-    return size_t((a.n_states * 4 + 3) & ~3) * 4 + size_t((a.n_patterns + 1) & ~1) * sizeof(PatRec) +
-           size_t(a.tape_steps) * 32 * 2 * sizeof(uint16_t);
+    return align16(size_t(a.n_clones + a.n_states) * 8) + align16(size_t(a.n_clones) * 4) +
+           align16(size_t(a.n_patterns) * sizeof(PatRec)) + align16(size_t(a.tape_steps) * 64);
 }
 
 // warps per CTA: as many as fit beside the tables (32 for the default table; bigger custom tables get fewer)
 static int eval_warps(const EvalArgs& a) {
-    const size_t tables = table_smem_bytes(a);
-    if (tables + sizeof(WarpSmem) > kSmemLimit) return 0;
-    const size_t fit = (kSmemLimit - tables) / sizeof(WarpSmem);
+    const size_t tables = table_smem_bytes(a), per_warp = warp_bytes(a.list_cap);
+    if (tables + per_warp > kSmemLimit) return 0;
+    const size_t fit = (kSmemLimit - tables) / per_warp;
     return int(fit < size_t(kWarpsPerCta) ? fit : size_t(kWarpsPerCta));
 }
 
-size_t eval_smem_bytes(const EvalArgs& a) { return table_smem_bytes(a) + size_t(eval_warps(a)) * sizeof(WarpSmem); }
+size_t eval_smem_bytes(const EvalArgs& a) { return table_smem_bytes(a) + size_t(eval_warps(a)) * warp_bytes(a.list_cap); }
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
     const int warps = eval_warps(a);
-    if (warps == 0) return cudaErrorInvalidConfiguration;                    // table too large for shared memory
+    if (warps == 0 || a.list_cap * 32 < 2 * kCells || a.tape_steps > kMaxTapeSteps)
+        return cudaErrorInvalidConfiguration;                               // table too large for shared memory
     const size_t smem = eval_smem_bytes(a);
     cudaError_t err = cudaFuncSetAttribute(ac_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

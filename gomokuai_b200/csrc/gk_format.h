@@ -38,25 +38,26 @@ GK_HD inline uint32_t em_prev(uint32_t e) { return (e >> 9) & 1u; }
 // The host words above are the documented, inspectable form (gk_table_entries).  The copies
 // uploaded to the GPU are re-encoded so that the scan loop needs as few integer ops as possible.
 //
-// ---- device transition word: D[state * 4 + v], v = raw 2-bit cell value (0 empty, 1 black,
-//      2 white, 3 off-board pad), i.e. the columns are permuted so no symbol mapping is needed.
-//      The fields are placed so that the scan loop's dependent chain is "LDS, one LOP3, LDS":
-//   [ 0]    emission 0 is "at previous symbol"
-//   [ 1]    emission 1 is "at previous symbol"
-//   [ 2, 4) compound class of emission 0's pattern (0 none, 1 LiveThree, 2 DeadThree, 3 LiveTwo): lets the
-//           13-symbol window rescans skip emissions of the wrong class without loading the pattern record
-//   [ 4,14) next state, i.e. (word & 0x3ff0) is the BYTE offset of the next state's row
-//   [14,23) emission 1 pattern id, 0x1ff = none
-//   [23,32) emission 0 pattern id, 0x1ff = none  (so: word >= kDevEmitFloor  <=>  no emission)
-// Bits [2,14) are replaced by (step * 32 + lane) when the word is pushed to the emission queue.
+// ---- device automaton: "cloned arrival" next table -----------------------------------------------
+// Every distinct (destination state, emission set) pair of an emitting transition becomes its own
+// CLONE of the destination state: same outgoing row, but a low id.  Ids [0, n_clones) are clones,
+// ids [n_clones, n_clones + n_states) are the plain states in host order.  Then
+//   next16[id * 4 + v] (uint16) = BYTE offset (id' * 8) of the destination row, v = raw 2-bit cell
+//                                 value (0 empty, 1 black, 2 white, 3 off-board pad),
+//   "this step emitted"  <=>  offset < n_clones * 8   (one compare, no mask, no second load),
+// and the state-dependent chain of one scan step is  IADD (offset + v * 2), LDS.U16.
+//   erec[clone] (uint32): what an arrival at that clone emits
+//     [ 0, 9) pattern id of emission 0      [ 9] emission 0 is "at previous symbol"
+//     [10,19) pattern id of emission 1, 0x1ff = none      [19] same flag for emission 1
+//     [20,22) compound class of emission 0's pattern (0 none, 1 LiveThree, 2 DeadThree, 3 LiveTwo)
+// Emission list entry (uint16, kernel internal): clone id << 6 | scan step.
 constexpr uint32_t kDevNoPid = 0x1ffu;
-constexpr uint32_t kDevEmitFloor = kDevNoPid << 23;
-constexpr uint32_t kDevNextMask = 0x3ff0u;
-constexpr uint32_t kDevEmitMask = 0xffffc003u;    // the bits of a device word that describe its emissions
+constexpr int kMaxClones = 1024;                  // clone id << 6 | step must fit 16 bits
+constexpr int kMaxTapeSteps = 64;
 GK_HD inline int sym_to_value(int sym) { return (sym + 1) & 3; }   // table symbol index -> raw cell value
-GK_HD inline uint32_t dw_pid(uint32_t w, int k) { return (w >> (23 - 9 * k)) & 0x1ffu; }
-GK_HD inline uint32_t dw_prev(uint32_t w, int k) { return (w >> k) & 1u; }
-GK_HD inline uint32_t dw_cclass0(uint32_t w) { return (w >> 2) & 3u; }
+GK_HD inline uint32_t er_pid(uint32_t e, int k) { return (e >> (10 * k)) & 0x1ffu; }
+GK_HD inline uint32_t er_prev(uint32_t e, int k) { return (e >> (9 + 10 * k)) & 1u; }
+GK_HD inline uint32_t er_cclass0(uint32_t e) { return (e >> 20) & 3u; }
 
 // ---- device pattern record: 2 words per pattern ---------------------------------------------------
 //   w0 [ 0,16) up to four scored cells, one nibble each: bits 0..2 = j (cell is the j-th char from
@@ -81,15 +82,14 @@ constexpr int kTypeFive = 8;
 // Every line is followed by trail_pad (>= 2) pad symbols; two pads take ANY state to the state
 // "one '?' read from the root" (checked by the table compiler), which is also where a line has
 // to start, so the chain needs no explicit restart between lines.
-//   src[step * 32 + lane]  (uint16)  where this step's symbol lives in the warp's board copy:
-//        [0,7)  byte offset of the 32-bit board word (cell >> 4) * 4; pads read cell 225 (value 3)
-//        [8,13) rotate-right amount that brings the cell's 2 bits to bits 2..3: (2*(cell & 15) + 30) & 31
+//   src[step * 32 + lane]  (uint16)  where this step's symbol lives in the warp's copy of the board
+//        (lane w of the warp holds board word w; words 14 / 15 carry all-ones above cell 224):
+//        [0,5)  board word index cell >> 4; pads read cell 225, which the kernel forces to 3
+//        [8,13) rotate-right amount that brings the cell's 2 bits to bits 1..2: (2*(cell & 15) + 31) & 31
 //   info[step * 32 + lane] (uint16)  only read when the step emitted:
 //        [0,9)  virtual cell of this step on its line (cell0 + index * stride; runs past 224 on pads)
 //        [9,11) direction: 0 row, 1 column, 2 diagonal (+1,+1), 3 anti-diagonal (-1,+1)
 constexpr int kPadCell = 225;                     // any cell index in [225, 272) reads as pad
 GK_HD inline int dir_stride(int dir) { return dir == 0 ? 1 : dir == 1 ? 15 : dir == 2 ? 16 : 14; }
 
-// ---- emission queue entry (kernel internal) -----------------------------------------------------------
-//   a device transition word with bits [2,13) replaced by step * 32 + lane
 }  // namespace gk

@@ -10,10 +10,10 @@
 namespace gk {
 
 struct EvalArgs {
-    const uint32_t* trans; int n_states;       // device copies of the compiled table, device encodings (gk_format.h)
+    const uint16_t* next16; const uint32_t* erec; int n_states, n_clones;   // device copies of the compiled table (gk_format.h)
     const PatRec* patrec; int n_patterns;
     const uint16_t* tape_src; const uint16_t* tape_info; int tape_steps;
-    uint32_t start_state;
+    int root_off, start_off, list_cap;
     const uint32_t* boards; long long n;
     int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
 };

@@ -274,7 +274,7 @@ std::vector<Line> board_lines() {                              // the 72 lines t
 }
 
 // Longest-processing-time-first packing of whole lines onto the 32 lanes of a warp.
-void build_tape(HostTable& t) {
+bool build_tape(HostTable& t) {
     std::vector<Line> lines = board_lines();
     std::vector<int> order(lines.size());
     std::iota(order.begin(), order.end(), 0);
@@ -287,8 +287,9 @@ void build_tape(HostTable& t) {
         load[best] += lines[li].len + t.trail_pad;
     }
     t.tape_steps = (*std::max_element(load.begin(), load.end()) + 1) & ~1;   // the kernel unrolls by two
-    const auto src_of = [](int cell) {
-        return static_cast<uint16_t>(((cell >> 4) * 4) | (((2 * (cell & 15) + 30) & 31) << 8));
+    if (t.tape_steps > kMaxTapeSteps) return false;
+    const auto src_of = [](int cell) {                        // gk_format.h: board word index | rotate amount << 8
+        return static_cast<uint16_t>((cell >> 4) | (((2 * (cell & 15) + 31) & 31) << 8));
     };
     t.tape_src.assign(static_cast<size_t>(t.tape_steps) * 32, src_of(kPadCell));   // filler: a pad that belongs to no line
     t.tape_info.assign(static_cast<size_t>(t.tape_steps) * 32, 0);
@@ -303,6 +304,33 @@ void build_tape(HostTable& t) {
             }
         }
     }
+    // Emission-list capacity: the largest number of emitting steps any lane chain can produce, over ALL
+    // boards (cells take the values empty / black / white, pads are fixed) -- a max-plus walk of the
+    // automaton along each lane's tape.  The kernel's per-lane lists are sized by this, so they cannot overflow.
+    int worst = 0;
+    for (int l = 0; l < 32; ++l) {
+        std::vector<int> best(t.n_states, -1), next_best(t.n_states);
+        best[t.start_state] = 0;
+        for (int step = 0; step < t.tape_steps; ++step) {
+            const bool pad = t.tape_src[static_cast<size_t>(step) * 32 + l] == src_of(kPadCell);
+            std::fill(next_best.begin(), next_best.end(), -1);
+            for (int st = 0; st < t.n_states; ++st) {
+                if (best[st] < 0) continue;
+                for (int sym = 0; sym < 4; ++sym) {
+                    if (pad != (sym == kSymPad)) continue;
+                    const uint32_t w = t.trans[static_cast<size_t>(st) * 4 + sym];
+                    const int got = best[st] + (tw_nemit(w) != 0 ? 1 : 0);
+                    int& slot = next_best[tw_next(w)];
+                    slot = std::max(slot, got);
+                }
+            }
+            best.swap(next_best);
+        }
+        worst = std::max(worst, *std::max_element(best.begin(), best.end()));
+    }
+    t.list_cap = std::max(worst, 16);
+    while (t.list_cap % 4 != 2) ++t.list_cap;                  // cap / 2 odd: lanes' lists start in different banks
+    return true;
 }
 
 }  // namespace
@@ -416,22 +444,45 @@ bool compile_table(const std::vector<Proto>& protos, HostTable& t) {
         for (int s : cur)
             if (s != t.start_state) { t.error = "board edge does not reset the automaton"; return false; }
     }
-    t.dev_trans.assign(t.trans.size(), 0);
-    for (int id = 0; id < t.n_states; ++id)
-        for (int sym = 0; sym < 4; ++sym) {
-            const uint32_t w = t.trans[static_cast<size_t>(id) * 4 + sym];
-            uint32_t d = tw_next(w) << 4;
+    // device automaton (gk_format.h): one clone of the destination per distinct (destination, emission set)
+    {
+        std::map<std::pair<int, uint32_t>, int> clone_of;     // (destination, emission bits of the host word) -> clone id
+        std::vector<std::pair<int, uint32_t>> clones;
+        for (int id = 0; id < t.n_states; ++id)
+            for (int sym = 0; sym < 4; ++sym) {
+                const uint32_t w = t.trans[static_cast<size_t>(id) * 4 + sym];
+                if (tw_nemit(w) == 0) continue;
+                const auto key = std::make_pair(static_cast<int>(tw_next(w)), w >> 10);
+                if (clone_of.emplace(key, static_cast<int>(clones.size())).second) clones.push_back(key);
+            }
+        t.n_clones = static_cast<int>(clones.size());
+        const int total = t.n_clones + t.n_states;
+        if (t.n_clones > kMaxClones || total * 8 > 65535) { t.error = "automaton too large for the 16-bit device table"; return false; }
+        t.dev_next.assign(static_cast<size_t>(total) * 4, 0);
+        t.dev_erec.assign(t.n_clones, 0);
+        const auto row_of = [&](int dev_id) { return dev_id < t.n_clones ? clones[dev_id].first : dev_id - t.n_clones; };
+        for (int dev_id = 0; dev_id < total; ++dev_id)
+            for (int sym = 0; sym < 4; ++sym) {
+                const uint32_t w = t.trans[static_cast<size_t>(row_of(dev_id)) * 4 + sym];
+                const int dest = tw_nemit(w) == 0 ? t.n_clones + static_cast<int>(tw_next(w))
+                                                  : clone_of.at({ static_cast<int>(tw_next(w)), w >> 10 });
+                t.dev_next[static_cast<size_t>(dev_id) * 4 + sym_to_value(sym)] = static_cast<uint16_t>(dest * 8);
+            }
+        for (int c = 0; c < t.n_clones; ++c) {
+            const uint32_t bits = clones[c].second;            // host word >> 10: count, emission 0, emission 1
+            const int n = static_cast<int>(bits & 3u);
+            uint32_t e = 0;
             for (int k = 0; k < 2; ++k) {
-                const bool has = k < static_cast<int>(tw_nemit(w));
-                d |= (has ? em_pid(tw_emit(w, k)) : kDevNoPid) << (23 - 9 * k);
-                d |= (has ? em_prev(tw_emit(w, k)) : 0u) << k;
+                const uint32_t em = (bits >> (2 + 10 * k)) & 0x3ffu;
+                e |= (k < n ? (em_pid(em) | em_prev(em) << 9) : kDevNoPid) << (10 * k);
             }
-            if (tw_nemit(w) > 0) {
-                const int type = t.patterns[em_pid(tw_emit(w, 0))].type;
-                d |= static_cast<uint32_t>(type == 5 ? 1 : type == 4 ? 2 : type == 3 ? 3 : 0) << 2;
-            }
-            t.dev_trans[static_cast<size_t>(id) * 4 + sym_to_value(sym)] = d;
+            const int type = t.patterns[em_pid((bits >> 2) & 0x3ffu)].type;
+            e |= static_cast<uint32_t>(type == 5 ? 1 : type == 4 ? 2 : type == 3 ? 3 : 0) << 20;
+            t.dev_erec[c] = e;
         }
+        t.root_off = t.n_clones * 8;
+        t.start_off = (t.n_clones + t.start_state) * 8;
+    }
     // How many symbols until the state forgets where it started (0: it never does).  Informational:
     // it bounds the context an emission can depend on.
     {
@@ -453,7 +504,7 @@ bool compile_table(const std::vector<Proto>& protos, HostTable& t) {
             if (all_single) t.sync_depth = depth;
         }
     }
-    build_tape(t);
+    if (!build_tape(t)) { t.error = "scan tape longer than 64 steps"; return false; }
     return true;
 }
 

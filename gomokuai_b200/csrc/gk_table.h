@@ -21,7 +21,11 @@ struct HostTable {
     int trail_pad = 0;                   // trailing '?' symbols after which no state can emit any more (>= 2)
     int tape_steps = 0;                  // scan steps per board (longest lane chain, even)
     // device encodings (gk_format.h)
-    std::vector<uint32_t> dev_trans;     // n_states * 4, indexed by raw cell value
+    std::vector<uint16_t> dev_next;      // (n_clones + n_states) * 4 row offsets, indexed by raw cell value
+    std::vector<uint32_t> dev_erec;      // n_clones emission records
+    int n_clones = 0;
+    int root_off = 0, start_off = 0;     // byte offsets of the root row / the line-start row in dev_next
+    int list_cap = 0;                    // emission-list slots per lane: max emitting steps of any lane chain (+ rounding)
     std::vector<PatRec> patrec;
     std::vector<uint16_t> tape_src;      // tape_steps * 32
     std::vector<uint16_t> tape_info;     // tape_steps * 32

@@ -82,6 +82,12 @@ gk_status gk_table_entries(const gk_table* table, uint32_t* h_entries, int capac
  * reaches the end of the string, Pattern.cpp:40-45,54), else -1; n_states int16 */
 gk_status gk_table_flush(const gk_table* table, int16_t* h_flush, int capacity);
 
+/* The re-encoded automaton the eval kernel reads (csrc/gk_format.h): (n_clones + n_states) rows of four
+ * uint16 row offsets and n_clones uint32 emission records.  info[6] = {n_rows, n_clones, root_off,
+ * start_off, list_cap, tape_steps}.  h_next / h_erec may be NULL to query the sizes only.  For tests. */
+gk_status gk_table_device_format(const gk_table* table, int info[6], uint16_t* h_next, int next_capacity,
+                                 uint32_t* h_erec, int erec_capacity);
+
 /* PatternSearch::execute / matches (src/Pattern.cpp:64-74) for a batch of symbol strings:
  * string i = d_codes[d_starts[i] .. d_starts[i+1]) with symbols 1..4 (EncodeCharset,
  * include/Mapping.h:40-48).  Emissions (pattern id, end offset) of string i are written to

@@ -83,3 +83,58 @@ def test_pack_and_synth(gk, port):
     # non-terminal by construction: the reference's evaluator reports no winner
     r = port.eval_batch(moves, starts, want_scores=False)
     assert r["bad"] == 0 and (r["winner"] == 0).all() and (r["cur_player"] != 0).all()
+
+
+def _walk_device(dev, codes, start=None):
+    """The eval kernel's scan loop in Python: one 16-bit load per symbol, emission iff offset < n_clones * 8."""
+    nxt, erec, thr = dev["next"], dev["erec"], dev["n_clones"] * 8
+    off, out, emitting_steps = (dev["root_off"] if start is None else start), [], 0
+    for i, c in enumerate(codes):
+        off = int(nxt[off >> 3, c % 4])                    # reference code 1..4 -> raw cell value 1, 2, 3, 0
+        if off < thr:
+            emitting_steps += 1
+            e = int(erec[off >> 3])
+            for k in range(2):
+                pid = (e >> (10 * k)) & 511
+                if pid != 511:
+                    out.append((pid, i - ((e >> (9 + 10 * k)) & 1)))
+    return out, emitting_steps
+
+
+def test_device_format_equals_host_format(gk):
+    """cloned-arrival table (what the kernel reads) == flat transducer (what the oracle pins), on random strings"""
+    t = gk.default_table()
+    entries, dev = t.entries(), t.device_format()
+    assert dev["next"].shape[0] == dev["n_clones"] + 558 and dev["n_clones"] <= 1024
+    assert dev["tape_steps"] == 34 and dev["list_cap"] == 18 and dev["root_off"] == dev["n_clones"] * 8
+    no_flush = np.full(558, -1)
+    for s in _strings(23, 20000):
+        codes = s.tolist()
+        assert _walk_device(dev, codes)[0] == _walk(entries, no_flush, codes), codes
+
+
+def test_list_capacity_bounds_emitting_steps(gk):
+    """no lane chain of the tape can emit on more steps than the per-lane list holds: adversarial +
+    random lines through the device table, from the line-start state, with the two trailing pads"""
+    dev = gk.default_table().device_format()
+    rng = np.random.default_rng(5)
+    worst = 0
+    dense = [[4, 1, 4, 1, 4, 1, 4, 1, 4, 1, 4, 1, 4, 1, 4], [1, 4] * 7 + [1], [4, 4, 1, 4, 4, 1, 4, 4, 1, 4, 4, 1, 4, 4, 1],
+             [2, 1, 4, 4, 4, 1, 4, 4, 4, 1, 4, 4, 4, 1, 2]]
+    lines = dense + [rng.choice([1, 2, 4, 4], size=15).tolist() for _ in range(20000)]
+    for line in lines:
+        _, steps = _walk_device(dev, line + [3, 3], start=dev["start_off"])
+        worst = max(worst, steps)
+    assert worst <= 9                                       # 15-cell line: at most 9 emitting steps (table compiler's DP)
+    assert 2 * worst <= dev["list_cap"]
+
+
+def test_custom_table_device_format(gk, kats):
+    k = kats["kat_protos"]
+    t = gk.Table(k["protos"], k["types"], k["scores"])
+    entries, dev = t.entries(), t.device_format()
+    no_flush = np.full(entries.shape[0], -1)
+    rng = np.random.default_rng(2)
+    for _ in range(3000):
+        codes = rng.integers(1, 5, size=int(rng.integers(1, 30))).tolist()
+        assert _walk_device(dev, codes)[0] == _walk(entries, no_flush, codes)
