@@ -83,26 +83,31 @@ __device__ __forceinline__ uint32_t squeeze_even(uint32_t x) {
 
 // One emission of pattern `rec` whose last char sits on virtual cell `vend` of a line with the
 // given direction (Updater::updatePatterns, Pattern.cpp:138-165).  Returns winner bits.
-__device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, const PatRec rec, int vend, uint32_t dir) {
+__device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, const PatRec rec, int vend, uint32_t dir, int stride) {
     const uint32_t type = pr_type(rec.w0), black = pr_black(rec.w0);
     if (type == kTypeFive) return black ? 1u : 2u;                              // :140-145
     atomicAdd(&ws.totals[black * 8 + type], 1u);                                // :147
     const int score = dir >= 2 ? int(rec.w1 >> 16) : int(rec.w1 & 0xffffu);     // :151-152
-    const int stride = dir_stride(dir);
     int* self = ws.scores + black * 3 * kCells;                                 // Group(f, f)
     int* rival = ws.scores + (black + 1) * kCells;                              // Group(f, -f)
+    const uint32_t ncells = pr_ncells(rec.w0);
+#pragma unroll
+    for (uint32_t s = 0; s < 4; ++s) {                                          // at most four scored cells: straight-line, predicated
+        const uint32_t nib = (rec.w0 >> (4 * s)) & 15u;
+        const int cell = vend - int(nib & 7u) * stride;
+        if (s < ncells) {
+            atomicAdd(&rival[cell], score);                                     // '_' and '^', :158-161
+            if (nib & 8u) atomicAdd(&self[cell], score);
+        }
+    }
     const uint32_t cclass = pr_cclass(rec.w0);
-    const uint32_t lo = 1u << (cclass * 8 - 8 + dir * 2);                       // only used when cclass != 0
-    uint32_t cells = rec.w0;
-    for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) {
-        const int cell = vend - int(cells & 7u) * stride;
-        atomicAdd(&rival[cell], score);                                         // '_' and '^', :158-161
-        if (cells & 8u) {
-            atomicAdd(&self[cell], score);
-            if (cclass) {                                                       // Record::set: 00 -> 01 -> 11, :395-400
-                uint32_t* word = &ws.flags[cell * 2 + black];
-                if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
-            }
+    if (cclass) {                                                               // Record::set: 00 -> 01 -> 11, :395-400
+        const uint32_t lo = 1u << (cclass * 8 - 8 + dir * 2);
+        uint32_t cells = rec.w0;
+        for (uint32_t n = ncells; n != 0; --n, cells >>= 4) {
+            if (!(cells & 8u)) continue;
+            uint32_t* word = &ws.flags[(vend - int(cells & 7u) * stride) * 2 + black];
+            if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
         }
     }
     return 0;
@@ -323,11 +328,11 @@ ac_eval_kernel(EvalArgs a) {
                 const uint32_t ent = lists[j * cap + (i - int(ws.prefix[j]))];
                 const uint32_t er = s_erec[ent >> 6];
                 const uint32_t inf = __ldg(a.tape_info + (ent & 63u) * 32u + uint32_t(j));
-                const uint32_t dir = inf >> 9;
-                const int vcell = inf & 0x1ff, stride = dir_stride(dir);
-                win |= apply_emission(ws, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir);
+                const uint32_t dir = (inf >> 9) & 3u;
+                const int vcell = inf & 0x1ff, stride = int(inf >> 11);
+                win |= apply_emission(ws, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir, stride);
                 const uint32_t p1 = er_pid(er, 1);
-                if (p1 != kDevNoPid) win |= apply_emission(ws, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir);
+                if (p1 != kDevNoPid) win |= apply_emission(ws, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir, stride);
             }
         }
         __syncwarp();
@@ -337,21 +342,21 @@ ac_eval_kernel(EvalArgs a) {
             unsigned short* clist = lists;                                          // the emission lists are dead now (32 * cap >= 450)
             int cn = 0;
             const uint2* f2 = reinterpret_cast<const uint2*>(ws.flags);             // one cell: white word, black word
+#pragma unroll 2
             for (int r = 0; r < (kCells + 31) / 32; ++r) {
                 const int cell = r * 32 + lane;
-                uint32_t hits = 0;
-                if (cell < kCells) {
-                    const uint2 f = f2[cell];
+                // cheap necessary condition first: a word with fewer than two raw bits cannot pass Compound::Test
+                const uint2 f = f2[cell < kCells ? cell : kCells];                  // flags[450..451] stay zero
+                const bool maybe = ((f.x & (f.x - 1)) | (f.y & (f.y - 1))) != 0;
+                const uint32_t m = __ballot_sync(0xffffffffu, maybe);
+                if (m) {                                                            // rare: a few cells per board
                     const uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu;   // Compound::Test, Pattern.cpp:424-433
                     const uint32_t bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
-                    hits = ((bw0 & (bw0 - 1)) != 0 ? 1u : 0u) | ((bw1 & (bw1 - 1)) != 0 ? 2u : 0u);
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, hits != 0);
-                if (m) {                                                            // rare: a few cells per board
-                    const uint32_t m0 = __ballot_sync(0xffffffffu, hits & 1u), m1 = __ballot_sync(0xffffffffu, hits & 2u);
-                    if (hits & 1u) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
+                    const bool h0 = (bw0 & (bw0 - 1)) != 0, h1 = (bw1 & (bw1 - 1)) != 0;
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                    if (h0) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
                     cn += __popc(m0);
-                    if (hits & 2u) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
+                    if (h1) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
                     cn += __popc(m1);
                 }
             }

@@ -89,6 +89,7 @@ constexpr int kTypeFive = 8;
 //   info[step * 32 + lane] (uint16)  only read when the step emitted:
 //        [0,9)  virtual cell of this step on its line (cell0 + index * stride; runs past 224 on pads)
 //        [9,11) direction: 0 row, 1 column, 2 diagonal (+1,+1), 3 anti-diagonal (-1,+1)
+//        [11,16) cell stride of that direction (1, 15, 16, 14)
 constexpr int kPadCell = 225;                     // any cell index in [225, 272) reads as pad
 GK_HD inline int dir_stride(int dir) { return dir == 0 ? 1 : dir == 1 ? 15 : dir == 2 ? 16 : 14; }
 

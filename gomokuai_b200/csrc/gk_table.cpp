@@ -300,7 +300,7 @@ bool build_tape(HostTable& t) {
             for (int i = 0; i < L.len + t.trail_pad; ++i, ++step) {
                 const int vcell = L.cell0 + i * L.stride;
                 t.tape_src[static_cast<size_t>(step) * 32 + l] = src_of(i < L.len ? vcell : kPadCell);
-                t.tape_info[static_cast<size_t>(step) * 32 + l] = static_cast<uint16_t>(vcell | L.dir << 9);
+                t.tape_info[static_cast<size_t>(step) * 32 + l] = static_cast<uint16_t>(vcell | L.dir << 9 | L.stride << 11);
             }
         }
     }
