@@ -253,6 +253,42 @@ def eval_batch_host(boards, table=None, want_scores=True, out=None):
     return out
 
 
+def eval_policy_batch(boards, table=None, want_scores=False, stream=None):
+    """gk_eval_policy_batch: the evaluator's policy heads for the side to move (Heuristic::EvaluationProbs /
+    EvaluationValue, include/algorithms/Heuristic.hpp:16-45).  Returns dict(probs[n,225] f32, value[n] f32,
+    winner[n] i8, pat_totals, cmp_totals and, if want_scores, scores[n,4,225] i32) of CUDA tensors."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    table = table or default_table()
+    n, dev = boards.shape[0], boards.device
+    out = {
+        "probs": torch.empty((n, CELLS), dtype=torch.float32, device=dev),
+        "value": torch.empty((n,), dtype=torch.float32, device=dev),
+        "scores": torch.empty((n, 4, CELLS), dtype=torch.int32, device=dev) if want_scores else None,
+        "pat_totals": torch.empty((n, 2, 8), dtype=torch.int16, device=dev),
+        "cmp_totals": torch.empty((n, 2, 3), dtype=torch.int16, device=dev),
+        "winner": torch.empty((n,), dtype=torch.int8, device=dev),
+    }
+    _check(lib().gk_eval_policy_batch(table.handle, _ptr(boards), n, _ptr(out["probs"]), _ptr(out["value"]),
+                                      _ptr(out["scores"]), _ptr(out["pat_totals"]), _ptr(out["cmp_totals"]),
+                                      _ptr(out["winner"]), _stream_ptr(stream)))
+    return out
+
+
+def eval_policy_batch_host(boards, table=None):
+    """Same through HOST buffers: returns numpy (probs[n,225] f32, value[n] f32, winner[n] i8)."""
+    table = table or default_table()
+    _require_init()
+    b = boards.numpy() if hasattr(boards, "numpy") else boards
+    b = np.ascontiguousarray(b).view(np.uint32).reshape(-1, BOARD_WORDS)
+    n = b.shape[0]
+    probs, value, winner = np.empty((n, CELLS), np.float32), np.empty((n,), np.float32), np.empty((n,), np.int8)
+    _check(lib().gk_eval_policy_batch_host(table.handle, b.ctypes.data_as(ctypes.c_void_p), n,
+                                           probs.ctypes.data_as(ctypes.c_void_p), value.ctypes.data_as(ctypes.c_void_p),
+                                           winner.ctypes.data_as(ctypes.c_void_p)))
+    return probs, value, winner
+
+
 def rollout_batch(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_base=0, want_trace=False, stream=None):
     """Random playouts. Returns dict(wdb[n,3] i32 = {white, draw, black}, winners[n,R] i8, lengths[n,R] u8)."""
     torch = _torch()

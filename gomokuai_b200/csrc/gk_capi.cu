@@ -361,6 +361,47 @@ gk_status gk_eval_batch_host(const gk_table* t, const uint32_t* h_boards, int n,
     return GK_OK;
 }
 
+gk_status gk_eval_policy_batch(const gk_table* t, const uint32_t* d_boards, int n, float* d_probs, float* d_value,
+                               int32_t* d_scores, uint16_t* d_pat_totals, uint16_t* d_cmp_totals, int8_t* d_winner,
+                               void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (!t || n < 0 || (n > 0 && !d_boards)) return fail(GK_ERR_INVALID, "bad arguments");
+    if (reinterpret_cast<uintptr_t>(d_scores) & 15u) return fail(GK_ERR_INVALID, "d_scores must be 16-byte aligned");
+    if (gk_status s = ensure_uploaded(t)) return s;
+    gk::EvalArgs a = eval_args(t, d_boards, n, d_scores, d_pat_totals, d_cmp_totals, d_winner);
+    a.probs = d_probs; a.value = d_value;
+    GK_CUDA(gk::launch_eval(a, g_sm_count, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
+gk_status gk_eval_policy_batch_host(const gk_table* t, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
+                                    int8_t* h_win) {
+    if (gk_status s = require_device()) return s;
+    if (!t || n < 0 || (n > 0 && !h_boards)) return fail(GK_ERR_INVALID, "bad arguments");
+    if (gk_status s = ensure_uploaded(t)) return s;
+    const int chunk = std::min(n, 16384);
+    if (chunk == 0) return GK_OK;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (Pipe& p : g_pipes) if (gk_status s = pipe_reserve(p, chunk)) return s;
+    int k = 0;
+    for (int at = 0; at < n; at += chunk, ++k) {                      // the score buffer of the pipe doubles as probs + value
+        Pipe& p = g_pipes[k % kPipes];
+        const int m = std::min(chunk, n - at);
+        float* d_probs = reinterpret_cast<float*>(p.d_scores);
+        float* d_value = d_probs + size_t(chunk) * 225;
+        GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
+        gk::EvalArgs a = eval_args(t, p.d_boards, m, nullptr, nullptr, nullptr, h_win ? p.d_win : nullptr);
+        a.probs = h_probs ? d_probs : nullptr; a.value = h_value ? d_value : nullptr;
+        if (!a.probs && !a.value) a.value = d_value;
+        GK_CUDA(gk::launch_eval(a, g_sm_count, p.stream));
+        if (h_probs) GK_CUDA(cudaMemcpyAsync(h_probs + size_t(at) * 225, d_probs, size_t(m) * 900, cudaMemcpyDeviceToHost, p.stream));
+        if (h_value) GK_CUDA(cudaMemcpyAsync(h_value + at, d_value, size_t(m) * 4, cudaMemcpyDeviceToHost, p.stream));
+        if (h_win) GK_CUDA(cudaMemcpyAsync(h_win + at, p.d_win, size_t(m), cudaMemcpyDeviceToHost, p.stream));
+    }
+    for (Pipe& p : g_pipes) GK_CUDA(cudaStreamSynchronize(p.stream));
+    return GK_OK;
+}
+
 // ---- rollouts --------------------------------------------------------------------------------------
 static gk_status rollout_common(const uint32_t* d_boards, int n, int rollouts_per_pos, uint64_t key, uint32_t ctr_hi,
                                 int pos_base, const uint8_t* d_r_stream, int stream_stride, int32_t* d_wdb,

@@ -210,6 +210,88 @@ __device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t idx, uint32_t
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 __host__ __device__ inline size_t warp_bytes(int list_cap) { return sizeof(WarpSmem) + size_t(list_cap) * 64; }
 
+// Heuristic::DensityWeight / EvaluationProbs / EvaluationValue (include/algorithms/Heuristic.hpp:16-45) for the
+// side to move, from the finished score maps of one board.  `mine` is the lane's 15-bit row mask
+// (lanes 0..14 white rows, 15..29 black rows).  Each lane owns the cells lane, lane + 32, ...
+//   density(P)[c]  = { count, weight } of P's stones on the weighted offsets of the clipped 7x7 window
+//                    (Pattern.cpp:236-272; occupied cells are filtered to 0 by DensityWeight's max(x, 0))
+//   DW(P)          = normalized( 3 W / (1 + 2 N) )                                       (:40-45)
+//   probs          = normalized( 0.6 S(p,p) . DW(p) + 0.4 S(-p,p) . DW(-p) ), one-hot centre on an empty board (:16-27)
+//   value          = tanh( (1.2 <S(p,p), DW(p)> - <S(-p,-p), DW(-p)>) / 500 )            (:32-36)
+// Floating point: sums run lane-strided then by warp shuffle, so they differ from Eigen's packet order in
+// the last bits (tolerance in tests/test_heads.py).
+__device__ __forceinline__ void policy_heads(const WarpSmem& ws, const uint16_t* s_lut, uint32_t mine, int lane,
+                                             float* probs_out, float* value_out) {
+    const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
+    const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
+    const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
+    const int p = n_black == n_white ? 1 : 0;                      // Group(player to move): black moves first (Game.h:128)
+    float dw[2][8], n2[2] = { 0.f, 0.f };
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane + 32 * k, cc = c < kCells ? c : kCells - 1;
+        const int y = cc / kWidth, x = cc - y * kWidth;
+        const bool open = c < kCells && cell_value(ws.board, cc) == 0u;
+#pragma unroll
+        for (int P = 0; P < 2; ++P) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int dy = -3; dy <= 3; ++dy) {
+                const int yy = y + dy;
+                const uint32_t row = __shfl_sync(0xffffffffu, mine, P * 15 + min(max(yy, 0), kHeight - 1));
+                const uint32_t w7 = ((row << 3) >> x) & 0x7fu;
+                const uint32_t t = s_lut[(dy < 0 ? -dy : dy) * 128 + w7];
+                if (yy >= 0 && yy < kHeight) acc += t;
+            }
+            const float N = float(acc & 0xffu), W = float(acc >> 8);
+            const float v = open ? (3.f * W) / (1.f + 2.f * N) : 0.f;
+            dw[P][k] = v;
+            n2[P] += v * v;
+        }
+    }
+#pragma unroll
+    for (int P = 0; P < 2; ++P) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) n2[P] += __shfl_xor_sync(0xffffffffu, n2[P], d);
+    }
+    const float nrm0 = n2[0] > 0.f ? sqrtf(n2[0]) : 1.f, nrm1 = n2[1] > 0.f ? sqrtf(n2[1]) : 1.f;
+    const int* s_self = ws.scores + 3 * p * kCells;                // S(p, p)
+    const int* s_anti = ws.scores + (2 * (1 - p) + p) * kCells;    // S(-p, p)
+    const int* s_rival = ws.scores + 3 * (1 - p) * kCells;         // S(-p, -p)
+    float a[8], a2 = 0.f, sdot = 0.f, rdot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane + 32 * k;
+        a[k] = 0.f;
+        if (c < kCells) {
+            const float w0 = dw[0][k] / nrm0, w1 = dw[1][k] / nrm1;            // normalized DW(white), DW(black)
+            const float wp = p ? w1 : w0, wr = p ? w0 : w1;
+            const float self_worthy = float(s_self[c]) * wp, rival_anti = float(s_anti[c]) * wr;
+            a[k] = 0.6f * self_worthy + 0.4f * rival_anti;
+            a2 += a[k] * a[k];
+            sdot += float(s_self[c]) * wp;
+            rdot += float(s_rival[c]) * wr;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, d);
+        rdot += __shfl_xor_sync(0xffffffffu, rdot, d);
+    }
+    const bool empty_board = n_black + n_white == 0;
+    const float an = a2 > 0.f ? sqrtf(a2) : 1.f;
+    if (probs_out) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + 32 * k;
+            if (c < kCells) probs_out[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : a[k] / an;
+        }
+    }
+    if (value_out && lane == 0) *value_out = float(tanh((1.2 * double(sdot) - double(rdot)) / 500.0));
+}
+
+template <bool kHeads>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
 ac_eval_kernel(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -218,12 +300,24 @@ ac_eval_kernel(EvalArgs a) {
     uint32_t* s_erec = reinterpret_cast<uint32_t*>(smem_raw + align16(size_t(n_rows) * 8));
     PatRec* s_patrec = reinterpret_cast<PatRec*>(reinterpret_cast<unsigned char*>(s_erec) + align16(size_t(a.n_clones) * 4));
     uint16_t* s_src = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_patrec) + align16(size_t(a.n_patterns) * sizeof(PatRec)));
-    unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64);
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64));
+    unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_lut) + (kHeads ? 4 * 128 * sizeof(uint16_t) : 0);
 
     for (int i = threadIdx.x; i < n_rows * 4; i += blockDim.x) s_next[i] = a.next16[i];
     for (int i = threadIdx.x; i < a.n_clones; i += blockDim.x) s_erec[i] = a.erec[i];
     for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
     for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) s_src[i] = a.tape_src[i];
+    if (kHeads) {
+        // density of one window row: count | weight << 8 of the stones in a 7-bit row slice, by |dy|
+        // (Evaluator::BlockWeights, Pattern.cpp:598-609; the matrix is symmetric in dx and dy)
+        const int wts[4][7] = { { 1, 3, 4, 0, 4, 3, 1 }, { 0, 3, 5, 4, 5, 3, 0 }, { 0, 4, 3, 3, 3, 4, 0 }, { 2, 0, 0, 1, 0, 0, 2 } };
+        for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) {
+            int n = 0, w = 0;
+            for (int bit = 0; bit < 7; ++bit)
+                if ((i >> bit) & 1) { w += wts[i >> 7][bit]; n += wts[i >> 7][bit] > 0; }
+            s_lut[i] = uint16_t(n | w << 8);
+        }
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -257,9 +351,10 @@ ac_eval_kernel(EvalArgs a) {
         __syncwarp();
 
         // ---- phase 1: block score ----------------------------------------------------------------
+        uint32_t mine = 0;                                                  // this lane's 15-bit row of stones (also used by the heads)
         {
             const int pg = lane >= 15, y = lane - 15 * pg;                  // lanes 0..14 white rows, 15..29 black rows
-            uint32_t mine = 0, occ = 0;
+            uint32_t occ = 0;
             if (lane < 30) {
                 const int off = 30 * y;
                 const uint32_t lo = ws.board[off >> 5], hi = ws.board[(off >> 5) + 1];
@@ -382,6 +477,10 @@ ac_eval_kernel(EvalArgs a) {
         }
         __syncwarp();
 
+        if (kHeads) {
+            policy_heads(ws, s_lut, mine, lane, a.probs ? a.probs + b * kCells : nullptr, a.value ? a.value + b : nullptr);
+            __syncwarp();
+        }
         // ---- phase 5: output --------------------------------------------------------------------------
         if (a.scores) {
             const int4* s4 = reinterpret_cast<const int4*>(ws.scores);
@@ -431,14 +530,18 @@ static size_t table_smem_bytes(const EvalArgs& a) {
 }
 
 // warps per CTA: as many as fit beside the tables (32 for the default table; bigger custom tables get fewer)
+static bool wants_heads(const EvalArgs& a) { return a.probs != nullptr || a.value != nullptr; }
+
 static int eval_warps(const EvalArgs& a) {
-    const size_t tables = table_smem_bytes(a), per_warp = warp_bytes(a.list_cap);
+    const size_t tables = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0), per_warp = warp_bytes(a.list_cap);
     if (tables + per_warp > kSmemLimit) return 0;
     const size_t fit = (kSmemLimit - tables) / per_warp;
     return int(fit < size_t(kWarpsPerCta) ? fit : size_t(kWarpsPerCta));
 }
 
-size_t eval_smem_bytes(const EvalArgs& a) { return table_smem_bytes(a) + size_t(eval_warps(a)) * warp_bytes(a.list_cap); }
+size_t eval_smem_bytes(const EvalArgs& a) {
+    return table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) + size_t(eval_warps(a)) * warp_bytes(a.list_cap);
+}
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
@@ -446,12 +549,15 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     if (warps == 0 || a.list_cap * 32 < 2 * kCells || a.tape_steps > kMaxTapeSteps)
         return cudaErrorInvalidConfiguration;                               // table too large for shared memory
     const size_t smem = eval_smem_bytes(a);
-    cudaError_t err = cudaFuncSetAttribute(ac_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
     const long long want = (a.n + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? want : sm_count);               // persistent: one CTA per SM
-    ac_eval_kernel<<<grid, warps * 32, smem, stream>>>(a);
-    return cudaGetLastError();
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kernel<<<grid, warps * 32, smem, stream>>>(a);
+        return cudaGetLastError();
+    };
+    return wants_heads(a) ? launch(ac_eval_kernel<true>) : launch(ac_eval_kernel<false>);
 }
 
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t stream) {

@@ -16,6 +16,7 @@ struct EvalArgs {
     int root_off, start_off, list_cap;
     const uint32_t* boards; long long n;
     int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
+    float* probs; float* value;                 // policy heads for the side to move (null = not wanted)
 };
 size_t eval_smem_bytes(const EvalArgs& a);
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream);

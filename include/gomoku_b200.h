@@ -106,6 +106,20 @@ gk_status gk_eval_batch(const gk_table* table, const uint32_t* d_boards, int n,
 gk_status gk_eval_batch_host(const gk_table* table, const uint32_t* h_boards, int n,
                              int32_t* h_scores, uint16_t* h_pat_totals, uint16_t* h_cmp_totals, int8_t* h_winner);
 
+/* ---- policy heads of the pattern evaluator ("next" row f1 of SURVEY.md section 8) ----------------
+ * gk_eval_batch plus, fused into the same kernel, what TraditionalPolicy::hybridSimulate reads from
+ * the evaluator for the side to move (include/policies/Traditional.h:49-69, include/algorithms/
+ * Heuristic.hpp:16-45): d_probs float[n][225] = Heuristic::EvaluationProbs (density-weighted scores,
+ * L2-normalised as Eigen's normalized(); a single 1.0 on the centre for an empty board) and d_value
+ * float[n] = Heuristic::EvaluationValue (tanh of the weighted score balance).  Any output may be
+ * NULL; with d_scores == NULL only 904 bytes per position leave the GPU instead of 3 645.
+ * Floating point: equal to the reference up to summation order (see tests/test_heads.py). */
+gk_status gk_eval_policy_batch(const gk_table* table, const uint32_t* d_boards, int n, float* d_probs, float* d_value,
+                               int32_t* d_scores, uint16_t* d_pat_totals, uint16_t* d_cmp_totals, int8_t* d_winner,
+                               void* stream);
+gk_status gk_eval_policy_batch_host(const gk_table* table, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
+                                    int8_t* h_winner);
+
 /* ---- random rollouts ----------------------------------------------------------------
  * Replaces Default::RandomRollout / Default::Simulate (include/algorithms/MonteCarlo.hpp:
  * 37-47,83-88) and RandomPolicy::averagedSimulate (include/policies/Random.h:22-35) for

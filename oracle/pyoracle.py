@@ -221,6 +221,43 @@ def augment_planes(states, probs):
     return np.stack(st), np.stack(pr)
 
 
+# ---- policy heads (row f1): numpy restatement over an oracle's evaluator state ---------------------------
+def policy_heads(orc, move_list):
+    """Heuristic::EvaluationProbs / EvaluationValue / DensityWeight (include/algorithms/Heuristic.hpp:16-45)
+    for the side to move, computed from the scores and density arrays of `orc` (the C restatement or the
+    compiled reference) after replaying `move_list`.  float32 throughout, as the reference's VectorXf;
+    only the summation order is numpy's instead of Eigen's.  -> (probs f32[225], value f32)"""
+    f32 = np.float32
+    r = orc.eval_moves(move_list)
+    assert r["bad"] == 0
+    _, _, den = orc.eval_flags()
+    den = den.reshape(2, 2, 225)                                  # [Group(player)][count | weight][cell], Pattern.h:218
+    scores = r["scores"].astype(f32)                              # [Group(favour, perspective)][cell]
+    p = 1 if len(move_list) % 2 == 0 else 0                       # Group(player to move); black moves first
+
+    def density_weight(g):                                        # :40-45  normalize(3W / (1 + 2N)), max(x, 0) filter
+        n = np.maximum(den[g, 0], 0).astype(f32)
+        w = np.maximum(den[g, 1], 0).astype(f32)
+        v = (f32(3) * w) / (f32(1) + f32(2) * n)
+        z = f32(np.sum(v * v, dtype=f32))
+        return v / f32(np.sqrt(z)) if z > 0 else v                # Eigen normalized(): unchanged when the norm is 0
+
+    dw_self, dw_rival = density_weight(p), density_weight(1 - p)
+    if len(move_list) > 0:                                        # :18-23
+        self_worthy = scores[3 * p] * dw_self                     # scores(player, player)
+        rival_anti = scores[2 * (1 - p) + p] * dw_rival           # scores(-player, player)
+        a = f32(0.6) * self_worthy + f32(0.4) * rival_anti
+        z = f32(np.sum(a * a, dtype=f32))
+        probs = a / f32(np.sqrt(z)) if z > 0 else a
+    else:                                                         # :24-27 empty board: the centre
+        probs = np.zeros(225, f32)
+        probs[7 * 15 + 7] = 1.0
+    sw = f32(np.dot(scores[3 * p], dw_self))                      # :33-35
+    rw = f32(np.dot(scores[3 * (1 - p)], dw_rival))
+    value = f32(np.tanh((1.2 * float(sw) - float(rw)) / 500.0))
+    return probs.astype(f32), value
+
+
 class PortOracle(Oracle):
     """extras only the C restatement has (Philox stream, apply/revert, degenerate counter)"""
 
