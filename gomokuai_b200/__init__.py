@@ -289,6 +289,28 @@ def eval_policy_batch_host(boards, table=None):
     return probs, value, winner
 
 
+def guided_rollout_batch(boards, mode="max", key=SYNTH_KEY, ctr_hi=0, game_base=0, max_moves=CELLS, want_moves=True,
+                         table=None, stream=None):
+    """Pattern-guided playouts (Heuristic::EvaluatedRollout, include/algorithms/Heuristic.hpp:61-91), one warp per game,
+    whole games inside one kernel.  mode "max" = MaxEvaluatedRollout, "sample" = RandomEvaluatedRollout.
+    Returns dict(winner[n] i8, length[n] i16, moves[n,max_moves] i16 (-1 padded), final_boards[n,16] i32)."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    table = table or default_table()
+    n, dev = boards.shape[0], boards.device
+    out = {
+        "winner": torch.empty((n,), dtype=torch.int8, device=dev),
+        "length": torch.empty((n,), dtype=torch.int16, device=dev),
+        "moves": torch.full((n, max_moves), -1, dtype=torch.int16, device=dev) if want_moves else None,
+        "final_boards": torch.empty((n, BOARD_WORDS), dtype=torch.int32, device=dev),
+    }
+    _check(lib().gk_guided_rollout_batch(table.handle, _ptr(boards), n, {"max": 1, "sample": 2}[mode], ctypes.c_uint64(key),
+                                         ctypes.c_uint32(ctr_hi), int(game_base), int(max_moves), _ptr(out["winner"]),
+                                         _ptr(out["length"]), _ptr(out["moves"]), _ptr(out["final_boards"]),
+                                         _stream_ptr(stream)))
+    return out
+
+
 def rollout_batch(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_base=0, want_trace=False, stream=None):
     """Random playouts. Returns dict(wdb[n,3] i32 = {white, draw, black}, winners[n,R] i8, lengths[n,R] u8)."""
     torch = _torch()

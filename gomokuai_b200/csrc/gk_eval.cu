@@ -221,7 +221,7 @@ __host__ __device__ inline size_t warp_bytes(int list_cap) { return sizeof(WarpS
 // Floating point: sums run lane-strided then by warp shuffle, so they differ from Eigen's packet order in
 // the last bits (tolerance in tests/test_heads.py).
 __device__ __forceinline__ void policy_heads(const WarpSmem& ws, const uint16_t* s_lut, uint32_t mine, int lane,
-                                             float* probs_out, float* value_out) {
+                                             float* probs_out, float* value_out, float (&pr)[8], int& n_stones, int& to_move) {
     const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
     const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
     const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
@@ -281,17 +281,76 @@ __device__ __forceinline__ void policy_heads(const WarpSmem& ws, const uint16_t*
     }
     const bool empty_board = n_black + n_white == 0;
     const float an = a2 > 0.f ? sqrtf(a2) : 1.f;
-    if (probs_out) {
+    n_stones = n_black + n_white;
+    to_move = p;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = lane + 32 * k;
-            if (c < kCells) probs_out[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : a[k] / an;
-        }
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane + 32 * k;
+        pr[k] = c >= kCells ? 0.f : empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : a[k] / an;
+        if (probs_out && c < kCells) probs_out[c] = pr[k];
     }
     if (value_out && lane == 0) *value_out = float(tanh((1.2 * double(sdot) - double(rdot)) / 500.0));
 }
 
-template <bool kHeads>
+__device__ __forceinline__ uint32_t philox_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                               uint32_t which) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return which == 0 ? c0 : which == 1 ? c1 : which == 2 ? c2 : c3;
+}
+
+// The move of one step of Heuristic::EvaluatedRollout (include/algorithms/Heuristic.hpp:61-91) from the
+// probabilities held by the warp (lane owns cells lane + 32 k).  Returns -1 when no cell has weight.
+//   mode 1  MaxEvaluatedRollout: the most probable cell, lowest index among equals (Eigen maxCoeff)
+//   mode 2  RandomEvaluatedRollout: a draw from the discrete distribution `probs` (Board::getRandomMove(probs),
+//           Game.cpp:75-78).  The reference's std::discrete_distribution / mt19937 stream is implementation
+//           defined; here the weights are quantised to w = round(p * 2^20), cells are ordered by index, and the
+//           draw is r = mulhi32(philox word, sum w): the first cell whose running sum exceeds r.
+__device__ __forceinline__ int select_move(const float (&pr)[8], int lane, int mode, uint32_t rnd) {
+    if (mode == 1) {
+        float best = 0.f;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (pr[k] > best) { best = pr[k]; arg = lane + 32 * k; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        return best > 0.f ? arg : -1;
+    }
+    uint32_t w[8], base = 0;
+    int chosen = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = uint32_t(pr[k] * 1048576.f + 0.5f);
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) total += w[k];
+    total = __reduce_add_sync(0xffffffffu, total);
+    if (total == 0) return -1;
+    const uint32_t r = __umulhi(rnd, total);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {                                  // cells 32 k .. 32 k + 31 in index order
+        uint32_t incl = w[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (w[k] != 0 && base + incl > r && base + incl - w[k] <= r) chosen = lane + 32 * k;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return __reduce_min_sync(0xffffffffu, chosen);
+}
+
+template <bool kHeads, bool kGuided>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
 ac_eval_kernel(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -342,6 +401,8 @@ ac_eval_kernel(EvalArgs a) {
         }
         if (lane == 14) bw |= 0xfffffffcu;                                  // cells 225.. are pads
         if (lane == 15) bw = 0xffffffffu;
+        int played = 0, result = 0;                                         // guided mode: moves played so far / final winner
+      next_move:                                                            // guided mode re-enters here after every move
         if (lane < kBoardSmem) ws.board[lane] = bw;
         {
             int4* z = reinterpret_cast<int4*>(ws.scores);
@@ -478,8 +539,34 @@ ac_eval_kernel(EvalArgs a) {
         __syncwarp();
 
         if (kHeads) {
-            policy_heads(ws, s_lut, mine, lane, a.probs ? a.probs + b * kCells : nullptr, a.value ? a.value + b : nullptr);
+            float pr[8];
+            int n_stones, to_move;
+            policy_heads(ws, s_lut, mine, lane, (a.probs && !kGuided) ? a.probs + b * kCells : nullptr,
+                         (a.value && !kGuided) ? a.value + b : nullptr, pr, n_stones, to_move);
             __syncwarp();
+            if (kGuided) {
+                // Heuristic::EvaluatedRollout (Heuristic.hpp:61-72): while (!ev.checkGameEnd()) applyMove(probs_to_move(...))
+                const uint32_t won = __reduce_or_sync(0xffffffffu, win);
+                int cell = -1;
+                if (won) result = (won & 1u) ? 1 : -1;                       // a Five emission ended the game, Pattern.cpp:140-145
+                else if (n_stones < kCells && played < a.g_max_moves) {      // Evaluator::checkGameEnd, Pattern.cpp:343-353
+                    uint32_t rnd = 0;
+                    if (a.g_mode == 2)
+                        rnd = philox_word(uint32_t(played) >> 2, 0u, uint32_t(a.g_game_base) + uint32_t(b), a.g_ctr_hi, a.g_key_lo,
+                                          a.g_key_hi, uint32_t(played) & 3u);
+                    cell = select_move(pr, lane, a.g_mode, rnd);
+                }
+                if (cell >= 0) {
+                    if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
+                    if (lane == (cell >> 4)) bw |= (to_move ? 1u : 2u) << ((cell & 15) * 2);
+                    ++played;
+                    __syncwarp();
+                    goto next_move;
+                }
+                if (a.g_winner && lane == 0) a.g_winner[b] = (int8_t)result;
+                if (a.g_length && lane == 0) a.g_length[b] = (int16_t)played;
+                if (a.g_final && lane < kBoardWords) a.g_final[b * kBoardWords + lane] = lane == 14 ? (bw & 3u) : lane == 15 ? 0u : bw;
+            }
         }
         // ---- phase 5: output --------------------------------------------------------------------------
         if (a.scores) {
@@ -530,7 +617,7 @@ static size_t table_smem_bytes(const EvalArgs& a) {
 }
 
 // warps per CTA: as many as fit beside the tables (32 for the default table; bigger custom tables get fewer)
-static bool wants_heads(const EvalArgs& a) { return a.probs != nullptr || a.value != nullptr; }
+static bool wants_heads(const EvalArgs& a) { return a.probs != nullptr || a.value != nullptr || a.g_mode != 0; }
 
 static int eval_warps(const EvalArgs& a) {
     const size_t tables = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0), per_warp = warp_bytes(a.list_cap);
@@ -557,7 +644,8 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
         kernel<<<grid, warps * 32, smem, stream>>>(a);
         return cudaGetLastError();
     };
-    return wants_heads(a) ? launch(ac_eval_kernel<true>) : launch(ac_eval_kernel<false>);
+    if (a.g_mode != 0) return launch(ac_eval_kernel<true, true>);
+    return wants_heads(a) ? launch(ac_eval_kernel<true, false>) : launch(ac_eval_kernel<false, false>);
 }
 
 cudaError_t launch_scan(const ScanArgs& a, cudaStream_t stream) {

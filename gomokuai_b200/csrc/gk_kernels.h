@@ -17,6 +17,10 @@ struct EvalArgs {
     const uint32_t* boards; long long n;
     int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
     float* probs; float* value;                 // policy heads for the side to move (null = not wanted)
+    // guided playouts (g_mode != 0): every warp plays its board to the end inside the kernel
+    int g_mode;                                 // 0 off, 1 most probable move, 2 move drawn from the probabilities
+    uint32_t g_key_lo, g_key_hi, g_ctr_hi; int g_game_base, g_max_moves;
+    int8_t* g_winner; int16_t* g_length; int16_t* g_moves; uint32_t* g_final;   // per game; any may be null
 };
 size_t eval_smem_bytes(const EvalArgs& a);
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream);

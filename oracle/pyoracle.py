@@ -258,6 +258,37 @@ def policy_heads(orc, move_list):
     return probs.astype(f32), value
 
 
+def guided_rollout(orc, port_oracle, move_list, mode, key, game, ctr_hi=0, max_moves=225):
+    """Heuristic::EvaluatedRollout (include/algorithms/Heuristic.hpp:61-91) from the position after `move_list`:
+    while the evaluator has no winner and the board is not full, play the move chosen from policy_heads --
+    mode "max": first maximum (MaxEvaluatedRollout); mode "sample": the documented quantised draw of
+    include/gomoku_b200.h (weights round(p * 2^20), r = mulhi32(Philox word, sum)).  -> (winner, moves played)"""
+    moves, played = list(move_list), []
+    f32 = np.float32
+    while True:
+        r = orc.eval_moves(moves)
+        if r["winner"] != 0:
+            return int(r["winner"]), played
+        if len(moves) == 225 or len(played) >= max_moves:
+            return 0, played
+        probs, _ = policy_heads(orc, moves)
+        if mode == "max":
+            if not (probs.max() > 0):
+                return 0, played
+            cell = int(np.argmax(probs))                            # first maximum, as Eigen's maxCoeff(&index)
+        else:
+            w = (probs * f32(1048576.0) + f32(0.5)).astype(np.uint32)
+            total = int(w.sum(dtype=np.uint64))
+            if total == 0:
+                return 0, played
+            k = len(played)
+            word = port_oracle.philox([k >> 2, 0, game, ctr_hi], [key & 0xffffffff, key >> 32])[k & 3]
+            rr = (word * total) >> 32
+            cell = int(np.searchsorted(np.cumsum(w.astype(np.uint64)), rr, side="right"))
+        moves.append(cell)
+        played.append(cell)
+
+
 class PortOracle(Oracle):
     """extras only the C restatement has (Philox stream, apply/revert, degenerate counter)"""
 

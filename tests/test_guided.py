@@ -1,0 +1,69 @@
+"""Pattern-guided playouts (BASELINE config 5): Heuristic::EvaluatedRollout semantics
+(include/algorithms/Heuristic.hpp:61-91) with every game played to its end inside one kernel.
+
+Parity statement.  The moves are chosen from floating-point probabilities (tests/test_heads.py states their
+tolerance), so a trajectory can legitimately differ from the CPU restatement where two candidate cells are
+closer than that tolerance.  The test therefore requires: every game is LEGAL and correctly adjudicated
+(replayed through the oracle's Board), and >= 97 % of the games are move-for-move identical to the oracle's
+restatement of the loop (measured here: see the assertion message on failure)."""
+import numpy as np
+import pytest
+
+from conftest import random_positions
+from oracle import pyoracle
+
+KEY = 0x474F4D4F4B5531
+
+
+def _starts(seed, n):
+    port = pyoracle.port()
+    lists = [[], [112], [0], [224, 210]] + random_positions(seed, n, lo=2, hi=60)
+    return [m for m in lists if port.eval_moves(m)["winner"] == 0]
+
+
+def test_oracle_guided_rollout_is_a_legal_game(port):
+    for mode in ("max", "sample"):
+        for g, m in enumerate(_starts(4, 12)):
+            winner, played = pyoracle.guided_rollout(port, port, m, mode, KEY, g)
+            full = list(m) + played
+            assert len(set(full)) == len(full) and all(0 <= c < 225 for c in full)
+            r = port.board_play(full)
+            assert r["applied"] == len(full) and r["winner"] == winner
+            assert winner != 0 or len(full) == 225 or len(played) == 0 or port.eval_moves(full)["winner"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["max", "sample"])
+def test_gpu_guided_rollouts_vs_oracle(gpu, mode):
+    port = pyoracle.port()
+    lists = _starts(31, 160)
+    mv, st = pyoracle.pack_moves(lists)
+    out = gpu.guided_rollout_batch(gpu.pack_moves(mv, st), mode=mode, key=KEY, game_base=1000)
+    winner, length, moves = out["winner"].cpu().numpy(), out["length"].cpu().numpy(), out["moves"].cpu().numpy()
+    final = out["final_boards"].cpu().numpy().view(np.uint32)
+    same = 0
+    for i, m in enumerate(lists):
+        played = moves[i, :length[i]].tolist()
+        full = list(m) + played
+        assert (moves[i, length[i]:] == -1).all()
+        assert len(set(full)) == len(full)                              # legal: no cell twice
+        r = port.board_play(full)                                       # adjudication by the oracle's Board
+        assert r["applied"] == len(full) and r["winner"] == winner[i], (i, full)
+        if winner[i] == 0:
+            assert len(full) == 225 or port.eval_moves(full)["winner"] == 0
+        fm, fs = pyoracle.pack_moves([full])
+        assert np.array_equal(gpu.pack_moves(fm, fs)[0], final[i])
+        w, p = pyoracle.guided_rollout(port, port, m, mode, KEY, 1000 + i)
+        same += int(w == winner[i] and p == played)
+    assert same >= 0.97 * len(lists), f"{same} of {len(lists)} games identical to the oracle"
+
+
+@pytest.mark.gpu
+def test_gpu_guided_max_moves_and_determinism(gpu):
+    boards, _, _ = gpu.synth_positions(0, 64)
+    a = gpu.guided_rollout_batch(boards, mode="sample", key=KEY, max_moves=3)
+    assert int(a["length"].max()) <= 3
+    b = gpu.guided_rollout_batch(boards, mode="sample", key=KEY)
+    c = gpu.guided_rollout_batch(boards[32:], mode="sample", key=KEY, game_base=32)
+    assert np.array_equal(b["moves"].cpu().numpy()[32:], c["moves"].cpu().numpy())   # independent of batch split
+    assert np.array_equal(b["winner"].cpu().numpy()[32:], c["winner"].cpu().numpy())
