@@ -275,15 +275,33 @@ def eval_policy_batch(boards, table=None, want_scores=False, stream=None):
     return out
 
 
-def eval_policy_batch_host(boards, table=None):
-    """Same through HOST buffers: returns numpy (probs[n,225] f32, value[n] f32, winner[n] i8)."""
+def hybrid_simulate_batch(boards, table=None, want_flags=False, stream=None):
+    """TraditionalPolicy::hybridSimulate for a batch (include/policies/Traditional.h:49-69): probs after
+    Heuristic::DecisiveFilter, value, winner (+ the per-cell decisive flag words if want_flags)."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    table = table or default_table()
+    n, dev = boards.shape[0], boards.device
+    out = {"probs": torch.empty((n, CELLS), dtype=torch.float32, device=dev),
+           "value": torch.empty((n,), dtype=torch.float32, device=dev),
+           "winner": torch.empty((n,), dtype=torch.int8, device=dev),
+           "dflags": torch.empty((n, CELLS), dtype=torch.int32, device=dev) if want_flags else None}
+    _check(lib().gk_hybrid_simulate_batch(table.handle, _ptr(boards), n, _ptr(out["probs"]), _ptr(out["value"]),
+                                          _ptr(out["winner"]), _ptr(out["dflags"]), _stream_ptr(stream)))
+    return out
+
+
+def eval_policy_batch_host(boards, table=None, decisive=False):
+    """Same through HOST buffers: returns numpy (probs[n,225] f32, value[n] f32, winner[n] i8).
+    decisive=True applies Heuristic::DecisiveFilter (= gk_hybrid_simulate_batch_host)."""
     table = table or default_table()
     _require_init()
     b = boards.numpy() if hasattr(boards, "numpy") else boards
     b = np.ascontiguousarray(b).view(np.uint32).reshape(-1, BOARD_WORDS)
     n = b.shape[0]
     probs, value, winner = np.empty((n, CELLS), np.float32), np.empty((n,), np.float32), np.empty((n,), np.int8)
-    _check(lib().gk_eval_policy_batch_host(table.handle, b.ctypes.data_as(ctypes.c_void_p), n,
+    fn = lib().gk_hybrid_simulate_batch_host if decisive else lib().gk_eval_policy_batch_host
+    _check(fn(table.handle, b.ctypes.data_as(ctypes.c_void_p), n,
                                            probs.ctypes.data_as(ctypes.c_void_p), value.ctypes.data_as(ctypes.c_void_p),
                                            winner.ctypes.data_as(ctypes.c_void_p)))
     return probs, value, winner

@@ -374,8 +374,32 @@ gk_status gk_eval_policy_batch(const gk_table* t, const uint32_t* d_boards, int 
     return GK_OK;
 }
 
+gk_status gk_hybrid_simulate_batch(const gk_table* t, const uint32_t* d_boards, int n, float* d_probs, float* d_value,
+                                   int8_t* d_winner, uint32_t* d_dflags, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (!t || n < 0 || (n > 0 && (!d_boards || !d_probs))) return fail(GK_ERR_INVALID, "bad arguments");
+    if (gk_status s = ensure_uploaded(t)) return s;
+    gk::EvalArgs a = eval_args(t, d_boards, n, nullptr, nullptr, nullptr, d_winner);
+    a.probs = d_probs; a.value = d_value; a.decisive = 1; a.dflags = d_dflags;
+    GK_CUDA(gk::launch_eval(a, g_sm_count, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
+static gk_status policy_host(const gk_table* t, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
+                             int8_t* h_win, int decisive);
+
+gk_status gk_hybrid_simulate_batch_host(const gk_table* t, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
+                                        int8_t* h_win) {
+    return policy_host(t, h_boards, n, h_probs, h_value, h_win, 1);
+}
+
 gk_status gk_eval_policy_batch_host(const gk_table* t, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
                                     int8_t* h_win) {
+    return policy_host(t, h_boards, n, h_probs, h_value, h_win, 0);
+}
+
+static gk_status policy_host(const gk_table* t, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
+                             int8_t* h_win, int decisive) {
     if (gk_status s = require_device()) return s;
     if (!t || n < 0 || (n > 0 && !h_boards)) return fail(GK_ERR_INVALID, "bad arguments");
     if (gk_status s = ensure_uploaded(t)) return s;
@@ -391,7 +415,7 @@ gk_status gk_eval_policy_batch_host(const gk_table* t, const uint32_t* h_boards,
         float* d_value = d_probs + size_t(chunk) * 225;
         GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
         gk::EvalArgs a = eval_args(t, p.d_boards, m, nullptr, nullptr, nullptr, h_win ? p.d_win : nullptr);
-        a.probs = h_probs ? d_probs : nullptr; a.value = h_value ? d_value : nullptr;
+        a.probs = h_probs ? d_probs : nullptr; a.value = h_value ? d_value : nullptr; a.decisive = decisive;
         if (!a.probs && !a.value) a.value = d_value;
         GK_CUDA(gk::launch_eval(a, g_sm_count, p.stream));
         if (h_probs) GK_CUDA(cudaMemcpyAsync(h_probs + size_t(at) * 225, d_probs, size_t(m) * 900, cudaMemcpyDeviceToHost, p.stream));

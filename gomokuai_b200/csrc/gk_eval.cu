@@ -83,7 +83,12 @@ __device__ __forceinline__ uint32_t squeeze_even(uint32_t x) {
 
 // One emission of pattern `rec` whose last char sits on virtual cell `vend` of a line with the
 // given direction (Updater::updatePatterns, Pattern.cpp:138-165).  Returns winner bits.
-__device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, const PatRec rec, int vend, uint32_t dir, int stride) {
+// dflags (policy-head variants only): per cell, which (type >= DeadThree, favour, perspective) pattern flags and
+// which (compound type, favour, perspective) compound flags are set in ANY direction -- what
+// Heuristic::DecisiveFilter reads through Record::get(favour, perspective) (Heuristic.hpp:147-151):
+//   bit (type - 4) * 4 + Group(favour, perspective), bit 16 + compound type * 4 + Group(favour, perspective)
+__device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflags, const PatRec rec, int vend, uint32_t dir,
+                                                   int stride) {
     const uint32_t type = pr_type(rec.w0), black = pr_black(rec.w0);
     if (type == kTypeFive) return black ? 1u : 2u;                              // :140-145
     atomicAdd(&ws.totals[black * 8 + type], 1u);                                // :147
@@ -110,14 +115,20 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, const PatRec re
             if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
         }
     }
+    if (dflags && type >= 4u) {                                                 // update_pose: '_' both perspectives, '^' the rival's, :153-161
+        const uint32_t rival_bit = 1u << ((type - 4u) * 4u + black + 1u), self_bit = 1u << ((type - 4u) * 4u + black * 3u);
+        uint32_t cells = rec.w0;
+        for (uint32_t n = ncells; n != 0; --n, cells >>= 4)
+            atomicOr(&dflags[vend - int(cells & 7u) * stride], (cells & 8u) ? (rival_bit | self_bit) : rival_bit);
+    }
     return 0;
 }
 
 // Compound::updateAntis (Pattern.cpp:520-543): rescan the 13-symbol window centred on `cell`
 // from the root state and give +600 (rival's perspective) to the other '_' / '^' cells of the
 // first emission of class `cclass` that has `cell` on a '_'.
-__device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t next_addr, uint32_t root_off, uint32_t emit_thr,
-                                           const uint32_t* s_erec, const PatRec* s_patrec,
+__device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t* dflags, uint32_t anti_bit, uint32_t next_addr,
+                                           uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
                                            int cell, uint32_t dir, uint32_t cclass, int* rival) {
     const int cx = cell % kWidth, cy = cell / kWidth;
     const int stride = dir_stride(dir);
@@ -157,7 +168,10 @@ __device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t next_addr, uin
             cells = rec.w0;
             for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) {
                 const int j = int(cells & 7u);
-                if (j != off) atomicAdd(&rival[cell + (off - j) * stride], 600);
+                if (j != off) {
+                    atomicAdd(&rival[cell + (off - j) * stride], 600);          // updatePose(current, component, -favour), :536
+                    if (dflags) atomicOr(&dflags[cell + (off - j) * stride], anti_bit);
+                }
             }
             return;                                                             // only the first such pattern, :540
         }
@@ -167,7 +181,7 @@ __device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t next_addr, uin
 // Compound::locate + updateCritical for one (cell, player) whose flags passed Compound::Test
 // (Pattern.cpp:440-518).  Returns the two updateAntis tasks in t0 / t1 (0 = none):
 // cell | black << 8 | dir << 9 | class << 11 | 1 << 13.
-__device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t idx, uint32_t& t0, uint32_t& t1) {
+__device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t* dflags, uint32_t idx, uint32_t& t0, uint32_t& t1) {
     const uint32_t f = ws.flags[idx];
     const int cell = idx >> 1;
     const uint32_t black = idx & 1u;
@@ -204,11 +218,15 @@ __device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t idx, uint32_t
     atomicAdd(&ws.scores[black * 3 * kCells + cell], 600 * ncomp);              // updateCritical, :515-518
     atomicAdd(&ws.scores[(black + 1) * kCells + cell], 600 * ncomp);
     atomicAdd(&ws.totals[16 + black * 3 + type], 1u);                           // one compound, :505-508
-    if (!triple && l3 == 0) { t0 = first; t1 = second; }                        // exactly two components here, :500-502
+    if (dflags) atomicOr(&dflags[cell], (1u << (16 + type * 4 + black * 3)) | (1u << (16 + type * 4 + black + 1)));   // updateCritical
+    if (!triple && l3 == 0) { t0 = first | uint32_t(type) << 14; t1 = second | uint32_t(type) << 14; }   // exactly two components here, :500-502
 }
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-__host__ __device__ inline size_t warp_bytes(int list_cap) { return sizeof(WarpSmem) + size_t(list_cap) * 64; }
+constexpr int kDflagWords = 228;                                               // 225 used (16-byte multiple)
+__host__ __device__ inline size_t warp_bytes(int list_cap, bool heads) {
+    return sizeof(WarpSmem) + size_t(list_cap) * 64 + (heads ? kDflagWords * 4 : 0);
+}
 
 // Heuristic::DensityWeight / EvaluationProbs / EvaluationValue (include/algorithms/Heuristic.hpp:16-45) for the
 // side to move, from the finished score maps of one board.  `mine` is the lane's 15-bit row mask
@@ -290,6 +308,49 @@ __device__ __forceinline__ void policy_heads(const WarpSmem& ws, const uint16_t*
         if (probs_out && c < kCells) probs_out[c] = pr[k];
     }
     if (value_out && lane == 0) *value_out = float(tanh((1.2 * double(sdot) - double(rdot)) / 500.0));
+}
+
+// Heuristic::DecisiveFilter (include/algorithms/Heuristic.hpp:93-161): walk the priority automaton
+// +4 > -4 > +L3 == +To44 > -L3 == -To44 >= +To43 > -To43 > +To33 > -To33 over the pattern / compound totals; at the
+// first class with a non-zero count keep only the cells flagged for one of the remaining candidates
+// (Record::get(player, cur_player), any direction) and re-normalise.  p = Group(side to move).
+__device__ __forceinline__ void decisive_filter(const WarpSmem& ws, const uint32_t* dflags, float (&pr)[8], int p, int lane) {
+    // the automaton table (:101-105) visits (state, anti) in this fixed order until a candidate has a count
+    //   state: 0 = _4 {LiveFour, DeadFour}, 1 = L3 {LiveThree}, 2..4 = To44 / To43 / To33 {compound 2 / 1 / 0}
+    const int order[10][2] = { { 0, 0 }, { 0, 1 }, { 1, 0 }, { 2, 0 }, { 1, 1 }, { 2, 1 }, { 3, 0 }, { 3, 1 }, { 4, 0 }, { 4, 1 } };
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        if (mask) break;
+        const int state = order[i][0], anti = order[i][1];
+        const int pl = anti ? 1 - p : p, g = 2 * pl + p;                        // Group(favour = pl, perspective = cur)
+        if (state == 0) {
+            const uint32_t l4 = ws.totals[pl * 8 + 7], d4 = ws.totals[pl * 8 + 6];
+            if (l4) mask = (1u << (3 * 4 + g)) | (1u << (2 * 4 + g));           // [LiveFour, DeadFour] both stay queued
+            else if (d4) mask = 1u << (2 * 4 + g);
+        } else if (state == 1) {
+            if (ws.totals[pl * 8 + 5]) mask = 1u << (1 * 4 + g);
+        } else {
+            const int ct = 4 - state;                                           // Pattern::Size + (To33 - state)
+            if (ws.totals[16 + pl * 3 + ct]) mask = 1u << (16 + ct * 4 + g);
+        }
+        if (mask && anti && state != 0) mask |= 1u << (0 * 4 + 2 * (1 - pl) + p);   // own DeadThree also counters, :133-135
+    }
+    if (!mask) return;
+    float n2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = lane + 32 * k;
+        if (c >= kCells || !(dflags[c] & mask)) pr[k] = 0.f;
+        n2 += pr[k] * pr[k];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, d);
+    if (n2 > 0.f) {
+        const float nrm = sqrtf(n2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pr[k] = pr[k] / nrm;
+    }
 }
 
 __device__ __forceinline__ uint32_t philox_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -381,8 +442,9 @@ ac_eval_kernel(EvalArgs a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cap = a.list_cap;
-    WarpSmem& ws = *reinterpret_cast<WarpSmem*>(s_warps + size_t(warp) * warp_bytes(cap));
+    WarpSmem& ws = *reinterpret_cast<WarpSmem*>(s_warps + size_t(warp) * warp_bytes(cap, kHeads));
     uint16_t* lists = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(&ws) + sizeof(WarpSmem));   // [lane][cap]
+    uint32_t* dflags = kHeads ? reinterpret_cast<uint32_t*>(lists + 32 * cap) : nullptr;
     const uint32_t lt = lanemask_lt();
     const uint32_t emit_thr = uint32_t(a.n_clones) * 8u;
     // shared-window addresses, made opaque so the compiler keeps them in registers instead of
@@ -408,6 +470,7 @@ ac_eval_kernel(EvalArgs a) {
             int4* z = reinterpret_cast<int4*>(ws.scores);
             for (int i = lane; i < (kScoreWords + kFlagWords) / 4; i += 32) z[i] = make_int4(0, 0, 0, 0);   // scores + flags are contiguous
             if (lane < kTotalWords) ws.totals[lane] = 0;
+            if (kHeads) for (int i = lane; i < kDflagWords; i += 32) dflags[i] = 0;
         }
         __syncwarp();
 
@@ -486,9 +549,9 @@ ac_eval_kernel(EvalArgs a) {
                 const uint32_t inf = __ldg(a.tape_info + (ent & 63u) * 32u + uint32_t(j));
                 const uint32_t dir = (inf >> 9) & 3u;
                 const int vcell = inf & 0x1ff, stride = int(inf >> 11);
-                win |= apply_emission(ws, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir, stride);
+                win |= apply_emission(ws, dflags, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir, stride);
                 const uint32_t p1 = er_pid(er, 1);
-                if (p1 != kDevNoPid) win |= apply_emission(ws, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir, stride);
+                if (p1 != kDevNoPid) win |= apply_emission(ws, dflags, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir, stride);
             }
         }
         __syncwarp();
@@ -519,7 +582,7 @@ ac_eval_kernel(EvalArgs a) {
             __syncwarp();
             for (int base = 0; base < cn; base += 32) {                             // warp-uniform trip count
                 uint32_t t0 = 0, t1 = 0;
-                if (base + lane < cn) compound_at(ws, clist[base + lane], t0, t1);
+                if (base + lane < cn) compound_at(ws, dflags, clist[base + lane], t0, t1);
                 // spread the window rescans: task s = 2 * (rank of the owning lane) + which
                 const uint32_t owners = __ballot_sync(0xffffffffu, t0 != 0);
                 const int ntask = 2 * __popc(owners);
@@ -530,8 +593,9 @@ ac_eval_kernel(EvalArgs a) {
                     const uint32_t task = (s & 1) ? tb : ta;
                     if (s < ntask) {
                         const uint32_t black = (task >> 8) & 1u;
-                        anti_cells(ws, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, int(task & 0xffu),
-                                   (task >> 9) & 3u, (task >> 11) & 3u, ws.scores + (black + 1) * kCells);
+                        anti_cells(ws, dflags, 1u << (16 + ((task >> 14) & 3u) * 4 + black + 1), next_addr, uint32_t(a.root_off),
+                                   emit_thr, s_erec, s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
+                                   ws.scores + (black + 1) * kCells);
                     }
                 }
             }
@@ -541,9 +605,17 @@ ac_eval_kernel(EvalArgs a) {
         if (kHeads) {
             float pr[8];
             int n_stones, to_move;
-            policy_heads(ws, s_lut, mine, lane, (a.probs && !kGuided) ? a.probs + b * kCells : nullptr,
-                         (a.value && !kGuided) ? a.value + b : nullptr, pr, n_stones, to_move);
+            policy_heads(ws, s_lut, mine, lane, nullptr, (a.value && !kGuided) ? a.value + b : nullptr, pr, n_stones, to_move);
             __syncwarp();
+            if (!kGuided) {
+                if (a.decisive) decisive_filter(ws, dflags, pr, to_move, lane);  // TraditionalPolicy::hybridSimulate, Traditional.h:52-53
+                if (a.probs) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (lane + 32 * k < kCells) a.probs[b * kCells + lane + 32 * k] = pr[k];
+                }
+                if (a.dflags) for (int i = lane; i < kCells; i += 32) a.dflags[b * kCells + i] = dflags[i];
+            }
             if (kGuided) {
                 // Heuristic::EvaluatedRollout (Heuristic.hpp:61-72): while (!ev.checkGameEnd()) applyMove(probs_to_move(...))
                 const uint32_t won = __reduce_or_sync(0xffffffffu, win);
@@ -617,17 +689,21 @@ static size_t table_smem_bytes(const EvalArgs& a) {
 }
 
 // warps per CTA: as many as fit beside the tables (32 for the default table; bigger custom tables get fewer)
-static bool wants_heads(const EvalArgs& a) { return a.probs != nullptr || a.value != nullptr || a.g_mode != 0; }
+static bool wants_heads(const EvalArgs& a) {
+    return a.probs != nullptr || a.value != nullptr || a.g_mode != 0 || a.dflags != nullptr;
+}
 
 static int eval_warps(const EvalArgs& a) {
-    const size_t tables = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0), per_warp = warp_bytes(a.list_cap);
+    const size_t tables = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0),
+                 per_warp = warp_bytes(a.list_cap, wants_heads(a));
     if (tables + per_warp > kSmemLimit) return 0;
     const size_t fit = (kSmemLimit - tables) / per_warp;
     return int(fit < size_t(kWarpsPerCta) ? fit : size_t(kWarpsPerCta));
 }
 
 size_t eval_smem_bytes(const EvalArgs& a) {
-    return table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) + size_t(eval_warps(a)) * warp_bytes(a.list_cap);
+    return table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) +
+           size_t(eval_warps(a)) * warp_bytes(a.list_cap, wants_heads(a));
 }
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {

@@ -17,6 +17,8 @@ struct EvalArgs {
     const uint32_t* boards; long long n;
     int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
     float* probs; float* value;                 // policy heads for the side to move (null = not wanted)
+    int decisive;                               // apply Heuristic::DecisiveFilter to probs
+    uint32_t* dflags;                           // [n][225] per-cell decisive flag bits (gk_eval.cu), for inspection; may be null
     // guided playouts (g_mode != 0): every warp plays its board to the end inside the kernel
     int g_mode;                                 // 0 off, 1 most probable move, 2 move drawn from the probabilities
     uint32_t g_key_lo, g_key_hi, g_ctr_hi; int g_game_base, g_max_moves;

@@ -120,6 +120,48 @@ Policy::EvalResult RandomPolicy::averagedSimulate(Board& board) {               
     return { Default::GpuRolloutValue(board, static_cast<int>(c_rollouts)), Default::UniformProbs(board) };
 }
 
+// ---- RAVE select / update without AMAF (MonteCarlo.hpp:150-186) --------------------------------------------------
+Node* RAVE::Select(Policy*, const Node* node) { return node->children[0].get(); }          // :150-153
+
+void RAVE::BackPropogate(Policy* policy, Node* node, Board&, double value) {               // :156-186 with UseRave = false
+    float v = static_cast<float>(value);
+    for (; node != nullptr; node = node->parent, v = -v) {
+        std::size_t max_index = 0;
+        double max_score = -std::numeric_limits<double>::infinity();
+        for (std::size_t i = 0; i < node->children.size(); ++i) {
+            const Node* child = node->children[i].get();
+            const double score = Default::PUCB(child, policy->c_puct) + child->state_value;
+            if (score > max_score) { max_score = score; max_index = i; }
+        }
+        if (!node->children.empty()) node->children[0].swap(node->children[max_index]);       // best child to the front
+        node->node_visits += 1;
+        node->state_value += (v - node->state_value) / static_cast<float>(node->node_visits);
+    }
+}
+
+// ---- TraditionalPolicy (policies/Traditional.h) ---------------------------------------------------------------------
+TraditionalPolicy::TraditionalPolicy(double c_puct, double c_bias, bool use_rave)
+    : Policy([this](const Node* node) { return RAVE::Select(this, node); },
+             [this](Node* node, Board& board, const Probs& probs) { return Default::Expand(this, node, board, probs, false); },
+             [this](Board& board) { return hybridSimulate(board); },
+             [this](Node* node, Board& board, double value) { RAVE::BackPropogate(this, node, board, value); }, c_puct),
+      c_bias(c_bias), c_useRave(use_rave) {
+    if (use_rave) throw std::invalid_argument("TraditionalPolicy: use_rave is not supported (AMAF statistics are outside the hot path)");
+}
+
+Policy::EvalResult TraditionalPolicy::hybridSimulate(Board& board) {                       // Traditional.h:49-69
+    ensure_gpu();
+    gk_table* table = nullptr;
+    if (gk_table_default(&table) != GK_OK) throw std::runtime_error(std::string("gk_table_default: ") + gk_last_error());
+    std::uint32_t packed[16];
+    board.pack(packed);
+    Probs probs(BOARD_SIZE, 0.0f);
+    float value = 0.0f;
+    if (gk_hybrid_simulate_batch_host(table, packed, 1, probs.data(), &value, nullptr) != GK_OK)
+        throw std::runtime_error(std::string("gk_hybrid_simulate_batch_host: ") + gk_last_error());
+    return { value, probs };                                                                // DecisiveFilter never sets report.level
+}
+
 // ---- MCTS (MCTS.cpp:60-198) ---------------------------------------------------------------------------------
 static Node* updateRoot(MCTS& mcts, std::unique_ptr<Node>&& next) {
     mcts.m_root = std::move(next);

@@ -91,6 +91,26 @@ public:
     std::size_t c_rollouts;
 };
 
+// RAVE::Select / RAVE::BackPropogate<false> (algorithms/MonteCarlo.hpp:150-186): back-propagation keeps the
+// best-scoring child (PUCB + state value) at index 0 of every node on the path, select takes children[0].
+struct RAVE {
+    static Node* Select(Policy* policy, const Node* node);
+    static void BackPropogate(Policy* policy, Node* node, Board& board, double value);
+};
+
+// TraditionalPolicy (policies/Traditional.h:13-73): pattern evaluator instead of random playouts.
+// simulate = hybridSimulate: Heuristic::EvaluationProbs filtered by Heuristic::DecisiveFilter, and
+// Heuristic::EvaluationValue, computed by ac_eval_kernel (gk_hybrid_simulate_batch_host).  The reference keeps an
+// incremental Evaluator synchronised with the tree walk (CachedApplyMove / CachedRevertMove); the GPU evaluates
+// the leaf position from scratch, so the board itself is walked (Policy::applyMove / revertMove).
+class TraditionalPolicy : public Policy {
+public:
+    explicit TraditionalPolicy(double c_puct = C_PUCT, double c_bias = 0.0, bool use_rave = false);
+    EvalResult hybridSimulate(Board& board);
+    double c_bias;
+    bool c_useRave;
+};
+
 class MCTS {                                         // MCTS.h:135-180
 public:
     explicit MCTS(milliseconds c_duration = C_DURATION, Position last_move = -1, Player last_player = Player::White,

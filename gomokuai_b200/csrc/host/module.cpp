@@ -172,6 +172,12 @@ PYBIND11_MODULE(CorePyExt, mod) {
             return "RandomPolicy(c_puct: " + std::to_string(p.c_puct) + ", c_rollouts: " + std::to_string(p.c_rollouts) + ", init_acts: " + std::to_string(p.m_initActs) + ")";
         });
 
+    py::class_<TraditionalPolicy, Policy, std::shared_ptr<TraditionalPolicy>>(mod, "TraditionalPolicy", "Traditional policy with MC + Pattern Matching algorithm (GPU pattern evaluator)")
+        .def(py::init<double, double, bool>(), "c_puct"_a = C_PUCT, "c_bias"_a = 0, "use_rave"_a = false)
+        .def("__repr__", [](const TraditionalPolicy& p) {
+            return "TraditionalPolicy(c_puct: " + std::to_string(p.c_puct) + ", init_acts: " + std::to_string(p.m_initActs) + ")";
+        });
+
     // ---- new: root-parallel search -------------------------------------------------------------------------------
     py::class_<RootParallelSearch>(mod, "RootParallelSearch", "Root-parallel MCTS: many trees, leaves simulated in one GPU batch per round")
         .def(py::init([](int trees, int c_rollouts, double c_puct, std::uint64_t seed, int replica_base, int threads, bool noise) {

@@ -119,6 +119,15 @@ gk_status gk_eval_policy_batch(const gk_table* table, const uint32_t* d_boards, 
                                void* stream);
 gk_status gk_eval_policy_batch_host(const gk_table* table, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
                                     int8_t* h_winner);
+/* TraditionalPolicy::hybridSimulate (include/policies/Traditional.h:49-69) for a batch of leaf positions:
+ * EvaluationProbs, then Heuristic::DecisiveFilter (Heuristic.hpp:93-161: if a four / live three / compound of
+ * either side decides the position, only its key cells keep probability, re-normalised), and EvaluationValue.
+ * d_dflags (nullable): uint32[n][225], which (pattern type >= DeadThree | compound type, favour, perspective)
+ * flags are set per cell -- bit (type-4)*4 + g or 16 + compound*4 + g, g = 2*(favour==Black) + (perspective==Black). */
+gk_status gk_hybrid_simulate_batch(const gk_table* table, const uint32_t* d_boards, int n, float* d_probs, float* d_value,
+                                   int8_t* d_winner, uint32_t* d_dflags, void* stream);
+gk_status gk_hybrid_simulate_batch_host(const gk_table* table, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
+                                        int8_t* h_winner);
 
 /* ---- pattern-guided playouts (BASELINE config 5) -------------------------
  * Replaces Heuristic::EvaluatedRollout (include/algorithms/Heuristic.hpp:61-91) for n independent games:

@@ -258,6 +258,66 @@ def policy_heads(orc, move_list):
     return probs.astype(f32), value
 
 
+def decisive_filter(orc, move_list, probs):
+    """Heuristic::DecisiveFilter (include/algorithms/Heuristic.hpp:93-161) on the evaluator state of `orc` after
+    replaying `move_list`: walk the priority automaton +4 > -4 > +L3 == +To44 > -L3 == -To44 >= +To43 > -To43 >
+    +To33 > -To33 over the pattern / compound totals; at the first class with a non-zero count keep only the cells
+    whose per-cell flag Record::get(player, cur_player) is set for one of the remaining candidates, re-normalise.
+    Returns (filtered probs f32[225], candidates [(pattern index, player)]) -- candidates is empty when nothing fired."""
+    f32 = np.float32
+    r = orc.eval_moves(move_list)
+    pf, cf, _ = orc.eval_flags()                                   # per-cell Record fields: [225][8], [225][3]
+    cur = 1 if len(move_list) % 2 == 0 else -1                     # Player::Black = 1, White = -1
+    SIZE, L4, D4, L3, D3 = 9, 7, 6, 5, 4                            # Pattern::Type (include/Pattern.h:19-24)
+    S4, SL3, TO44, TO43, TO33, END = range(6)                      # Heuristic.hpp:98
+    table = [[(S4, 1), (TO44, 0), (SL3, 1), (TO43, 1), (TO33, 1), (END, 0)],      # :101-105
+             [(SL3, 0), (TO44, 1), (TO43, 0), (TO33, 0), (END, 0), (END, 1)]]
+
+    def count(pattern, player):                                     # :125-130 totals, [0 = White, 1 = Black]
+        g = 1 if player == 1 else 0
+        return int(r["pat_totals"][g][pattern]) if pattern < SIZE else int(r["cmp_totals"][g][pattern - SIZE])
+
+    def flag(cell, pattern, player):                                # :147-151 Record::get(favour, perspective), Pattern.cpp:408-411
+        group = ((player == 1) << 1) | (cur == 1)
+        field = int(pf[cell][pattern]) if pattern < SIZE else int(cf[cell][pattern % SIZE])
+        return (field >> (8 * group)) & 0xff
+
+    probs = np.array(probs, f32)
+    state, anti, cand = S4, 0, []
+    while state != END:
+        player = -cur if anti else cur
+        if state == S4:
+            cand += [(L4, player), (D4, player)]
+        elif state == SL3:
+            cand += [(L3, player)]
+        else:
+            cand += [(SIZE + (TO33 - state), player)]
+        while cand:
+            pattern, pl = cand[0]
+            if count(pattern, pl) != 0:
+                if anti and state != S4:
+                    cand.append((D3, -pl))
+                break
+            cand.pop(0)
+        if cand:
+            keep = np.array([any(flag(i, pt, pl) for pt, pl in cand) for i in range(225)])
+            probs = np.where(keep, probs, f32(0)).astype(f32)
+            z = f32(np.sum(probs * probs, dtype=f32))
+            if z > 0:
+                probs = probs / f32(np.sqrt(z))
+            return probs, cand
+        state, anti = table[anti][state]
+    return probs, []
+
+
+def hybrid_simulate(orc, move_list):
+    """TraditionalPolicy::hybridSimulate (include/policies/Traditional.h:49-69): DecisiveFilter never sets
+    report.level, so the result is always {EvaluationValue, filtered EvaluationProbs}."""
+    probs, value = policy_heads(orc, move_list)
+    probs, _ = decisive_filter(orc, move_list, probs)
+    return value, probs
+
+
 def guided_rollout(orc, port_oracle, move_list, mode, key, game, ctr_hi=0, max_moves=225):
     """Heuristic::EvaluatedRollout (include/algorithms/Heuristic.hpp:61-91) from the position after `move_list`:
     while the evaluator has no winner and the board is not full, play the move chosen from policy_heads --

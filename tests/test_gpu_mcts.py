@@ -76,3 +76,31 @@ def test_decided_root_returns_empty_statistics(core, kats):
         b.apply_move(core.Position(x, y))
     stats = core.RootParallelSearch(trees=8).run(b, 10)
     assert stats.sum() == 0
+
+
+def test_traditional_policy_simulate_is_hybrid_simulate(core, gpu):
+    """TraditionalPolicy.eval_state == TraditionalPolicy::hybridSimulate (Traditional.h:49-69) of the oracle"""
+    from oracle import pyoracle
+    port = pyoracle.port()
+    moves = [112, 113, 97, 98, 127, 128, 82]
+    b = core.Board()
+    for c in moves:
+        b.apply_move(c)
+    value, probs = core.TraditionalPolicy().eval_state(b)
+    rv, rp = pyoracle.hybrid_simulate(port, moves)
+    assert abs(value - float(rv)) <= 2e-5 and np.allclose(np.asarray(probs), rp, rtol=2e-5, atol=2e-6)
+    assert list(map(int, b.move_record)) == moves
+
+
+def test_traditional_policy_mcts_blocks_an_open_four(core):
+    b = core.Board()
+    for c in (112, 0, 113, 1, 114, 30, 115, 31):        # black has four in a row (112..115), black to move: 111 or 116 wins
+        b.apply_move(c)
+    m = core.MCTS(c_iterations=200, policy=core.TraditionalPolicy())
+    move = int(m.get_action(b))
+    assert move in (111, 116)
+    b2 = core.Board()
+    for c in (112, 0, 113, 1, 114, 30, 45):             # white to move must answer the open three / four threat on row 7
+        b2.apply_move(c)
+    m2 = core.MCTS(c_iterations=200, policy=core.TraditionalPolicy())
+    assert int(m2.get_action(b2)) in (110, 111, 115, 116)
