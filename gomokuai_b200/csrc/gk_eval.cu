@@ -96,23 +96,22 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
     int* self = ws.scores + black * 3 * kCells;                                 // Group(f, f)
     int* rival = ws.scores + (black + 1) * kCells;                              // Group(f, -f)
     const uint32_t ncells = pr_ncells(rec.w0);
+    // compound classes keep saturating per-cell flags (Record::set: 00 -> 01 -> 11, :395-400); lo = 0 for the other patterns
+    const uint32_t cclass = pr_cclass(rec.w0);
+    const uint32_t lo = cclass ? 1u << (cclass * 8 - 8 + dir * 2) : 0u;
 #pragma unroll
     for (uint32_t s = 0; s < 4; ++s) {                                          // at most four scored cells: straight-line, predicated
         const uint32_t nib = (rec.w0 >> (4 * s)) & 15u;
         const int cell = vend - int(nib & 7u) * stride;
         if (s < ncells) {
             atomicAdd(&rival[cell], score);                                     // '_' and '^', :158-161
-            if (nib & 8u) atomicAdd(&self[cell], score);
-        }
-    }
-    const uint32_t cclass = pr_cclass(rec.w0);
-    if (cclass) {                                                               // Record::set: 00 -> 01 -> 11, :395-400
-        const uint32_t lo = 1u << (cclass * 8 - 8 + dir * 2);
-        uint32_t cells = rec.w0;
-        for (uint32_t n = ncells; n != 0; --n, cells >>= 4) {
-            if (!(cells & 8u)) continue;
-            uint32_t* word = &ws.flags[(vend - int(cells & 7u) * stride) * 2 + black];
-            if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
+            if (nib & 8u) {
+                atomicAdd(&self[cell], score);
+                if (lo) {
+                    uint32_t* word = &ws.flags[cell * 2 + black];
+                    if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
+                }
+            }
         }
     }
     if (dflags && type >= 4u) {                                                 // update_pose: '_' both perspectives, '^' the rival's, :153-161
