@@ -126,7 +126,10 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
 // Compound::updateAntis (Pattern.cpp:520-543): rescan the 13-symbol window centred on `cell`
 // from the root state and give +600 (rival's perspective) to the other '_' / '^' cells of the
 // first emission of class `cclass` that has `cell` on a '_'.
-__device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t* dflags, uint32_t anti_bit, uint32_t next_addr,
+// kRawBoard: `board` is the caller's packed board in global memory (deferred tasks, see the kernel): cells
+// holding the invalid value 3 read as white there too; `rival` may then point into the global score block.
+template <bool kRawBoard>
+__device__ __forceinline__ void anti_cells(const uint32_t* board, uint32_t* dflags, uint32_t anti_bit, uint32_t next_addr,
                                            uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
                                            int cell, uint32_t dir, uint32_t cclass, int* rival) {
     const int cx = cell % kWidth, cy = cell / kWidth;
@@ -143,7 +146,10 @@ __device__ __forceinline__ void anti_cells(WarpSmem& ws, uint32_t* dflags, uint3
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         uint32_t v = 3u;
-        if (i >= lo && i <= hi) v = cell_value(ws.board, cell + (i - 6) * stride);
+        if (i >= lo && i <= hi) {
+            v = cell_value(board, cell + (i - 6) * stride);
+            if (kRawBoard && v == 3u) v = 2u;
+        }
         window |= v << (2 * i + 1);
     }
     uint32_t nx = root_off;
@@ -452,6 +458,27 @@ ac_eval_kernel(EvalArgs a) {
     uint32_t list_addr = smem_addr(lists + lane * cap);
     asm volatile("" : "+r"(next_addr), "+r"(src_addr), "+r"(list_addr));
 
+    // Deferred updateAntis tasks (plain evaluator only).  A board yields ~10 window rescans, each a serial 13-step
+    // chain: run per board they keep ~10 of 32 lanes busy.  Instead every lane parks at most one task (board, task
+    // word) in registers; when the next board's tasks no longer fit, all parked tasks run together, reading the
+    // board from global memory and adding their +600s to the ALREADY STORED score block with global atomics.
+    const bool defer = !kHeads && a.scores != nullptr;
+    uint32_t pend_task = 0;
+    long long pend_board = 0;
+    auto flush_pending = [&]() {
+        __threadfence();                                                    // the parked boards' score stores precede the atomics
+        __syncwarp();
+        __threadfence();
+        if (pend_task) {
+            const uint32_t black = (pend_task >> 8) & 1u;
+            anti_cells<true>(a.boards + pend_board * kBoardWords, nullptr, 0u, next_addr, uint32_t(a.root_off), emit_thr, s_erec,
+                             s_patrec, int(pend_task & 0xffu), (pend_task >> 9) & 3u, (pend_task >> 11) & 3u,
+                             a.scores + pend_board * kScoreWords + (black + 1) * kCells);
+        }
+        pend_task = 0;
+        __syncwarp();
+    };
+
     const int warps = blockDim.x >> 5;
     for (long long b = (long long)blockIdx.x * warps + warp; b < a.n; b += (long long)gridDim.x * warps) {
         // ---- phase 0 ---------------------------------------------------------------------------
@@ -585,6 +612,17 @@ ac_eval_kernel(EvalArgs a) {
                 // spread the window rescans: task s = 2 * (rank of the owning lane) + which
                 const uint32_t owners = __ballot_sync(0xffffffffu, t0 != 0);
                 const int ntask = 2 * __popc(owners);
+                if (!kHeads && defer && ntask <= 32) {                              // park the tasks on free lanes
+                    if (ntask == 0) continue;
+                    uint32_t free_lanes = __ballot_sync(0xffffffffu, pend_task == 0);
+                    if (__popc(free_lanes) < ntask) { flush_pending(); free_lanes = 0xffffffffu; }
+                    const int r = __popc(free_lanes & lt);                          // this lane's rank among the free lanes
+                    const bool take = pend_task == 0 && r < ntask;
+                    const int owner = take ? int(__fns(owners, 0, (r >> 1) + 1)) : 0;
+                    const uint32_t ta = __shfl_sync(0xffffffffu, t0, owner), tb = __shfl_sync(0xffffffffu, t1, owner);
+                    if (take) { pend_task = (r & 1) ? tb : ta; pend_board = b; }
+                    continue;
+                }
                 for (int s0 = 0; s0 < ntask; s0 += 32) {
                     const int s = s0 + lane;
                     const int owner = s < ntask ? int(__fns(owners, 0, (s >> 1) + 1)) : 0;
@@ -592,9 +630,9 @@ ac_eval_kernel(EvalArgs a) {
                     const uint32_t task = (s & 1) ? tb : ta;
                     if (s < ntask) {
                         const uint32_t black = (task >> 8) & 1u;
-                        anti_cells(ws, dflags, 1u << (16 + ((task >> 14) & 3u) * 4 + black + 1), next_addr, uint32_t(a.root_off),
-                                   emit_thr, s_erec, s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
-                                   ws.scores + (black + 1) * kCells);
+                        anti_cells<false>(ws.board, dflags, 1u << (16 + ((task >> 14) & 3u) * 4 + black + 1), next_addr,
+                                          uint32_t(a.root_off), emit_thr, s_erec, s_patrec, int(task & 0xffu), (task >> 9) & 3u,
+                                          (task >> 11) & 3u, ws.scores + (black + 1) * kCells);
                     }
                 }
             }
@@ -651,6 +689,7 @@ ac_eval_kernel(EvalArgs a) {
         if (a.winner && lane == 0) a.winner[b] = (win & 1u) ? 1 : (win & 2u) ? -1 : 0;
         __syncwarp();
     }
+    if (defer && __ballot_sync(0xffffffffu, pend_task != 0)) flush_pending();
 }
 
 // PatternSearch::matches for arbitrary symbol strings, one thread per string (test / tooling path).
