@@ -186,8 +186,10 @@ __device__ __forceinline__ void anti_cells(const uint32_t* board, uint32_t* dfla
 // Compound::locate + updateCritical for one (cell, player) whose flags passed Compound::Test
 // (Pattern.cpp:440-518).  Returns the two updateAntis tasks in t0 / t1 (0 = none):
 // cell | black << 8 | dir << 9 | class << 11 | 1 << 13.
-__device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t* dflags, uint32_t idx, uint32_t& t0, uint32_t& t1) {
-    const uint32_t f = ws.flags[idx];
+// `scores` / `totals32` are the warp's shared accumulators, or (deferred form) the board's stored score block and
+// the 32-bit word holding its first compound total in global memory (`totals_stride_bits` = 16 there: uint16 fields).
+__device__ __forceinline__ void compound_at(int* scores, uint32_t* totals32, int totals_field_bits, uint32_t* dflags,
+                                            uint32_t f, uint32_t idx, uint32_t& t0, uint32_t& t1) {
     const int cell = idx >> 1;
     const uint32_t black = idx & 1u;
     // states: S0 0, L2 1, LD3 2, To33 3, To43 4, To44 5
@@ -220,9 +222,13 @@ __device__ __forceinline__ void compound_at(WarpSmem& ws, uint32_t* dflags, uint
     t0 = t1 = 0;
     const int type = state - 3;
     if (type < 0) return;   // needs an L3 plus two lower-class patterns on one cell of one line: excluded by exhaustive line enumeration (tests)
-    atomicAdd(&ws.scores[black * 3 * kCells + cell], 600 * ncomp);              // updateCritical, :515-518
-    atomicAdd(&ws.scores[(black + 1) * kCells + cell], 600 * ncomp);
-    atomicAdd(&ws.totals[16 + black * 3 + type], 1u);                           // one compound, :505-508
+    atomicAdd(&scores[black * 3 * kCells + cell], 600 * ncomp);                 // updateCritical, :515-518
+    atomicAdd(&scores[(black + 1) * kCells + cell], 600 * ncomp);
+    if (totals32) {                                                             // one compound, :505-508
+        const uint32_t field = black * 3 + uint32_t(type);
+        if (totals_field_bits == 32) atomicAdd(&totals32[field], 1u);
+        else atomicAdd(&totals32[field >> 1], 1u << (16 * (field & 1u)));       // two uint16 totals per word
+    }
     if (dflags) atomicOr(&dflags[cell], (1u << (16 + type * 4 + black * 3)) | (1u << (16 + type * 4 + black + 1)));   // updateCritical
     if (!triple && l3 == 0) { t0 = first | uint32_t(type) << 14; t1 = second | uint32_t(type) << 14; }   // exactly two components here, :500-502
 }
@@ -458,24 +464,39 @@ ac_eval_kernel(EvalArgs a) {
     uint32_t list_addr = smem_addr(lists + lane * cap);
     asm volatile("" : "+r"(next_addr), "+r"(src_addr), "+r"(list_addr));
 
-    // Deferred updateAntis tasks (plain evaluator only).  A board yields ~10 window rescans, each a serial 13-step
-    // chain: run per board they keep ~10 of 32 lanes busy.  Instead every lane parks at most one task (board, task
-    // word) in registers; when the next board's tasks no longer fit, all parked tasks run together, reading the
-    // board from global memory and adding their +600s to the ALREADY STORED score block with global atomics.
-    const bool defer = !kHeads && a.scores != nullptr;
-    uint32_t pend_task = 0;
+    // Deferred compounds (plain evaluator only).  A board yields ~5 compound candidates and ~10 updateAntis window
+    // rescans, each a serial chain: run per board they keep 5..10 of 32 lanes busy.  Instead every lane parks at most
+    // one candidate (board, cell/player index, its flag word) in registers; when the next board's candidates no
+    // longer fit, all parked candidates run together -- Compound::locate, then their rescans spread over the lanes --
+    // reading the boards from global memory and adding to the ALREADY STORED score blocks / totals with global atomics.
+    const bool defer = !kHeads && a.scores != nullptr && (reinterpret_cast<uintptr_t>(a.cmp_totals) & 3u) == 0;
+    uint32_t pend_idx = 0xffffffffu, pend_flags = 0;
     long long pend_board = 0;
     auto flush_pending = [&]() {
-        __threadfence();                                                    // the parked boards' score stores precede the atomics
+        __threadfence();                                                    // the parked boards' stores precede the atomics
         __syncwarp();
         __threadfence();
-        if (pend_task) {
-            const uint32_t black = (pend_task >> 8) & 1u;
-            anti_cells<true>(a.boards + pend_board * kBoardWords, nullptr, 0u, next_addr, uint32_t(a.root_off), emit_thr, s_erec,
-                             s_patrec, int(pend_task & 0xffu), (pend_task >> 9) & 3u, (pend_task >> 11) & 3u,
-                             a.scores + pend_board * kScoreWords + (black + 1) * kCells);
+        uint32_t t0 = 0, t1 = 0;
+        if (pend_idx != 0xffffffffu)
+            compound_at(a.scores + pend_board * kScoreWords,
+                        a.cmp_totals ? reinterpret_cast<uint32_t*>(a.cmp_totals + pend_board * 6) : nullptr, 16, nullptr,
+                        pend_flags, pend_idx, t0, t1);
+        pend_idx = 0xffffffffu;
+        const uint32_t owners = __ballot_sync(0xffffffffu, t0 != 0);
+        const int ntask = 2 * __popc(owners);
+        for (int s0 = 0; s0 < ntask; s0 += 32) {
+            const int s = s0 + lane;
+            const int owner = s < ntask ? int(__fns(owners, 0, (s >> 1) + 1)) : 0;
+            const uint32_t ta = __shfl_sync(0xffffffffu, t0, owner), tb = __shfl_sync(0xffffffffu, t1, owner);
+            const long long tboard = __shfl_sync(0xffffffffu, pend_board, owner);
+            const uint32_t task = (s & 1) ? tb : ta;
+            if (s < ntask) {
+                const uint32_t black = (task >> 8) & 1u;
+                anti_cells<true>(a.boards + tboard * kBoardWords, nullptr, 0u, next_addr, uint32_t(a.root_off), emit_thr, s_erec,
+                                 s_patrec, int(task & 0xffu), (task >> 9) & 3u, (task >> 11) & 3u,
+                                 a.scores + tboard * kScoreWords + (black + 1) * kCells);
+            }
         }
-        pend_task = 0;
         __syncwarp();
     };
 
@@ -607,22 +628,26 @@ ac_eval_kernel(EvalArgs a) {
             }
             __syncwarp();
             for (int base = 0; base < cn; base += 32) {                             // warp-uniform trip count
+                if (!kHeads && defer && cn <= 32) {                                 // park the candidates on free lanes (a board with more is done in place:
+                    const int nnew = cn;                                            //  a flush must never meet candidates of a board not stored yet)
+                    uint32_t free_lanes = __ballot_sync(0xffffffffu, pend_idx == 0xffffffffu);
+                    if (__popc(free_lanes) < nnew) { flush_pending(); free_lanes = 0xffffffffu; }
+                    const int r = __popc(free_lanes & lt);                          // this lane's rank among the free lanes
+                    if (pend_idx == 0xffffffffu && r < nnew) {
+                        pend_idx = clist[base + r];
+                        pend_flags = ws.flags[pend_idx];
+                        pend_board = b;
+                    }
+                    continue;
+                }
                 uint32_t t0 = 0, t1 = 0;
-                if (base + lane < cn) compound_at(ws, dflags, clist[base + lane], t0, t1);
+                if (base + lane < cn) {
+                    const uint32_t idx = clist[base + lane];
+                    compound_at(ws.scores, ws.totals + 16, 32, dflags, ws.flags[idx], idx, t0, t1);
+                }
                 // spread the window rescans: task s = 2 * (rank of the owning lane) + which
                 const uint32_t owners = __ballot_sync(0xffffffffu, t0 != 0);
                 const int ntask = 2 * __popc(owners);
-                if (!kHeads && defer && ntask <= 32) {                              // park the tasks on free lanes
-                    if (ntask == 0) continue;
-                    uint32_t free_lanes = __ballot_sync(0xffffffffu, pend_task == 0);
-                    if (__popc(free_lanes) < ntask) { flush_pending(); free_lanes = 0xffffffffu; }
-                    const int r = __popc(free_lanes & lt);                          // this lane's rank among the free lanes
-                    const bool take = pend_task == 0 && r < ntask;
-                    const int owner = take ? int(__fns(owners, 0, (r >> 1) + 1)) : 0;
-                    const uint32_t ta = __shfl_sync(0xffffffffu, t0, owner), tb = __shfl_sync(0xffffffffu, t1, owner);
-                    if (take) { pend_task = (r & 1) ? tb : ta; pend_board = b; }
-                    continue;
-                }
                 for (int s0 = 0; s0 < ntask; s0 += 32) {
                     const int s = s0 + lane;
                     const int owner = s < ntask ? int(__fns(owners, 0, (s >> 1) + 1)) : 0;
@@ -689,7 +714,7 @@ ac_eval_kernel(EvalArgs a) {
         if (a.winner && lane == 0) a.winner[b] = (win & 1u) ? 1 : (win & 2u) ? -1 : 0;
         __syncwarp();
     }
-    if (defer && __ballot_sync(0xffffffffu, pend_task != 0)) flush_pending();
+    if (defer && __ballot_sync(0xffffffffu, pend_idx != 0xffffffffu)) flush_pending();
 }
 
 // PatternSearch::matches for arbitrary symbol strings, one thread per string (test / tooling path).
