@@ -198,26 +198,34 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
 
     Lane L{};
     bool active = false, dead = false;
-    uint32_t acc[3] = { 0, 0, 0 };                                               // white / draw / black of position acc_pos
+    uint32_t acc_white = 0, acc_draw = 0, acc_black = 0;                         // outcomes so far of position acc_pos
+    const bool trace = a.winners != nullptr || a.lengths != nullptr;
     uint32_t acc_pos = 0xffffffffu;
     uint32_t rnd[4] = { 0, 0, 0, 0 };
     const uint8_t* inj = nullptr;
 
-    auto finish = [&](uint32_t result) {                                         // result: 1 black, 2 white, 3 draw
-        const int win = result == 1u ? 1 : result == 2u ? -1 : 0;
-        const size_t g = size_t(L.pos) * a.rollouts_per_pos + L.roll;
-        if (a.winners) a.winners[g] = (int8_t)win;
-        if (a.lengths) a.lengths[g] = (uint8_t)L.moves;
-        acc[win + 1] += 1;
-        active = false;
+    // result: 0 game goes on, 1 black won, 2 white won, 3 draw.  Branch-free on the hot path: three predicated
+    // adds per step for every lane; the per-rollout trace is written only when the caller asked for it.
+    auto finish = [&](uint32_t result) {
+        acc_black += result == 1u;
+        acc_white += result == 2u;
+        acc_draw += result == 3u;
+        if (result) {
+            if (trace) {
+                const size_t g = size_t(L.pos) * a.rollouts_per_pos + L.roll;
+                if (a.winners) a.winners[g] = (int8_t)(result == 1u ? 1 : result == 2u ? -1 : 0);
+                if (a.lengths) a.lengths[g] = (uint8_t)L.moves;
+            }
+            active = false;
+        }
     };
     auto flush = [&]() {
         if (a.wdb && acc_pos != 0xffffffffu) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (acc[i]) atomicAdd(a.wdb + size_t(acc_pos) * 3 + i, int(acc[i]));
+            if (acc_white) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 0, int(acc_white));
+            if (acc_draw) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 1, int(acc_draw));
+            if (acc_black) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 2, int(acc_black));
         }
-        acc[0] = acc[1] = acc[2] = 0;
+        acc_white = acc_draw = acc_black = 0;
     };
 
     for (;;) {
@@ -283,8 +291,7 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
                     } else {
                         r = __umulhi(rnd[s], uint32_t(kCells));
                     }
-                    const uint32_t result = play_move(my, L, r);
-                    if (result) finish(result);
+                    finish(play_move(my, L, r));
                 }
             }
         }

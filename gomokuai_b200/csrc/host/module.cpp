@@ -180,12 +180,13 @@ PYBIND11_MODULE(CorePyExt, mod) {
 
     // ---- new: root-parallel search -------------------------------------------------------------------------------
     py::class_<RootParallelSearch>(mod, "RootParallelSearch", "Root-parallel MCTS: many trees, leaves simulated in one GPU batch per round")
-        .def(py::init([](int trees, int c_rollouts, double c_puct, std::uint64_t seed, int replica_base, int threads, bool noise) {
+        .def(py::init([](int trees, int c_rollouts, double c_puct, std::uint64_t seed, int replica_base, int threads, bool noise, bool eager) {
                  RootParallelConfig cfg;
                  cfg.trees = trees; cfg.c_rollouts = c_rollouts; cfg.c_puct = c_puct; cfg.seed = seed;
-                 cfg.replica_base = replica_base; cfg.threads = threads; cfg.noise = noise;
+                 cfg.replica_base = replica_base; cfg.threads = threads; cfg.noise = noise; cfg.eager = eager;
                  return new RootParallelSearch(cfg);
-             }), "trees"_a = 256, "c_rollouts"_a = 5, "c_puct"_a = C_PUCT, "seed"_a = 1, "replica_base"_a = 0, "threads"_a = 0, "noise"_a = true)
+             }), "trees"_a = 256, "c_rollouts"_a = 5, "c_puct"_a = C_PUCT, "seed"_a = 1, "replica_base"_a = 0, "threads"_a = 0, "noise"_a = true,
+             "eager"_a = false)
         .def("run", [](RootParallelSearch& s, const Board& b, int playouts_per_tree) {
             { py::gil_scoped_release release; s.run(b, playouts_per_tree); }
             py::array_t<std::int64_t> a({ 3, int(BOARD_SIZE) });

@@ -20,12 +20,22 @@ namespace gomoku {
 
 namespace {
 
-struct ANode {                      // arena node, 28 bytes
-    std::int32_t parent, first_child;
-    std::int16_t n_children, position;
+// Arena node.  The reference expands a leaf into one heap node per empty cell (MonteCarlo.hpp:71-80; 40-50 % of its
+// time is operator new, Final Report.md:102).  With RandomPolicy every child of a node has the same prior and starts
+// at value 0 / visits 0, so all NEVER-VISITED children of a node tie on the PUCB score and Default::Select takes the
+// lowest cell among them (strict `>`, MonteCarlo.hpp:57-68).  Children are therefore materialised only when they are
+// first selected -- in increasing cell order, kept in a sibling list -- and the untouched ones are represented by a
+// cursor.  Selection visits exactly the nodes the eager tree would (tests/test_gpu_mcts.py compares the two).
+// The root keeps a materialised block of children when Dirichlet noise makes their priors differ.
+struct ANode {
+    std::int32_t parent, first_child, last_child, next_sibling;
+    std::int16_t n_children;        // children that exist as nodes
+    std::int16_t n_moves;           // legal moves here (empty cells); > 0 once the node has been expanded
+    std::int16_t position, cursor;  // the move into this node; highest cell materialised so far (-1 none)
     float value, prior;             // running mean from the view of who moved into the node; prior of the move
     std::int32_t visits;
     std::int8_t player;             // who played `position`
+    std::int8_t eager;              // children are one contiguous block [first_child, first_child + n_children)
 };
 
 struct Tree {
@@ -112,17 +122,60 @@ Position RootParallelSearch::bestMove(const Stats& stats) {
     return most > 0 ? Position(best) : Position(-1);
 }
 
-// expand `node` over the empty cells of `board` with uniform priors (MonteCarlo.hpp:50-55,71-80)
-static void expand(Tree& t, std::int32_t node, const Board& board) {
+static ANode make_node(std::int32_t parent, int position, float prior, int player) {
+    ANode n{};
+    n.parent = parent; n.first_child = n.last_child = n.next_sibling = -1;
+    n.position = static_cast<std::int16_t>(position); n.cursor = -1;
+    n.prior = prior; n.player = static_cast<std::int8_t>(player);
+    return n;
+}
+
+// expand `node` over the empty cells of `board` with uniform priors (MonteCarlo.hpp:50-55,71-80); `eager`
+// materialises the children at once (the reference's layout), otherwise they appear when first selected
+static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
     const int empties = static_cast<int>(board.moveCounts(Player::None));
     if (empties == 0) return;
+    t.nodes[node].n_moves = static_cast<std::int16_t>(empties);
+    if (!eager) return;
     const float prior = 1.0f / static_cast<float>(empties);
     const std::int32_t first = static_cast<std::int32_t>(t.nodes.size());
-    const std::int8_t player = static_cast<std::int8_t>(-t.nodes[node].player);
+    const int player = -t.nodes[node].player;
     for (int c = 0; c < BOARD_SIZE; ++c)
-        if (board.cell(c) == 0) t.nodes.push_back(ANode{ node, -1, 0, static_cast<std::int16_t>(c), 0.0f, prior, 0, player });
+        if (board.cell(c) == 0) t.nodes.push_back(make_node(node, c, prior, player));
     t.nodes[node].first_child = first;
     t.nodes[node].n_children = static_cast<std::int16_t>(empties);
+    t.nodes[node].eager = 1;
+}
+
+// Default::Select (MonteCarlo.hpp:57-68) on a lazily expanded node: the best materialised child, or -- when the
+// common score of the never-visited children is strictly higher -- the lowest never-visited cell, created now.
+static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
+    const ANode parent = t.nodes[node];
+    const double sq = std::sqrt(static_cast<double>(parent.visits));
+    const float prior = 1.0f / static_cast<float>(parent.n_moves);
+    std::int32_t best = parent.first_child;                          // as the reference: the first child unless one scores above -1
+    double best_score = -1.0;
+    for (std::int32_t c = parent.first_child; c >= 0; c = t.nodes[c].next_sibling) {   // increasing cell order
+        const ANode& ch = t.nodes[c];
+        const double score = ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);
+        if (score > best_score) { best_score = score; best = c; }
+    }
+    if (parent.n_children < parent.n_moves) {                       // someone has never been visited: value 0, visits 0
+        const double fresh = 0.0 + c_puct * prior * sq / 1.0;
+        if (best < 0 || fresh > best_score) {
+            int cell = parent.cursor + 1;
+            while (t.board.cell(cell) != 0) ++cell;                 // the lowest empty cell above the cursor
+            const std::int32_t created = static_cast<std::int32_t>(t.nodes.size());
+            t.nodes.push_back(make_node(node, cell, prior, -parent.player));
+            ANode& p = t.nodes[node];
+            if (p.last_child >= 0) t.nodes[p.last_child].next_sibling = created; else p.first_child = created;
+            p.last_child = created;
+            p.n_children += 1;
+            p.cursor = static_cast<std::int16_t>(cell);
+            return created;
+        }
+    }
+    return best;
 }
 
 void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
@@ -135,8 +188,8 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     for (int i = 0; i < n_trees; ++i) {
         Tree& t = m->trees[i];
         t.nodes.clear();
-        t.nodes.reserve(static_cast<std::size_t>(playouts_per_tree) * 64 + 256);
-        t.nodes.push_back(ANode{ -1, -1, 0, -1, 0.0f, 1.0f, 0, static_cast<std::int8_t>(root_last) });
+        t.nodes.reserve(m_cfg.eager ? static_cast<std::size_t>(playouts_per_tree) * 64 + 256 : static_cast<std::size_t>(playouts_per_tree) * 2 + 256);
+        t.nodes.push_back(make_node(-1, -1, 1.0f, static_cast<int>(root_last)));
         t.board = root;
         t.black_wins.fill(0);
         t.white_wins.fill(0);
@@ -156,17 +209,21 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
                 Tree& t = m->trees[i];
                 std::int32_t node = 0;
                 t.root_child = -1;
-                while (t.nodes[node].n_children > 0) {
-                    const ANode& parent = t.nodes[node];
-                    const double sq = std::sqrt(static_cast<double>(parent.visits));
-                    std::int32_t best = parent.first_child;
-                    double best_score = -1.0;
-                    for (std::int32_t c = parent.first_child, e = c + parent.n_children; c < e; ++c) {
-                        const ANode& ch = t.nodes[c];
-                        const double score = ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);   // PUCB, :23-28,57-68
-                        if (score > best_score) { best_score = score; best = c; }
+                while (t.nodes[node].n_moves > 0) {                  // expanded: descend
+                    if (!t.nodes[node].eager) {
+                        node = select_lazy(t, node, c_puct);
+                    } else {
+                        const ANode& parent = t.nodes[node];
+                        const double sq = std::sqrt(static_cast<double>(parent.visits));
+                        std::int32_t best = parent.first_child;
+                        double best_score = -1.0;
+                        for (std::int32_t c = parent.first_child, e = c + parent.n_children; c < e; ++c) {
+                            const ANode& ch = t.nodes[c];
+                            const double score = ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);   // PUCB, :23-28,57-68
+                            if (score > best_score) { best_score = score; best = c; }
+                        }
+                        node = best;
                     }
-                    node = best;
                     if (t.root_child < 0) t.root_child = t.nodes[node].position;
                     t.board.applyMove(Position(t.nodes[node].position), false);
                 }
@@ -189,7 +246,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
                 const std::int32_t* r = &m->wdb[static_cast<std::size_t>(i) * 3];
                 const float black_value = static_cast<float>(r[2] - r[0]) / static_cast<float>(m_cfg.c_rollouts);
                 if (!t.terminal) {
-                    expand(t, t.leaf, t.board);
+                    expand(t, t.leaf, t.board, m_cfg.eager || (t.leaf == 0 && m_cfg.noise));
                     if (t.leaf == 0 && m_cfg.noise) {                // Default::AddNoise on the root's fresh children
                         ANode& rt = t.nodes[0];
                         std::gamma_distribution<float> gamma(0.05f, 1.0f);
@@ -219,8 +276,11 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     for (Tree& t : m->trees) {
         nodes += static_cast<std::int64_t>(t.nodes.size());
         const ANode& rt = t.nodes[0];
-        for (std::int32_t c = rt.first_child, e = c + rt.n_children; rt.n_children > 0 && c < e; ++c)
-            m_stats[t.nodes[c].position] += t.nodes[c].visits;
+        if (rt.eager) {
+            for (std::int32_t c = rt.first_child, e = c + rt.n_children; c < e; ++c) m_stats[t.nodes[c].position] += t.nodes[c].visits;
+        } else {
+            for (std::int32_t c = rt.first_child; c >= 0; c = t.nodes[c].next_sibling) m_stats[t.nodes[c].position] += t.nodes[c].visits;
+        }
         for (int c = 0; c < BOARD_SIZE; ++c) {
             m_stats[BOARD_SIZE + c] += t.black_wins[c];
             m_stats[2 * BOARD_SIZE + c] += t.white_wins[c];

@@ -23,6 +23,7 @@ struct RootParallelConfig {
     int replica_base = 0;       // first global tree index of this rank (keeps streams disjoint across ranks)
     int threads = 0;            // host threads for tree work (0 = hardware concurrency)
     bool noise = true;          // Dirichlet noise on root priors (Default::AddNoise, MonteCarlo.hpp:97-108)
+    bool eager = false;         // materialise every child at expansion like the reference (slow; kept to test the lazy tree against)
 };
 
 class RootParallelSearch {

@@ -56,6 +56,20 @@ def test_root_parallel_search_statistics(core):
     assert s.leaves == 64 * 40 and s.nodes > 64 * 200
 
 
+def test_lazy_tree_equals_the_eager_tree(core):
+    """children materialised on first selection (the arena design) visit exactly the nodes of the reference's
+    expand-everything tree: same seeds -> identical root statistics, with and without root noise"""
+    b = core.Board()
+    for c in (112, 113, 97, 98, 128):
+        b.apply_move(c)
+    for noise in (True, False):
+        lazy = core.RootParallelSearch(trees=48, c_rollouts=5, seed=3, threads=3, noise=noise)
+        eager = core.RootParallelSearch(trees=48, c_rollouts=5, seed=3, threads=3, noise=noise, eager=True)
+        a, e = lazy.run(b, 300), eager.run(b, 300)
+        assert np.array_equal(a, e)
+        assert lazy.nodes * 20 < eager.nodes                # ~1 node per playout instead of ~220
+
+
 def test_root_parallel_search_finds_the_winning_move(core):
     from gomokuai_b200 import root_parallel as rp
     b = core.Board()
