@@ -500,6 +500,18 @@ gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last
     return GK_OK;
 }
 
+gk_status gk_host_alloc(void** out, size_t bytes) {
+    if (gk_status s = require_device()) return s;
+    if (!out) return fail(GK_ERR_INVALID, "out is null");
+    GK_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return GK_OK;
+}
+
+gk_status gk_host_free(void* ptr) {
+    if (ptr) GK_CUDA(cudaFreeHost(ptr));
+    return GK_OK;
+}
+
 // ---- host utilities ------------------------------------------------------------------------------------
 gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards) {
     if (!moves || !starts || !h_boards || n < 0) return fail(GK_ERR_INVALID, "bad arguments");

@@ -4,9 +4,16 @@
 //   planes: [stones of the side to move, stones of the opponent, empty cells, last move (one-hot),
 //            second-to-last move (one-hot), 1 if black is to move]
 //   variants (augment = 1), in the reference's order: for i in 0..3: rot90(i), fliplr(rot90(i))
-// Pure data movement: 64 B in, 1 350 B (or 10 800 B) out per position -- HBM-write bound.  One warp
-// stages the six base planes as bytes in shared memory, then streams the variants out as 16-byte
-// stores through a precomputed (variant, byte) -> base-byte table.
+// Pure data movement: 64 B in, 1 350 B (or 10 800 B) out per position -- HBM-write bound.
+//
+// One warp per position, everything as BIT planes until the last moment:
+//   1. lanes 0..14 hold the 15-bit rows of "my stones" / "opponent's stones" (and the two one-hot planes);
+//      their transposes come from 15 ballots each;
+//   2. every variant of every plane is one of {plane, transpose} with rows and / or bits reversed, so a
+//      variant row is a shuffle plus an optional bit reversal; the 15-bit rows are OR-ed into the position's
+//      output BIT stream in shared memory (10 800 bits for 8 variants);
+//   3. the stream is expanded to bytes 16 at a time (4 bits -> 4 bytes by one multiply and one mask) and
+//      written with 128-bit stores.  No byte ever goes through shared memory.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -20,75 +27,128 @@ namespace {
 
 constexpr int kPlaneBytes = 6 * kCells;        // 1350
 constexpr int kWarps = 8;
+constexpr int kStreamWords = 344;              // 8 x 1350 bits = 337.5 words, padded to a 16-byte multiple + slack for funnel reads
+
+__device__ __forceinline__ uint32_t squeeze_even15(uint32_t x) {                // even bits of a 30-bit field -> 15 contiguous bits
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// transpose of a 15 x 15 bit matrix held as rows in lanes 0..14: row j of the result = column j of the input
+__device__ __forceinline__ uint32_t transpose15(uint32_t row, int lane) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int j = 0; j < kWidth; ++j) {
+        const uint32_t col = __ballot_sync(0xffffffffu, (row >> j) & 1u) & 0x7fffu;
+        if (lane == j) t = col;
+    }
+    return t;
+}
+
+__device__ __forceinline__ uint32_t spread4(uint32_t nibble) {                  // 4 bits -> 4 bytes of 0 / 1
+    return (nibble * 0x00204081u) & 0x01010101u;
+}
 
 __global__ void __launch_bounds__(kWarps * 32)
 encode_states_kernel(EncodeArgs a) {
-    __shared__ uint16_t s_map[8 * kPlaneBytes];            // (variant, byte) -> index into the base planes
-    __shared__ __align__(16) uint8_t s_base[kWarps][kPlaneBytes + 10];
+    __shared__ uint16_t s_perm[8 * kCells];                // (variant, cell) -> source cell, for the probabilities
+    __shared__ __align__(16) uint32_t s_stream[kWarps][kStreamWords];
     const int variants = a.augment ? 8 : 1;
-    for (int f = threadIdx.x; f < variants * kPlaneBytes; f += blockDim.x) {
-        const int v = f / kPlaneBytes, rem = f - v * kPlaneBytes, p = rem / kCells, i = rem - p * kCells;
-        const int r = i / kWidth, c = i - r * kWidth, cf = (v & 1) ? kWidth - 1 - c : c;   // fliplr after the rotation
-        int r0, c0;
-        switch (v >> 1) {                                  // np.rot90(m, k)[r][c]
-            case 0: r0 = r; c0 = cf; break;
-            case 1: r0 = cf; c0 = kWidth - 1 - r; break;
-            case 2: r0 = kWidth - 1 - r; c0 = kWidth - 1 - cf; break;
-            default: r0 = kWidth - 1 - cf; c0 = r; break;
+    if (a.probs) {
+        for (int f = threadIdx.x; f < variants * kCells; f += blockDim.x) {
+            const int v = f / kCells, i = f - v * kCells;
+            const int r = i / kWidth, c = i - r * kWidth, cf = (v & 1) ? kWidth - 1 - c : c;   // fliplr after the rotation
+            int r0, c0;
+            switch (v >> 1) {                              // np.rot90(m, k)[r][c]
+                case 0: r0 = r; c0 = cf; break;
+                case 1: r0 = cf; c0 = kWidth - 1 - r; break;
+                case 2: r0 = kWidth - 1 - r; c0 = kWidth - 1 - cf; break;
+                default: r0 = kWidth - 1 - cf; c0 = r; break;
+            }
+            s_perm[f] = uint16_t(r0 * kWidth + c0);
         }
-        s_map[f] = uint16_t(p * kCells + r0 * kWidth + c0);
+        __syncthreads();
     }
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t* base = s_base[warp];
-    const long long out_bytes = (long long)variants * kPlaneBytes;
+    uint32_t* stream = s_stream[warp];
+    const int out_bytes = variants * kPlaneBytes;
     for (long long b = (long long)blockIdx.x * kWarps + warp; b < a.n; b += (long long)gridDim.x * kWarps) {
         uint32_t w = 0;
         if (lane < kBoardWords) w = __ldg(a.boards + b * kBoardWords + lane);
+        w &= ~((w >> 1) & 0x55555555u);                                       // a cell holding the invalid value 3 reads as white (as in ac_eval)
+        if (lane == 14) w &= 3u;                                              // only cell 224 lives in word 14
+        if (lane == 15) w = 0u;
         // stone counts decide the side to move: black iff #black == #white (Game.h:128, Game.cpp:52)
-        uint32_t v = lane == 14 ? (w & 3u) : lane == 15 ? 0u : w;
-        const int blk = __popc(v & 0x55555555u & ~(v >> 1)), wht = __popc((v >> 1) & 0x55555555u & ~v);
-        const int nb = __reduce_add_sync(0xffffffffu, blk), nw = __reduce_add_sync(0xffffffffu, wht);
-        const uint32_t mine = nb == nw ? 1u : 2u;
+        const int nb = __reduce_add_sync(0xffffffffu, __popc(w & 0x55555555u & ~(w >> 1)));
+        const int nw = __reduce_add_sync(0xffffffffu, __popc((w >> 1) & 0x55555555u & ~w));
+        const bool black_to_move = nb == nw;
+        // ---- 1. bit rows (lanes 0..14) and their transposes --------------------------------------------------
+        const int y = lane < kHeight ? lane : 0, off = 30 * y;
+        const uint32_t lo = __shfl_sync(0xffffffffu, w, off >> 5), hi = __shfl_sync(0xffffffffu, w, (off >> 5) + 1);
+        const uint32_t v30 = __funnelshift_r(lo, hi, off & 31) & 0x3fffffffu;
+        uint32_t blk = squeeze_even15(v30 & ~(v30 >> 1)), wht = squeeze_even15((v30 >> 1) & ~v30);
+        if (lane >= kHeight) blk = wht = 0;
         const int last1 = a.last_moves ? a.last_moves[b * 2] : -1, last2 = a.last_moves ? a.last_moves[b * 2 + 1] : -1;
-        for (int c0 = 0; c0 < kCells; c0 += 32) {                          // warp-uniform trip count (shuffles inside)
-            const int c = c0 + lane;
-            const uint32_t word = __shfl_sync(0xffffffffu, w, (c >> 4) & 15);
-            const uint32_t val = (word >> ((c & 15) * 2)) & 3u;
-            if (c < kCells) {
-                base[c] = val == mine;
-                base[kCells + c] = val == (3u - mine);
-                base[2 * kCells + c] = val == 0u;
-                base[3 * kCells + c] = c == last1;
-                base[4 * kCells + c] = c == last2;
-                base[5 * kCells + c] = mine == 1u;
+        uint32_t base[4], tr[4];                                              // mine, opponent's, last, second-to-last
+        base[0] = black_to_move ? blk : wht;
+        base[1] = black_to_move ? wht : blk;
+        base[2] = (last1 >= 0 && last1 / kWidth == lane) ? 1u << (last1 % kWidth) : 0u;
+        base[3] = (last2 >= 0 && last2 / kWidth == lane) ? 1u << (last2 % kWidth) : 0u;
+        tr[0] = transpose15(base[0], lane);
+        tr[1] = transpose15(base[1], lane);
+        tr[2] = (last1 >= 0 && last1 % kWidth == lane) ? 1u << (last1 / kWidth) : 0u;
+        tr[3] = (last2 >= 0 && last2 % kWidth == lane) ? 1u << (last2 / kWidth) : 0u;
+        // ---- 2. the output bit stream ---------------------------------------------------------------------------
+        for (int i = lane; i < kStreamWords / 4; i += 32) reinterpret_cast<uint4*>(stream)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        const uint32_t side = black_to_move ? 0x7fffu : 0u;
+        for (int v = 0; v < variants; ++v) {
+            const int k = v >> 1;
+            const bool use_t = k & 1, reversed = (k >= 2) != bool(v & 1);
+            const int src_row = (k == 1 || k == 2) ? kHeight - 1 - y : y;     // lanes >= 15 read row 0 and are masked below
+            uint32_t rows[6];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                uint32_t r = __shfl_sync(0xffffffffu, use_t ? tr[p] : base[p], src_row);
+                if (reversed) r = __brev(r) >> 17;
+                rows[p < 2 ? p : p + 1] = r;
+            }
+            rows[2] = ~(rows[0] | rows[1]) & 0x7fffu;                         // empty cells
+            rows[5] = side;
+            if (lane < kHeight) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p) {
+                    const int bit = (v * 6 + p) * kCells + lane * kWidth;
+                    const uint32_t r = rows[p];
+                    if (r) {
+                        atomicOr(&stream[bit >> 5], r << (bit & 31));
+                        if ((bit & 31) > 32 - kWidth) atomicOr(&stream[(bit >> 5) + 1], r >> (32 - (bit & 31)));
+                    }
+                }
             }
         }
         __syncwarp();
-        // the position's output range need not be 16-byte aligned (1350 = 84 x 16 + 6): byte-wise head up
-        // to the next 16-byte boundary, 128-bit body, byte-wise tail
+        // ---- 3. bits -> bytes, 128-bit stores.  The position's output range need not be 16-byte aligned
+        //         (1350 = 84 x 16 + 6): byte-wise head up to the next boundary, 128-bit body, byte-wise tail
         uint8_t* out = a.planes + b * out_bytes;
         const int head = int((16u - unsigned(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
-        const int body = (int(out_bytes) - head) / 16;
-        if (lane < head) out[lane] = base[s_map[lane]];
+        const int body = (out_bytes - head) / 16;
+        if (lane < head) out[lane] = (stream[lane >> 5] >> (lane & 31)) & 1u;
         for (int q = lane; q < body; q += 32) {
-            uint32_t pack[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int f = head + q * 16 + k * 4;
-                pack[k] = uint32_t(base[s_map[f]]) | uint32_t(base[s_map[f + 1]]) << 8 | uint32_t(base[s_map[f + 2]]) << 16 |
-                          uint32_t(base[s_map[f + 3]]) << 24;
-            }
-            *reinterpret_cast<uint4*>(out + head + q * 16) = make_uint4(pack[0], pack[1], pack[2], pack[3]);
+            const int bit = head + q * 16;
+            const uint32_t m = __funnelshift_r(stream[bit >> 5], stream[(bit >> 5) + 1], bit & 31);   // 16 stream bits in the low half
+            *reinterpret_cast<uint4*>(out + bit) = make_uint4(spread4(m & 15u), spread4((m >> 4) & 15u), spread4((m >> 8) & 15u),
+                                                              spread4((m >> 12) & 15u));
         }
-        for (int f = head + body * 16 + lane; f < out_bytes; f += 32) out[f] = base[s_map[f]];
-        if (a.probs) {                                                    // rot_probs / flip_probs: plane 0's cell permutation
+        for (int f = head + body * 16 + lane; f < out_bytes; f += 32) out[f] = (stream[f >> 5] >> (f & 31)) & 1u;
+        if (a.probs) {                                                        // rot_probs / flip_probs: the cell permutation of the variant
             const float* pin = a.probs + b * kCells;
             float* pout = a.probs_out + b * variants * kCells;
-            for (int f = lane; f < variants * kCells; f += 32) {
-                const int v = f / kCells;
-                pout[f] = __ldg(pin + s_map[v * kPlaneBytes + (f - v * kCells)]);
-            }
+            for (int f = lane; f < variants * kCells; f += 32) pout[f] = __ldg(pin + s_perm[f]);
         }
         __syncwarp();
     }
@@ -99,7 +159,7 @@ encode_states_kernel(EncodeArgs a) {
 cudaError_t launch_encode(const EncodeArgs& a, int sm_count, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
     const long long want = (a.n + kWarps - 1) / kWarps;
-    const long long resident = (long long)sm_count * 6;
+    const long long resident = (long long)sm_count * 8;
     encode_states_kernel<<<int(want < resident ? want : resident), kWarps * 32, 0, stream>>>(a);
     return cudaGetLastError();
 }

@@ -97,9 +97,10 @@ private:
 
 struct RootParallelSearch::Impl {
     std::vector<Tree> trees;
-    std::vector<std::uint32_t> packed;      // trees x 16
-    std::vector<std::int32_t> wdb;          // trees x 3
+    std::uint32_t* packed = nullptr;        // trees x 16, page-locked (allocated on first run, when the GPU is bound)
+    std::int32_t* wdb = nullptr;            // trees x 3, page-locked
     std::unique_ptr<Pool> pool;
+    ~Impl() { gk_host_free(packed); gk_host_free(wdb); }
 };
 
 RootParallelSearch::RootParallelSearch(const RootParallelConfig& cfg) : m(new Impl), m_cfg(cfg) {
@@ -108,8 +109,6 @@ RootParallelSearch::RootParallelSearch(const RootParallelConfig& cfg) : m(new Im
     threads = std::max(1, std::min(threads, cfg.trees));
     m->pool.reset(new Pool(threads));
     m->trees.resize(cfg.trees);
-    m->packed.resize(static_cast<std::size_t>(cfg.trees) * 16);
-    m->wdb.resize(static_cast<std::size_t>(cfg.trees) * 3);
 }
 
 RootParallelSearch::~RootParallelSearch() { delete m; }
@@ -196,6 +195,13 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         t.rng.seed(static_cast<std::uint32_t>(m_cfg.seed * 2654435761u + static_cast<std::uint32_t>(m_cfg.replica_base + i)));
     }
     ensure_gpu();
+    if (!m->packed) {
+        void *a = nullptr, *b = nullptr;
+        if (gk_host_alloc(&a, static_cast<std::size_t>(n_trees) * 64) != GK_OK || gk_host_alloc(&b, static_cast<std::size_t>(n_trees) * 12) != GK_OK)
+            throw std::runtime_error(std::string("gk_host_alloc: ") + gk_last_error());
+        m->packed = static_cast<std::uint32_t*>(a);
+        m->wdb = static_cast<std::int32_t*>(b);
+    }
     Board probe = root;
     if (probe.checkGameEnd() || playouts_per_tree <= 0) { seconds_total = 0; return; }   // nothing to search from a decided position
     const double c_puct = m_cfg.c_puct;
@@ -234,8 +240,8 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         });
         // ---- simulation: all leaves in one launch ------------------------------------------------------------
         const auto g0 = std::chrono::steady_clock::now();
-        if (gk_rollout_batch_host(m->packed.data(), n_trees, m_cfg.c_rollouts, m_cfg.seed, static_cast<std::uint32_t>(round),
-                                  m_cfg.replica_base, m->wdb.data()) != GK_OK)
+        if (gk_rollout_batch_host(m->packed, n_trees, m_cfg.c_rollouts, m_cfg.seed, static_cast<std::uint32_t>(round),
+                                  m_cfg.replica_base, m->wdb) != GK_OK)
             throw std::runtime_error(std::string("gk_rollout_batch_host: ") + gk_last_error());
         seconds_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
         leaves += n_trees;

@@ -34,6 +34,7 @@
  */
 #ifndef GOMOKU_B200_H_
 #define GOMOKU_B200_H_
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -183,6 +184,10 @@ gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_
  * under the same rotations / reflections (augment_game_data's rot_probs / flip_probs). */
 gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last_moves, int n, int augment,
                                  uint8_t* d_planes, const float* d_probs, float* d_probs_out, void* stream);
+
+/* Page-locked host buffers for the *_host entry points (cudaHostAlloc / cudaFreeHost). */
+gk_status gk_host_alloc(void** out, size_t bytes);
+gk_status gk_host_free(void* ptr);
 
 /* ---- host utilities (no GPU needed) ------------------------------------------------- */
 /* move lists (black first, alternating; position i = moves[starts[i]..starts[i+1])) -> packed boards */
