@@ -324,6 +324,39 @@ def run_gpu_arm(args, rank, world, local_rank):
         assert torch.equal(h_out["scores"][:4096], out["scores"][:4096].cpu())
         assert torch.equal(h_wdb, wdb.cpu())
 
+    # ---- the other configurations of BASELINE.json, briefly (same timing rules; extra objects of the JSON line) -----
+    extras = {}
+    pol = gk.eval_policy_batch(d_boards, table)                        # row f1: evaluator + policy heads, 904 B out per board
+    pol_ms, _ = timed(lambda: gk.eval_policy_batch(d_boards, table), max(3, args.steps // 4), 2)
+    h_pol = (torch.empty((n_eval, 225), dtype=torch.float32).pin_memory(), torch.empty((n_eval,), dtype=torch.float32).pin_memory(),
+             torch.empty((n_eval,), dtype=torch.int8).pin_memory())
+    pol_e2e_s = wall(lambda: gk.eval_policy_batch_host(h_pinned, table, out=h_pol), e2e_steps, 1)
+    if rank == 0:
+        assert torch.equal(h_pol[0][:2048], pol["probs"][:2048].cpu())
+    extras["policy_heads"] = {"metric": "board evals/sec with policy heads (probs + value, Heuristic.hpp:16-45)",
+                              "value": world * n_eval / (pol_ms * 1e-3), "unit": "boards/s", "ms_per_step": pol_ms,
+                              "e2e": {"value": world * n_eval / pol_e2e_s, "unit": "boards/s", "h2d_bytes_per_step": n_eval * 64,
+                                      "d2h_bytes_per_step": n_eval * 905, "ms_per_step": pol_e2e_s * 1e3}}
+    del pol, h_pol
+    n_games = 8192                                                      # configs[4]: concurrent guided self-play games per GPU
+    d_empty = torch.zeros((n_games, 16), dtype=torch.int32, device=dev)
+    sp = {}
+
+    def selfplay_step():
+        sp["r"] = gk.guided_rollout_batch(d_empty, mode="sample", key=gk.SYNTH_KEY, game_base=rank * n_games, want_moves=True)
+    sp_ms, _ = timed(selfplay_step, max(3, args.steps // 4), 2)
+    sp_moves = float(sp["r"]["length"].float().sum().item())
+    extras["selfplay"] = {"metric": "pattern-guided self-play games/sec (configs[4], 8192 concurrent games per GPU, sampled moves)",
+                          "value": world * n_games / (sp_ms * 1e-3), "unit": "games/s", "ms_per_step": sp_ms,
+                          "evaluated_moves_per_sec": world * sp_moves / (sp_ms * 1e-3), "mean_game_length": sp_moves / n_games}
+    n_enc = 1 << 18
+    d_last = torch.full((n_enc, 2), -1, dtype=torch.int16, device=dev)
+    enc_ms, _ = timed(lambda: gk.encode_states_batch(d_boards[:n_enc], d_last, augment=True), max(3, args.steps // 4), 2)
+    enc_gbs = n_enc * (64 + 4 + 10800) / (enc_ms * 1e-3) / 1e9
+    extras["encode"] = {"metric": "augmented feature planes (8 x 6 x 15 x 15 uint8 per position)", "value": world * n_enc / (enc_ms * 1e-3),
+                        "unit": "positions/s", "ms_per_step": enc_ms,
+                        "roofline": {"bound": "hbm", "achieved": enc_gbs, "unit": "GB/s", "kernel": "encode_states_kernel"}}
+
     clocks = sampler.summary()
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload --------------------------------------
@@ -385,6 +418,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             "cpu_baseline": cpu_roll,
         },
     }
+    extras["encode"]["roofline"].update({"peak": peak, "frac": extras["encode"]["roofline"]["achieved"] / peak})
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -291,20 +291,24 @@ def hybrid_simulate_batch(boards, table=None, want_flags=False, stream=None):
     return out
 
 
-def eval_policy_batch_host(boards, table=None, decisive=False):
-    """Same through HOST buffers: returns numpy (probs[n,225] f32, value[n] f32, winner[n] i8).
-    decisive=True applies Heuristic::DecisiveFilter (= gk_hybrid_simulate_batch_host)."""
+def eval_policy_batch_host(boards, table=None, decisive=False, out=None):
+    """Same through HOST buffers: returns (probs[n,225] f32, value[n] f32, winner[n] i8) -- numpy arrays, or the
+    pinned CPU tensors passed as out=(probs, value, winner).  decisive=True applies Heuristic::DecisiveFilter
+    (= gk_hybrid_simulate_batch_host)."""
     table = table or default_table()
     _require_init()
     b = boards.numpy() if hasattr(boards, "numpy") else boards
     b = np.ascontiguousarray(b).view(np.uint32).reshape(-1, BOARD_WORDS)
     n = b.shape[0]
-    probs, value, winner = np.empty((n, CELLS), np.float32), np.empty((n,), np.float32), np.empty((n,), np.int8)
+    if out is None:
+        out = (np.empty((n, CELLS), np.float32), np.empty((n,), np.float32), np.empty((n,), np.int8))
+
+    def hp(x):
+        return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else x.ctypes.data_as(ctypes.c_void_p)
+
     fn = lib().gk_hybrid_simulate_batch_host if decisive else lib().gk_eval_policy_batch_host
-    _check(fn(table.handle, b.ctypes.data_as(ctypes.c_void_p), n,
-                                           probs.ctypes.data_as(ctypes.c_void_p), value.ctypes.data_as(ctypes.c_void_p),
-                                           winner.ctypes.data_as(ctypes.c_void_p)))
-    return probs, value, winner
+    _check(fn(table.handle, b.ctypes.data_as(ctypes.c_void_p), n, hp(out[0]), hp(out[1]), hp(out[2])))
+    return out
 
 
 def guided_rollout_batch(boards, mode="max", key=SYNTH_KEY, ctr_hi=0, game_base=0, max_moves=CELLS, want_moves=True,

@@ -32,6 +32,14 @@ namespace gk {
 
 namespace {
 
+#ifndef GK_HEADS_INLINE
+#define GK_HEADS_INLINE __forceinline__
+#endif
+#ifndef GK_HEADS_UNROLL
+#define GK_HEADS_UNROLL 1
+#endif
+#define GK_PRAGMA(x) _Pragma(#x)
+#define GK_UNROLL(n) GK_PRAGMA(unroll n)
 constexpr int kWarpsPerCta = 32;
 constexpr size_t kSmemLimit = 227 * 1024;
 constexpr int kScoreWords = 4 * kCells;        // 900
@@ -249,58 +257,61 @@ __host__ __device__ inline size_t warp_bytes(int list_cap, bool heads) {
 //   value          = tanh( (1.2 <S(p,p), DW(p)> - <S(-p,-p), DW(-p)>) / 500 )            (:32-36)
 // Floating point: sums run lane-strided then by warp shuffle, so they differ from Eigen's packet order in
 // the last bits (tolerance in tests/test_heads.py).
-__device__ __forceinline__ void policy_heads(const WarpSmem& ws, const uint16_t* s_lut, uint32_t mine, int lane,
-                                             float* probs_out, float* value_out, float (&pr)[8], int& n_stones, int& to_move) {
+// The loops over cells are deliberately NOT unrolled and keep their per-cell values in shared memory (the flag
+// words and emission lists are dead by now): a fully unrolled version is 115 KB of code, and with 28 warps at
+// different places the kernel then waits on instruction fetch (ncu: stall_no_instruction 9 per issue).
+//   dwv  [2][225] floats over ws.flags: DensityWeight numerators 3W / (1 + 2N), then normalised
+//   prob [225]    floats over the emission lists: the move probabilities
+__device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const uint16_t* s_lut, uint32_t mine, int lane,
+                                          float* value_out, int& n_stones, int& to_move) {
+    float* dwv = reinterpret_cast<float*>(ws.flags);
     const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
     const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
     const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
     const int p = n_black == n_white ? 1 : 0;                      // Group(player to move): black moves first (Game.h:128)
-    float dw[2][8], n2[2] = { 0.f, 0.f };
-#pragma unroll
+    float n2w = 0.f, n2b = 0.f;
+    GK_UNROLL(GK_HEADS_UNROLL)
     for (int k = 0; k < 8; ++k) {
         const int c = lane + 32 * k, cc = c < kCells ? c : kCells - 1;
         const int y = cc / kWidth, x = cc - y * kWidth;
         const bool open = c < kCells && cell_value(ws.board, cc) == 0u;
+        uint32_t acc_w = 0, acc_b = 0;
 #pragma unroll
-        for (int P = 0; P < 2; ++P) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int dy = -3; dy <= 3; ++dy) {
-                const int yy = y + dy;
-                const uint32_t row = __shfl_sync(0xffffffffu, mine, P * 15 + min(max(yy, 0), kHeight - 1));
-                const uint32_t w7 = ((row << 3) >> x) & 0x7fu;
-                const uint32_t t = s_lut[(dy < 0 ? -dy : dy) * 128 + w7];
-                if (yy >= 0 && yy < kHeight) acc += t;
-            }
-            const float N = float(acc & 0xffu), W = float(acc >> 8);
-            const float v = open ? (3.f * W) / (1.f + 2.f * N) : 0.f;
-            dw[P][k] = v;
-            n2[P] += v * v;
+        for (int dy = -3; dy <= 3; ++dy) {
+            const int yy = min(max(y + dy, 0), kHeight - 1);
+            const bool in = y + dy >= 0 && y + dy < kHeight;
+            const uint32_t row_w = __shfl_sync(0xffffffffu, mine, yy), row_b = __shfl_sync(0xffffffffu, mine, 15 + yy);
+            const uint16_t* lut = s_lut + (dy < 0 ? -dy : dy) * 128;
+            const uint32_t tw = lut[((row_w << 3) >> x) & 0x7fu], tb = lut[((row_b << 3) >> x) & 0x7fu];
+            if (in) { acc_w += tw; acc_b += tb; }
         }
+        const float vw = open ? (3.f * float(acc_w >> 8)) / (1.f + 2.f * float(acc_w & 0xffu)) : 0.f;
+        const float vb = open ? (3.f * float(acc_b >> 8)) / (1.f + 2.f * float(acc_b & 0xffu)) : 0.f;
+        if (c < kCells) { dwv[c] = vw; dwv[kCells + c] = vb; }
+        n2w += vw * vw;
+        n2b += vb * vb;
     }
 #pragma unroll
-    for (int P = 0; P < 2; ++P) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) n2[P] += __shfl_xor_sync(0xffffffffu, n2[P], d);
+    for (int d = 16; d > 0; d >>= 1) {
+        n2w += __shfl_xor_sync(0xffffffffu, n2w, d);
+        n2b += __shfl_xor_sync(0xffffffffu, n2b, d);
     }
-    const float nrm0 = n2[0] > 0.f ? sqrtf(n2[0]) : 1.f, nrm1 = n2[1] > 0.f ? sqrtf(n2[1]) : 1.f;
+    const float nrm_w = n2w > 0.f ? sqrtf(n2w) : 1.f, nrm_b = n2b > 0.f ? sqrtf(n2b) : 1.f;
     const int* s_self = ws.scores + 3 * p * kCells;                // S(p, p)
     const int* s_anti = ws.scores + (2 * (1 - p) + p) * kCells;    // S(-p, p)
     const int* s_rival = ws.scores + 3 * (1 - p) * kCells;         // S(-p, -p)
-    float a[8], a2 = 0.f, sdot = 0.f, rdot = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = lane + 32 * k;
-        a[k] = 0.f;
-        if (c < kCells) {
-            const float w0 = dw[0][k] / nrm0, w1 = dw[1][k] / nrm1;            // normalized DW(white), DW(black)
-            const float wp = p ? w1 : w0, wr = p ? w0 : w1;
-            const float self_worthy = float(s_self[c]) * wp, rival_anti = float(s_anti[c]) * wr;
-            a[k] = 0.6f * self_worthy + 0.4f * rival_anti;
-            a2 += a[k] * a[k];
-            sdot += float(s_self[c]) * wp;
-            rdot += float(s_rival[c]) * wr;
-        }
+    float a2 = 0.f, sdot = 0.f, rdot = 0.f;
+    __syncwarp();
+#pragma unroll 1
+    for (int c = lane; c < kCells; c += 32) {
+        const float w0 = dwv[c] / nrm_w, w1 = dwv[kCells + c] / nrm_b;    // normalized DW(white), DW(black)
+        const float wp = p ? w1 : w0, wr = p ? w0 : w1;
+        const float self_worthy = float(s_self[c]) * wp, rival_anti = float(s_anti[c]) * wr;
+        const float av = 0.6f * self_worthy + 0.4f * rival_anti;
+        prob[c] = av;
+        a2 += av * av;
+        sdot += float(s_self[c]) * wp;
+        rdot += float(s_rival[c]) * wr;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -312,28 +323,24 @@ __device__ __forceinline__ void policy_heads(const WarpSmem& ws, const uint16_t*
     const float an = a2 > 0.f ? sqrtf(a2) : 1.f;
     n_stones = n_black + n_white;
     to_move = p;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = lane + 32 * k;
-        pr[k] = c >= kCells ? 0.f : empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : a[k] / an;
-        if (probs_out && c < kCells) probs_out[c] = pr[k];
-    }
+#pragma unroll 1
+    for (int c = lane; c < kCells; c += 32)
+        prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : prob[c] / an;
     if (value_out && lane == 0) *value_out = float(tanh((1.2 * double(sdot) - double(rdot)) / 500.0));
+    __syncwarp();
 }
 
 // Heuristic::DecisiveFilter (include/algorithms/Heuristic.hpp:93-161): walk the priority automaton
 // +4 > -4 > +L3 == +To44 > -L3 == -To44 >= +To43 > -To43 > +To33 > -To33 over the pattern / compound totals; at the
 // first class with a non-zero count keep only the cells flagged for one of the remaining candidates
 // (Record::get(player, cur_player), any direction) and re-normalise.  p = Group(side to move).
-__device__ __forceinline__ void decisive_filter(const WarpSmem& ws, const uint32_t* dflags, float (&pr)[8], int p, int lane) {
+__device__ GK_HEADS_INLINE void decisive_filter(const WarpSmem& ws, const uint32_t* dflags, float* prob, int p, int lane) {
     // the automaton table (:101-105) visits (state, anti) in this fixed order until a candidate has a count
     //   state: 0 = _4 {LiveFour, DeadFour}, 1 = L3 {LiveThree}, 2..4 = To44 / To43 / To33 {compound 2 / 1 / 0}
-    const int order[10][2] = { { 0, 0 }, { 0, 1 }, { 1, 0 }, { 2, 0 }, { 1, 1 }, { 2, 1 }, { 3, 0 }, { 3, 1 }, { 4, 0 }, { 4, 1 } };
     uint32_t mask = 0;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        if (mask) break;
-        const int state = order[i][0], anti = order[i][1];
+#pragma unroll 1
+    for (int i = 0; i < 10 && !mask; ++i) {
+        const int state = (0x4433212100 >> (4 * i)) & 15, anti = (0x2b2 >> i) & 1;   // (0,0)(0,1)(1,0)(2,0)(1,1)(2,1)(3,0)(3,1)(4,0)(4,1)
         const int pl = anti ? 1 - p : p, g = 2 * pl + p;                        // Group(favour = pl, perspective = cur)
         if (state == 0) {
             const uint32_t l4 = ws.totals[pl * 8 + 7], d4 = ws.totals[pl * 8 + 6];
@@ -349,19 +356,20 @@ __device__ __forceinline__ void decisive_filter(const WarpSmem& ws, const uint32
     }
     if (!mask) return;
     float n2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = lane + 32 * k;
-        if (c >= kCells || !(dflags[c] & mask)) pr[k] = 0.f;
-        n2 += pr[k] * pr[k];
+#pragma unroll 1
+    for (int c = lane; c < kCells; c += 32) {
+        const float v = (dflags[c] & mask) ? prob[c] : 0.f;
+        prob[c] = v;
+        n2 += v * v;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, d);
     if (n2 > 0.f) {
         const float nrm = sqrtf(n2);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pr[k] = pr[k] / nrm;
+#pragma unroll 1
+        for (int c = lane; c < kCells; c += 32) prob[c] = prob[c] / nrm;
     }
+    __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t philox_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -383,13 +391,13 @@ __device__ __forceinline__ uint32_t philox_word(uint32_t c0, uint32_t c1, uint32
 //           Game.cpp:75-78).  The reference's std::discrete_distribution / mt19937 stream is implementation
 //           defined; here the weights are quantised to w = round(p * 2^20), cells are ordered by index, and the
 //           draw is r = mulhi32(philox word, sum w): the first cell whose running sum exceeds r.
-__device__ __forceinline__ int select_move(const float (&pr)[8], int lane, int mode, uint32_t rnd) {
+__device__ GK_HEADS_INLINE int select_move(const float* prob, int lane, int mode, uint32_t rnd) {
     if (mode == 1) {
         float best = 0.f;
         int arg = 0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (pr[k] > best) { best = pr[k]; arg = lane + 32 * k; }
+#pragma unroll 1
+        for (int c = lane; c < kCells; c += 32)
+            if (prob[c] > best) { best = prob[c]; arg = c; }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, best, d);
@@ -398,25 +406,25 @@ __device__ __forceinline__ int select_move(const float (&pr)[8], int lane, int m
         }
         return best > 0.f ? arg : -1;
     }
-    uint32_t w[8], base = 0;
-    int chosen = 0x7fffffff;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = uint32_t(pr[k] * 1048576.f + 0.5f);
     uint32_t total = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) total += w[k];
+#pragma unroll 1
+    for (int c = lane; c < kCells; c += 32) total += uint32_t(prob[c] * 1048576.f + 0.5f);
     total = __reduce_add_sync(0xffffffffu, total);
     if (total == 0) return -1;
     const uint32_t r = __umulhi(rnd, total);
-#pragma unroll
+    uint32_t base = 0;
+    int chosen = 0x7fffffff;
+#pragma unroll 1
     for (int k = 0; k < 8; ++k) {                                  // cells 32 k .. 32 k + 31 in index order
-        uint32_t incl = w[k];
+        const int c = lane + 32 * k;
+        const uint32_t w = c < kCells ? uint32_t(prob[c] * 1048576.f + 0.5f) : 0u;
+        uint32_t incl = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += up;
         }
-        if (w[k] != 0 && base + incl > r && base + incl - w[k] <= r) chosen = lane + 32 * k;
+        if (w != 0 && base + incl > r && base + incl - w <= r) chosen = c;
         base += __shfl_sync(0xffffffffu, incl, 31);
     }
     return __reduce_min_sync(0xffffffffu, chosen);
@@ -665,17 +673,13 @@ ac_eval_kernel(EvalArgs a) {
         __syncwarp();
 
         if (kHeads) {
-            float pr[8];
+            float* prob = reinterpret_cast<float*>(lists);                   // 225 floats over the (dead) emission lists
             int n_stones, to_move;
-            policy_heads(ws, s_lut, mine, lane, nullptr, (a.value && !kGuided) ? a.value + b : nullptr, pr, n_stones, to_move);
-            __syncwarp();
+            policy_heads(ws, prob, s_lut, mine, lane, (a.value && !kGuided) ? a.value + b : nullptr, n_stones, to_move);
             if (!kGuided) {
-                if (a.decisive) decisive_filter(ws, dflags, pr, to_move, lane);  // TraditionalPolicy::hybridSimulate, Traditional.h:52-53
-                if (a.probs) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (lane + 32 * k < kCells) a.probs[b * kCells + lane + 32 * k] = pr[k];
-                }
+                if (a.decisive) decisive_filter(ws, dflags, prob, to_move, lane);  // TraditionalPolicy::hybridSimulate, Traditional.h:52-53
+                if (a.probs)
+                    for (int c = lane; c < kCells; c += 32) a.probs[b * kCells + c] = prob[c];
                 if (a.dflags) for (int i = lane; i < kCells; i += 32) a.dflags[b * kCells + i] = dflags[i];
             }
             if (kGuided) {
@@ -688,7 +692,7 @@ ac_eval_kernel(EvalArgs a) {
                     if (a.g_mode == 2)
                         rnd = philox_word(uint32_t(played) >> 2, 0u, uint32_t(a.g_game_base) + uint32_t(b), a.g_ctr_hi, a.g_key_lo,
                                           a.g_key_hi, uint32_t(played) & 3u);
-                    cell = select_move(pr, lane, a.g_mode, rnd);
+                    cell = select_move(prob, lane, a.g_mode, rnd);
                 }
                 if (cell >= 0) {
                     if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
