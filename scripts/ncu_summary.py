@@ -1,25 +1,36 @@
 """Turns an `ncu --set full` report of the bench-size launches into profiles/ncu_summary.json
-(per-launch dram bytes, warp instructions, issue utilisation) -- the figures bench.py quotes.
+(per-launch dram bytes, warp instructions, issue utilisation, stalls) -- the figures bench.py quotes.
 
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv ; python scripts/ncu_summary.py raw.csv
+The first launch of every distinct kernel is kept; ac_eval_kernel<0, 0> and rollout_kernel<0, 12> are
+stored under the plain names bench.py looks up.
 """
 import csv, json, os, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, units = rows[0], rows[1]
-col = {h: i for i, h in enumerate(hdr)}
-def num(r, name, scale=1.0):
-    try: return float(r[col[name]].replace(",", "")) * scale
-    except Exception: return None
+h, u = rows[0], rows[1]
+col = {x: i for i, x in enumerate(h)}
+scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+
+
+def num(r, name, unit_scaled=False):
+    try:
+        v = float(r[col[name]].replace(",", ""))
+        return v * scale.get(u[col[name]], 1.0) if unit_scaled else v
+    except Exception:
+        return None
+
+
 out = {}
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    key = "ac_eval_kernel" if "ac_eval" in name else "rollout_kernel" if "rollout_kernel" in name else None
-    if key is None: continue
-    unit_scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-    rd = num(r, "dram__bytes_read.sum", unit_scale.get(units[col["dram__bytes_read.sum"]], 1.0))
-    wr = num(r, "dram__bytes_write.sum", unit_scale.get(units[col["dram__bytes_write.sum"]], 1.0))
-    t_unit = units[col["gpu__time_duration.sum"]]
+    key = name.split("::")[-1].split("(")[0]
+    key = "ac_eval_kernel" if key.startswith("ac_eval_kernel<0, 0>") else "rollout_kernel" if key.startswith("rollout_kernel") else key
+    if key in out:
+        continue
+    rd, wr = num(r, "dram__bytes_read.sum", True), num(r, "dram__bytes_write.sum", True)
     out[key] = {
+        "kernel": name, "grid": r[col["launch__grid_size"]], "block": r[col["launch__block_size"]],
+        "ncu_duration": r[col["gpu__time_duration.sum"]] + " " + u[col["gpu__time_duration.sum"]],
         "dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_read_bytes": rd, "dram_write_bytes": wr,
         "warp_inst_per_launch": num(r, "smsp__inst_executed.sum"),
         "threads_per_inst": num(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
@@ -31,9 +42,10 @@ for r in rows[2:]:
         "dram_throughput_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
         "registers_per_thread": num(r, "launch__registers_per_thread"),
-        "ncu_duration": r[col["gpu__time_duration.sum"]] + " " + t_unit,
-        "grid": r[col["launch__grid_size"]], "block": r[col["launch__block_size"]],
+        "stalls_per_issue": {x.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): num(r, x)
+                             for x in h if "issue_stalled" in x and "per_issue_active" in x and (num(r, x) or 0) > 0.1},
     }
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_summary.json")
 json.dump(out, open(dst, "w"), indent=1)
-print(json.dumps(out, indent=1))
+for k, v in out.items():
+    print(k, v["ncu_duration"], "warp-inst", v["warp_inst_per_launch"], "issue%", v["issue_active_pct"], "dram bytes", v["dram_bytes_per_launch"])

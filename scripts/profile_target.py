@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu: a few launches of each hot kernel at the bench sizes."""
+"""Small fixed workload for ncu: a few launches of every kernel at the bench sizes."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,5 +15,13 @@ for _ in range(2):
 r = None
 for _ in range(2):
     r = gk.rollout_batch(bt[:4096].contiguous(), int(os.environ.get("GK_PROFILE_ROLLOUTS", 1024)))
+if os.environ.get("GK_PROFILE_ALL"):
+    m = min(n, 1 << 18)
+    pol = gk.eval_policy_batch(bt[:m])
+    hyb = gk.hybrid_simulate_batch(bt[:m])
+    g = gk.guided_rollout_batch(torch.zeros((8192, 16), dtype=torch.int32, device="cuda"), mode="sample")
+    last = torch.full((m, 2), -1, dtype=torch.int16, device="cuda")
+    enc = gk.encode_states_batch(bt[:m], last, augment=True)
+    enc1 = gk.encode_states_batch(bt[:m], last)
 torch.cuda.synchronize()
 print("ok", int(out["pat_totals"].sum()), int(r["wdb"].sum()))
