@@ -181,6 +181,34 @@ def unpack_boards(boards):
 
 
 # ---- device entry points (torch tensors on the bound GPU) ---------------------------------------------
+def nccl_unique_id():
+    """128-byte NCCL id made by rank 0 (gk_nccl_unique_id); hand it to the other ranks by any side channel."""
+    buf = (ctypes.c_uint8 * 128)()
+    _check(lib().gk_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def nccl_init(unique_id, world_size, rank):
+    """Join the library's own communicator (one process per GPU, after init())."""
+    _require_init()
+    buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+    _check(lib().gk_nccl_init(buf, int(world_size), int(rank)))
+
+
+def nccl_shutdown():
+    _check(lib().gk_nccl_shutdown())
+
+
+def root_allreduce(stats, stream=None):
+    """In-place sum of the int64[3,225] root statistics (a CUDA tensor) over the ranks of the library's
+    communicator: the single collective of the path (gk_root_allreduce, NCCL over NVLink)."""
+    torch = _torch()
+    if not stats.is_cuda or stats.dtype != torch.int64 or stats.numel() != 3 * CELLS or not stats.is_contiguous():
+        raise GomokuB200Error("stats must be a contiguous CUDA int64 tensor with 3*225 elements")
+    _check(lib().gk_root_allreduce(None, _ptr(stats), _stream_ptr(stream)))
+    return stats
+
+
 def _torch():
     import torch
     return torch

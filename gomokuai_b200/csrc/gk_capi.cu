@@ -1,6 +1,7 @@
 // gk_capi.cu -- the C-ABI of include/gomoku_b200.h: argument checking, table upload,
 // stream plumbing and the chunked host<->device pipelines.  No compute happens here.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstring>
@@ -497,6 +498,74 @@ gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last
         return fail(GK_ERR_INVALID, "bad arguments");
     gk::EncodeArgs a{ d_boards, d_last_moves, n, augment ? 1 : 0, d_planes, d_probs, d_probs_out };
     GK_CUDA(gk::launch_encode(a, g_sm_count, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
+// ---- NCCL, resolved at run time ---------------------------------------------------------------------------
+namespace {
+struct NcclId128 { char b[128]; };                                    // ncclUniqueId: passed by value (nccl.h)
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+} g_nccl;
+void* g_nccl_comm = nullptr;
+
+gk_status nccl_load() {
+    if (g_nccl.handle) return GK_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(GK_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+        return fail(GK_ERR_NCCL, "libnccl.so.2 lacks an expected symbol");
+    g_nccl.handle = h;
+    return GK_OK;
+}
+gk_status nccl_fail(int rc, const char* what) { return fail(GK_ERR_NCCL, std::string(what) + ": " + g_nccl.GetErrorString(rc)); }
+}  // namespace
+
+gk_status gk_nccl_unique_id(uint8_t id[128]) {
+    if (!id) return fail(GK_ERR_INVALID, "id is null");
+    if (gk_status s = nccl_load()) return s;
+    if (int rc = g_nccl.GetUniqueId(id)) return nccl_fail(rc, "ncclGetUniqueId");
+    return GK_OK;
+}
+
+gk_status gk_nccl_init(const uint8_t id[128], int world_size, int rank) {
+    if (gk_status s = require_device()) return s;
+    if (!id || world_size <= 0 || rank < 0 || rank >= world_size) return fail(GK_ERR_INVALID, "bad arguments");
+    if (gk_status s = nccl_load()) return s;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_nccl_comm) return fail(GK_ERR_INVALID, "gk_nccl_init called twice");
+    NcclId128 uid;
+    std::memcpy(uid.b, id, 128);
+    if (int rc = g_nccl.CommInitRank(&g_nccl_comm, world_size, uid, rank)) { g_nccl_comm = nullptr; return nccl_fail(rc, "ncclCommInitRank"); }
+    return GK_OK;
+}
+
+gk_status gk_root_allreduce(void* nccl_comm, int64_t* d_stats, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (!d_stats) return fail(GK_ERR_INVALID, "d_stats is null");
+    if (gk_status s = nccl_load()) return s;
+    void* comm = nccl_comm ? nccl_comm : g_nccl_comm;
+    if (!comm) return fail(GK_ERR_NOT_INIT, "no communicator: pass one or call gk_nccl_init");
+    constexpr int kNcclInt64 = 4, kNcclSum = 0;                      // ncclDataType_t / ncclRedOp_t (nccl.h)
+    if (int rc = g_nccl.AllReduce(d_stats, d_stats, 3 * GK_CELLS, kNcclInt64, kNcclSum, comm, static_cast<cudaStream_t>(stream)))
+        return nccl_fail(rc, "ncclAllReduce");
+    return GK_OK;
+}
+
+gk_status gk_nccl_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_nccl_comm) { g_nccl.CommDestroy(g_nccl_comm); g_nccl_comm = nullptr; }
     return GK_OK;
 }
 

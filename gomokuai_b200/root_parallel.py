@@ -2,13 +2,31 @@
 
 Every rank (one process per GPU) runs `trees_per_rank` independent search trees from the same
 root with disjoint Philox streams; leaves are simulated in batches by the rollout kernel.  The
-only exchange is ONE allreduce(sum) of the int64[3][225] root statistics per move
-(torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests); integer counts make the
-result independent of the reduction order.
+only exchange is ONE allreduce(sum) of the int64[3][225] root statistics per move; integer counts make
+the result independent of the reduction order.  On GPUs the sum goes through the C-ABI
+(`gk_root_allreduce`, the library's own NCCL communicator over NVLink; torch.distributed only carries
+the 128-byte NCCL id to the other ranks once); the gloo path exists for the CPU tests.
 """
 import math
 
 import numpy as np
+
+
+_gk_comm_ready = False
+
+
+def _ensure_gk_comm(group=None):
+    """Create the library's NCCL communicator once: rank 0 makes the id, the process group broadcasts it."""
+    global _gk_comm_ready
+    if _gk_comm_ready:
+        return
+    import torch.distributed as dist
+    import gomokuai_b200 as gk
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [gk.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    gk.nccl_init(box[0], world, rank)
+    _gk_comm_ready = True
 
 
 def allreduce_root_stats(stats, group=None):
@@ -18,12 +36,15 @@ def allreduce_root_stats(stats, group=None):
     stats = np.ascontiguousarray(stats, np.int64)
     if not (dist.is_available() and dist.is_initialized()):
         return stats
-    backend = dist.get_backend(group)
     t = torch.from_numpy(stats.copy())
-    if backend == "nccl":
-        t = t.cuda()
+    if dist.get_backend(group) == "nccl":
+        import gomokuai_b200 as gk
+        _ensure_gk_comm(group)
+        t = gk.root_allreduce(t.cuda())
+        torch.cuda.current_stream().synchronize()
+        return t.cpu().numpy()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    return t.cpu().numpy()
+    return t.numpy()
 
 
 def best_move(stats):

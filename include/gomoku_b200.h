@@ -185,6 +185,20 @@ gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_
 gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last_moves, int n, int augment,
                                  uint8_t* d_planes, const float* d_probs, float* d_probs_out, void* stream);
 
+/* ---- root-parallel exchange (BASELINE config 4) -------------------------------------------------------
+ * The only collective of the path: one allreduce(sum) of the int64[3][225] root statistics per move
+ * ([0] visits, [1] black-won, [2] white-won rollouts per root child) over NCCL (NVLink / NVSwitch).
+ * libnccl.so.2 is resolved at run time (dlopen), so the library has no link-time NCCL dependency and
+ * shares the copy already loaded by the process (e.g. torch's).
+ *   gk_nccl_unique_id   rank 0 creates the 128-byte id and hands it to the other ranks by any side channel
+ *   gk_nccl_init        every rank (one process per GPU, after gk_init) joins the communicator
+ *   gk_root_allreduce   in-place sum of d_stats over the ranks; `nccl_comm` = an ncclComm_t of the caller,
+ *                       or NULL for the communicator made by gk_nccl_init */
+gk_status gk_nccl_unique_id(uint8_t id[128]);
+gk_status gk_nccl_init(const uint8_t id[128], int world_size, int rank);
+gk_status gk_root_allreduce(void* nccl_comm, int64_t* d_stats, void* stream);
+gk_status gk_nccl_shutdown(void);
+
 /* Page-locked host buffers for the *_host entry points (cudaHostAlloc / cudaFreeHost). */
 gk_status gk_host_alloc(void** out, size_t bytes);
 gk_status gk_host_free(void* ptr);

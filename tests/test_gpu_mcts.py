@@ -118,3 +118,24 @@ def test_traditional_policy_mcts_blocks_an_open_four(core):
         b2.apply_move(c)
     m2 = core.MCTS(c_iterations=200, policy=core.TraditionalPolicy())
     assert int(m2.get_action(b2)) in (110, 111, 115, 116)
+
+
+def test_root_allreduce_through_the_c_abi(gpu):
+    """gk_root_allreduce on the library's own NCCL communicator (libnccl resolved at run time).  One rank:
+    the sum over a world of one is the identity; the 2-GPU run is scripts/bench_root_parallel.py."""
+    import torch
+    uid = gpu.nccl_unique_id()
+    assert len(uid) == 128
+    gpu.nccl_init(uid, 1, 0)
+    try:
+        with pytest.raises(gpu.GomokuB200Error):
+            gpu.nccl_init(uid, 1, 0)                     # a second communicator is refused
+        rng = np.random.default_rng(3)
+        stats = rng.integers(0, 1 << 40, size=(3, 225)).astype(np.int64)
+        t = gpu.root_allreduce(torch.from_numpy(stats).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(t.cpu().numpy(), stats)
+        with pytest.raises(gpu.GomokuB200Error):
+            gpu.root_allreduce(torch.zeros(10, dtype=torch.int64, device="cuda"))
+    finally:
+        gpu.nccl_shutdown()
