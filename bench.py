@@ -185,7 +185,7 @@ def run_reference_arm(args, rank):
                                       "sample": f"{n_roll_pos} positions x {n_roll} rollouts per step"},
                      "e2e": {"value": rvalue, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -420,9 +420,30 @@ def run_gpu_arm(args, rank, world, local_rank):
     }
     extras["encode"]["roofline"].update({"peak": peak, "frac": extras["encode"]["roofline"]["achieved"] / peak})
     line.update(extras)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything a library writes to fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line goes to the
+    saved descriptor through _emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, text)
+    else:
+        os.write(_REAL_STDOUT, text)
 
 
 def main():
@@ -437,6 +458,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args, rank)
     else:
