@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -443,6 +444,29 @@ gk_status gk_guided_rollout_batch(const gk_table* t, const uint32_t* d_boards, i
 }
 
 // ---- rollouts --------------------------------------------------------------------------------------
+// Slot-image scratch of the rollout kernels: one grow-only buffer per stream, so launches in flight on different
+// streams never share it.  Growing frees the old buffer with cudaFree, which waits for the device to drain.
+namespace {
+struct RolloutScratch { uint32_t* images = nullptr; size_t cap = 0; };
+std::map<cudaStream_t, RolloutScratch> g_rollout_scratch;
+std::mutex g_scratch_mutex;
+
+gk_status rollout_scratch(cudaStream_t stream, int n, uint32_t** out) {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    RolloutScratch& sc = g_rollout_scratch[stream];
+    const size_t need = gk::rollout_scratch_bytes(n);
+    if (need > sc.cap) {
+        if (sc.images) GK_CUDA(cudaFree(sc.images));
+        sc.images = nullptr; sc.cap = 0;
+        const size_t want = std::max(need, size_t(64) << 10);
+        GK_CUDA(cudaMalloc(&sc.images, want));
+        sc.cap = want;
+    }
+    *out = sc.images;
+    return GK_OK;
+}
+}  // namespace
+
 static gk_status rollout_common(const uint32_t* d_boards, int n, int rollouts_per_pos, uint64_t key, uint32_t ctr_hi,
                                 int pos_base, const uint8_t* d_r_stream, int stream_stride, int32_t* d_wdb,
                                 int8_t* d_winners, uint8_t* d_lengths, cudaStream_t stream) {
@@ -454,7 +478,10 @@ static gk_status rollout_common(const uint32_t* d_boards, int n, int rollouts_pe
     a.key_lo = uint32_t(key); a.key_hi = uint32_t(key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos_base;
     a.r_stream = d_r_stream; a.stream_stride = stream_stride;
     a.wdb = d_wdb; a.winners = d_winners; a.lengths = d_lengths;
-    GK_CUDA(gk::launch_rollout(a, g_sm_count, stream));
+    if (n == 0) return GK_OK;
+    uint32_t* images = nullptr;
+    if (gk_status s = rollout_scratch(stream, n, &images)) return s;
+    GK_CUDA(gk::launch_rollout(a, g_sm_count, images, stream));
     return GK_OK;
 }
 
@@ -487,6 +514,62 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
         return s;
     GK_CUDA(cudaMemcpyAsync(h_wdb, p.d_wdb, size_t(n) * 12, cudaMemcpyDeviceToHost, p.stream));
     GK_CUDA(cudaStreamSynchronize(p.stream));
+    return GK_OK;
+}
+
+// ---- asynchronous host entry points: several small batches in flight (root-parallel search) ----------------
+namespace {
+constexpr int kAsyncSlots = 8;
+struct AsyncSlot {
+    std::mutex mutex;
+    cudaStream_t stream = nullptr;
+    uint32_t* d_boards = nullptr; int32_t* d_wdb = nullptr; int cap = 0;
+};
+AsyncSlot g_async[kAsyncSlots];
+}  // namespace
+
+gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int rollouts_per_pos, uint64_t philox_key,
+                                 uint32_t ctr_hi, int pos_base, int32_t* h_wdb) {
+    if (gk_status s = require_device()) return s;
+    if (slot < 0 || slot >= kAsyncSlots) return fail(GK_ERR_INVALID, "slot out of range");
+    if (n < 0 || (n > 0 && (!h_boards || !h_wdb))) return fail(GK_ERR_INVALID, "bad arguments");
+    if (n == 0) return GK_OK;
+    AsyncSlot& a = g_async[slot];
+    std::lock_guard<std::mutex> lock(a.mutex);
+    if (!a.stream) GK_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    if (a.cap < n) {
+        GK_CUDA(cudaStreamSynchronize(a.stream));
+        cudaFree(a.d_boards); cudaFree(a.d_wdb);
+        a.d_boards = nullptr; a.d_wdb = nullptr; a.cap = 0;
+        const int want = std::max(n, 256);
+        GK_CUDA(cudaMalloc(&a.d_boards, size_t(want) * 64));
+        GK_CUDA(cudaMalloc(&a.d_wdb, size_t(want) * 12));
+        a.cap = want;
+    }
+    // page-locked boards (gk_host_alloc) are read by the kernel where they lie (unified addressing): one copy less
+    // on a path whose cost is launch latency; pageable boards are staged through the slot's device buffer
+    const uint32_t* boards = a.d_boards;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, h_boards) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        boards = static_cast<const uint32_t*>(attr.devicePointer);
+    else {
+        cudaGetLastError();
+        GK_CUDA(cudaMemcpyAsync(a.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, a.stream));
+    }
+    if (gk_status s = rollout_common(boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, a.d_wdb, nullptr,
+                                     nullptr, a.stream))
+        return s;
+    GK_CUDA(cudaMemcpyAsync(h_wdb, a.d_wdb, size_t(n) * 12, cudaMemcpyDeviceToHost, a.stream));
+    return GK_OK;
+}
+
+gk_status gk_rollout_wait(int slot) {
+    if (gk_status s = require_device()) return s;
+    if (slot < 0 || slot >= kAsyncSlots) return fail(GK_ERR_INVALID, "slot out of range");
+    AsyncSlot& a = g_async[slot];
+    cudaStream_t stream;
+    { std::lock_guard<std::mutex> lock(a.mutex); stream = a.stream; }
+    if (stream) GK_CUDA(cudaStreamSynchronize(stream));
     return GK_OK;
 }
 

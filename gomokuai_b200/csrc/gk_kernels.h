@@ -40,8 +40,11 @@ struct RolloutArgs {
     const uint8_t* r_stream; int stream_stride;     // non-null: injected start indices instead of Philox
     int32_t* wdb; int8_t* winners; uint8_t* lengths; // any may be null
 };
-cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stream);
-// number of kernels one launch_rollout call enqueues (wdb clear + rollout)
+// `images`: rollout_scratch_bytes(a.n) bytes of device scratch that stay untouched until the launch has finished
+// (one buffer per stream in flight)
+size_t rollout_scratch_bytes(int n);
+cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images, cudaStream_t stream);
+// number of kernels one launch_rollout call enqueues (slot images + wdb clear, rollouts)
 int rollout_launches(const RolloutArgs& a);
 
 struct EncodeArgs {

@@ -50,10 +50,12 @@ __device__ __forceinline__ bool has_five(uint32_t m) {      // five or more cons
 }
 
 // ---- position -> slot image ------------------------------------------------------------------
-// one warp per position; lane l builds slots l, l+32, l+64
-__global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, uint32_t* __restrict__ images) {
+// one warp per position; lane l builds slots l, l+32, l+64 (and clears the position's wdb counters)
+__global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, uint32_t* __restrict__ images,
+                                    int32_t* __restrict__ wdb) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
+    if (wdb && lane < 3) wdb[(size_t)warp * 3 + lane] = 0;
     const uint32_t* b = boards + (size_t)warp * kBoardWords;
     uint32_t* img = images + (size_t)warp * kImageWords;
     uint32_t any_five = 0;                                   // bit 0: black, bit 1: white
@@ -299,31 +301,18 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     flush();
 }
 
-uint32_t* g_images = nullptr;
-size_t g_images_cap = 0;
-
 }  // namespace
 
 int rollout_launches(const RolloutArgs& a) { return a.n > 0 ? 2 : 0; }
+size_t rollout_scratch_bytes(int n) { return size_t(n > 0 ? n : 0) * kImageWords * sizeof(uint32_t); }
 
-cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images, cudaStream_t stream) {
     if (a.n <= 0 || a.rollouts_per_pos <= 0) return cudaSuccess;
-    const size_t need = size_t(a.n) * kImageWords * sizeof(uint32_t);
+    if (!images) return cudaErrorInvalidValue;
     cudaError_t err;
-    if (need > g_images_cap) {                                                   // grow-only scratch owned by the library
-        if (g_images) { err = cudaFree(g_images); if (err != cudaSuccess) return err; }
-        g_images = nullptr; g_images_cap = 0;
-        err = cudaMalloc(&g_images, need);
-        if (err != cudaSuccess) return err;
-        g_images_cap = need;
-    }
-    build_images_kernel<<<(a.n * 32 + 255) / 256, 256, 0, stream>>>(a.boards, a.n, g_images);
+    build_images_kernel<<<(a.n * 32 + 255) / 256, 256, 0, stream>>>(a.boards, a.n, images, a.wdb);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    if (a.wdb) {
-        err = cudaMemsetAsync(a.wdb, 0, size_t(a.n) * 3 * sizeof(int32_t), stream);
-        if (err != cudaSuccess) return err;
-    }
     const size_t smem = size_t(kSlots + 1) * kThreads * sizeof(uint32_t);   // + one scratch slot per thread
     const unsigned long long total = (unsigned long long)a.n * a.rollouts_per_pos;
     unsigned long long blocks = (total + kTicketBlock - 1) / kTicketBlock;
@@ -334,7 +323,7 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, cudaStream_t stre
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, kThreads, smem, stream>>>(a, g_images);
+        kernel<<<grid, kThreads, smem, stream>>>(a, images);
         return cudaGetLastError();
     };
     if (a.r_stream) return launch(rollout_kernel<true, kRefillDefault>);

@@ -37,6 +37,7 @@ public:
     Player applyMove(Position move, bool checkVictory = true) {
         if (m_curPlayer != Player::None && checkMove(move)) {
             m_cells[move.id] = m_curPlayer == Player::Black ? 1 : 2;
+            m_packed[move.id >> 4] |= std::uint32_t(m_cells[move.id]) << ((move.id & 15) * 2);
             m_counts[idx(m_curPlayer)] += 1;
             m_counts[idx(Player::None)] -= 1;
             m_moveRecord.push_back(move);
@@ -53,6 +54,7 @@ public:
         }
         for (std::size_t i = 0; !m_moveRecord.empty() && i < count; ++i) {
             m_cells[m_moveRecord.back().id] = 0;
+            m_packed[m_moveRecord.back().id >> 4] &= ~(std::uint32_t(3) << ((m_moveRecord.back().id & 15) * 2));
             m_counts[idx(-m_curPlayer)] -= 1;
             m_counts[idx(Player::None)] += 1;
             m_moveRecord.pop_back();
@@ -103,6 +105,7 @@ public:
 
     void reset() {                                                                          // Game.cpp:138-146
         m_cells.fill(0);
+        m_packed.fill(0);
         m_counts = { 0, BOARD_SIZE, 0 };
         m_moveRecord.clear();
         m_curPlayer = Player::Black;
@@ -117,10 +120,9 @@ public:
     std::size_t moveCounts(Player player) const { return m_counts[idx(player)]; }            // Game.h:115-116
     std::uint8_t cell(int id) const { return m_cells[id]; }                                  // 0 empty, 1 black, 2 white
 
-    // the 64-byte image the GPU entry points take (include/gomoku_b200.h)
+    // the 64-byte image the GPU entry points take (include/gomoku_b200.h), kept up to date by applyMove / revertMove
     void pack(std::uint32_t out[16]) const {
-        for (int i = 0; i < 16; ++i) out[i] = 0;
-        for (int c = 0; c < BOARD_SIZE; ++c) out[c >> 4] |= std::uint32_t(m_cells[c]) << ((c & 15) * 2);
+        for (int i = 0; i < 16; ++i) out[i] = m_packed[i];
     }
 
     std::string toString() const {                                                          // Game.cpp:177-205
@@ -148,6 +150,7 @@ public:
 private:
     static int idx(Player p) { return static_cast<int>(p) + 1; }
     std::array<std::uint8_t, BOARD_SIZE> m_cells{};
+    std::array<std::uint32_t, 16> m_packed{};    // 2 bits per cell, cell c in word c / 16 at bits 2 (c % 16)
     std::array<std::size_t, 3> m_counts{};
 };
 

@@ -3,15 +3,21 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
 #include <thread>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "../../../include/gomoku_b200.h"
 #include "mcts.h"
@@ -27,34 +33,63 @@ namespace {
 // first selected -- in increasing cell order, kept in a sibling list -- and the untouched ones are represented by a
 // cursor.  Selection visits exactly the nodes the eager tree would (tests/test_gpu_mcts.py compares the two).
 // The root keeps a materialised block of children when Dirichlet noise makes their priors differ.
+// A node is split in two: what Default::Select reads of every child (value, prior, visits: 12 bytes) lives in three
+// parallel arrays, so the scan of the root's 200+ children streams 2.6 KB instead of 9 KB and vectorises; the links
+// stay in ANode.
 struct ANode {
     std::int32_t parent, first_child, last_child, next_sibling;
     std::int16_t n_children;        // children that exist as nodes
     std::int16_t n_moves;           // legal moves here (empty cells); > 0 once the node has been expanded
     std::int16_t position, cursor;  // the move into this node; highest cell materialised so far (-1 none)
-    float value, prior;             // running mean from the view of who moved into the node; prior of the move
-    std::int32_t visits;
     std::int8_t player;             // who played `position`
     std::int8_t eager;              // children are one contiguous block [first_child, first_child + n_children)
 };
 
 struct Tree {
     std::vector<ANode> nodes;
+    std::vector<float> value, prior;    // running mean from the view of who moved into the node; prior of the move
+    std::vector<std::int32_t> visits;
     Board board;
     std::int32_t leaf = 0;          // selected this round
     std::int16_t root_child = -1;   // root move of the current path (-1: the leaf is the root itself)
     bool terminal = false;
     std::mt19937 rng;
     std::array<std::int32_t, BOARD_SIZE> black_wins{}, white_wins{};   // rollouts below each root child
+
+    std::int32_t add(std::int32_t parent, int position, float pr, int player) {
+        ANode n{};
+        n.parent = parent; n.first_child = n.last_child = n.next_sibling = -1;
+        n.position = static_cast<std::int16_t>(position); n.cursor = -1;
+        n.player = static_cast<std::int8_t>(player);
+        nodes.push_back(n);
+        value.push_back(0.0f); prior.push_back(pr); visits.push_back(0);
+        return static_cast<std::int32_t>(nodes.size()) - 1;
+    }
+    void clear(std::size_t reserve) {
+        nodes.clear(); value.clear(); prior.clear(); visits.clear();
+        nodes.reserve(reserve); value.reserve(reserve); prior.reserve(reserve); visits.reserve(reserve);
+    }
 };
 
-// minimal fork-join pool: run(f) calls f(worker) on every worker and returns when all are done
-class Pool {
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+
+// spin, then yield: the workers of a search own their cores, but must survive being oversubscribed
+struct Backoff {
+    int spins = 0;
+    void operator()() { if (++spins < 4096) cpu_relax(); else std::this_thread::yield(); }
+};
+
+// Thread team: run(f) calls f(id) on every member and returns when all are done (one fork-join per search).
+class Team {
 public:
-    explicit Pool(int n) : n_(n) {
+    explicit Team(int n) : n_(n) {
         for (int i = 1; i < n_; ++i) threads_.emplace_back([this, i] { loop(i); });
     }
-    ~Pool() {
+    ~Team() {
         { std::lock_guard<std::mutex> l(mu_); stop_ = true; ++epoch_; }
         cv_.notify_all();
         for (auto& t : threads_) t.join();
@@ -93,21 +128,23 @@ private:
     bool stop_ = false;
 };
 
+constexpr int kMaxGroups = 4;       // leaf batches in flight (gk_rollout_submit_host slots 0..3)
+
 }  // namespace
 
 struct RootParallelSearch::Impl {
     std::vector<Tree> trees;
     std::uint32_t* packed = nullptr;        // trees x 16, page-locked (allocated on first run, when the GPU is bound)
     std::int32_t* wdb = nullptr;            // trees x 3, page-locked
-    std::unique_ptr<Pool> pool;
+    std::unique_ptr<Team> team;
     ~Impl() { gk_host_free(packed); gk_host_free(wdb); }
 };
 
 RootParallelSearch::RootParallelSearch(const RootParallelConfig& cfg) : m(new Impl), m_cfg(cfg) {
     if (cfg.trees <= 0 || cfg.c_rollouts <= 0) throw std::invalid_argument("trees and c_rollouts must be positive");
     int threads = cfg.threads > 0 ? cfg.threads : static_cast<int>(std::thread::hardware_concurrency());
-    threads = std::max(1, std::min(threads, cfg.trees));
-    m->pool.reset(new Pool(threads));
+    threads = std::max(2, std::min(threads, cfg.trees + 1));         // the calling thread drives the GPU, the others own trees
+    m->team.reset(new Team(threads));
     m->trees.resize(cfg.trees);
 }
 
@@ -121,14 +158,6 @@ Position RootParallelSearch::bestMove(const Stats& stats) {
     return most > 0 ? Position(best) : Position(-1);
 }
 
-static ANode make_node(std::int32_t parent, int position, float prior, int player) {
-    ANode n{};
-    n.parent = parent; n.first_child = n.last_child = n.next_sibling = -1;
-    n.position = static_cast<std::int16_t>(position); n.cursor = -1;
-    n.prior = prior; n.player = static_cast<std::int8_t>(player);
-    return n;
-}
-
 // expand `node` over the empty cells of `board` with uniform priors (MonteCarlo.hpp:50-55,71-80); `eager`
 // materialises the children at once (the reference's layout), otherwise they appear when first selected
 static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
@@ -140,23 +169,85 @@ static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
     const std::int32_t first = static_cast<std::int32_t>(t.nodes.size());
     const int player = -t.nodes[node].player;
     for (int c = 0; c < BOARD_SIZE; ++c)
-        if (board.cell(c) == 0) t.nodes.push_back(make_node(node, c, prior, player));
+        if (board.cell(c) == 0) t.add(node, c, prior, player);
     t.nodes[node].first_child = first;
     t.nodes[node].n_children = static_cast<std::int16_t>(empties);
     t.nodes[node].eager = 1;
 }
 
-// Default::Select (MonteCarlo.hpp:57-68) on a lazily expanded node: the best materialised child, or -- when the
-// common score of the never-visited children is strictly higher -- the lowest never-visited cell, created now.
+// PUCB score of node c under a parent with sqrt(visits) = sq: state_value + c_puct * P * sqrt(N) / (n + 1), the
+// product evaluated left to right in double like the reference (MonteCarlo.hpp:23-28,62)
+static inline double pucb(const Tree& t, std::int32_t c, double c_puct, double sq) {
+    return t.value[c] + c_puct * t.prior[c] * sq / static_cast<double>(t.visits[c] + 1);
+}
+
+// Default::Select (MonteCarlo.hpp:57-68) over a contiguous block of children: the first child with the highest score.
+// "The first child whose score is above -1 and above all before it" is the first occurrence of the maximum (every
+// score is >= -1), so the scan is a max reduction plus an equality search: no unpredictable branches, and four
+// children per step with AVX2 (same IEEE operations in the same order as the scalar form, hence the same choice).
+static int select_block_scalar(const float* v, const float* p, const std::int32_t* k, int n, double c_puct, double sq) {
+    double score[BOARD_SIZE];
+    double top = -1.0;
+    for (int i = 0; i < n; ++i) {
+        score[i] = static_cast<double>(v[i]) + c_puct * static_cast<double>(p[i]) * sq / static_cast<double>(k[i] + 1);
+        top = score[i] > top ? score[i] : top;
+    }
+    for (int i = 0; i < n; ++i)
+        if (score[i] == top) return i;
+    return 0;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static int select_block_avx2(const float* v, const float* p, const std::int32_t* k, int n,
+                                                             double c_puct, double sq) {
+    alignas(32) double score[BOARD_SIZE + 4];
+    const __m256d vc = _mm256_set1_pd(c_puct), vsq = _mm256_set1_pd(sq);
+    __m256d vtop = _mm256_set1_pd(-1.0);
+    const int n4 = n & ~3;
+    for (int i = 0; i < n4; i += 4) {
+        const __m256d val = _mm256_cvtps_pd(_mm_loadu_ps(v + i)), pr = _mm256_cvtps_pd(_mm_loadu_ps(p + i));
+        const __m256d cnt = _mm256_cvtepi32_pd(_mm_add_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i*>(k + i)), _mm_set1_epi32(1)));
+        const __m256d sc = _mm256_add_pd(val, _mm256_div_pd(_mm256_mul_pd(_mm256_mul_pd(vc, pr), vsq), cnt));
+        _mm256_store_pd(score + i, sc);
+        vtop = _mm256_max_pd(vtop, sc);
+    }
+    alignas(32) double lanes[4];
+    _mm256_store_pd(lanes, vtop);
+    double top = lanes[0];
+    for (int j = 1; j < 4; ++j) top = lanes[j] > top ? lanes[j] : top;
+    for (int i = n4; i < n; ++i) {
+        score[i] = static_cast<double>(v[i]) + c_puct * static_cast<double>(p[i]) * sq / static_cast<double>(k[i] + 1);
+        top = score[i] > top ? score[i] : top;
+    }
+    const __m256d vt = _mm256_set1_pd(top);
+    for (int i = 0; i < n4; i += 4) {
+        const int hit = _mm256_movemask_pd(_mm256_cmp_pd(_mm256_load_pd(score + i), vt, _CMP_EQ_OQ));
+        if (hit) return i + __builtin_ctz(static_cast<unsigned>(hit));
+    }
+    for (int i = n4; i < n; ++i)
+        if (score[i] == top) return i;
+    return 0;
+}
+#endif
+
+static std::int32_t select_block(const Tree& t, std::int32_t first, int n, double c_puct, double sq) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return first + select_block_avx2(&t.value[first], &t.prior[first], &t.visits[first], n, c_puct, sq);
+#endif
+    return first + select_block_scalar(&t.value[first], &t.prior[first], &t.visits[first], n, c_puct, sq);
+}
+
+// Default::Select on a lazily expanded node: the best materialised child, or -- when the common score of the
+// never-visited children is strictly higher -- the lowest never-visited cell, created now.
 static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
     const ANode parent = t.nodes[node];
-    const double sq = std::sqrt(static_cast<double>(parent.visits));
+    const double sq = std::sqrt(static_cast<double>(t.visits[node]));
     const float prior = 1.0f / static_cast<float>(parent.n_moves);
     std::int32_t best = parent.first_child;                          // as the reference: the first child unless one scores above -1
     double best_score = -1.0;
     for (std::int32_t c = parent.first_child; c >= 0; c = t.nodes[c].next_sibling) {   // increasing cell order
-        const ANode& ch = t.nodes[c];
-        const double score = ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);
+        const double score = pucb(t, c, c_puct, sq);
         if (score > best_score) { best_score = score; best = c; }
     }
     if (parent.n_children < parent.n_moves) {                       // someone has never been visited: value 0, visits 0
@@ -164,8 +255,7 @@ static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
         if (best < 0 || fresh > best_score) {
             int cell = parent.cursor + 1;
             while (t.board.cell(cell) != 0) ++cell;                 // the lowest empty cell above the cursor
-            const std::int32_t created = static_cast<std::int32_t>(t.nodes.size());
-            t.nodes.push_back(make_node(node, cell, prior, -parent.player));
+            const std::int32_t created = t.add(node, cell, prior, -parent.player);
             ANode& p = t.nodes[node];
             if (p.last_child >= 0) t.nodes[p.last_child].next_sibling = created; else p.first_child = created;
             p.last_child = created;
@@ -177,6 +267,49 @@ static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
     return best;
 }
 
+// One playout's descent (MCTS::playout, MCTS.cpp:158-166): walk to a leaf, leave the board there, pack it.
+static void select_leaf(Tree& t, double c_puct, std::uint32_t* packed) {
+    std::int32_t node = 0;
+    t.root_child = -1;
+    while (t.nodes[node].n_moves > 0) {                              // expanded: descend
+        const ANode& parent = t.nodes[node];
+        node = parent.eager ? select_block(t, parent.first_child, parent.n_children, c_puct, std::sqrt(static_cast<double>(t.visits[node])))
+                            : select_lazy(t, node, c_puct);
+        if (t.root_child < 0) t.root_child = t.nodes[node].position;
+        t.board.applyMove(Position(t.nodes[node].position), false);
+    }
+    t.leaf = node;
+    t.terminal = t.board.checkGameEnd();                             // MCTS.cpp:166
+    t.board.pack(packed);
+}
+
+// Expansion of the leaf + back-propagation of its simulated value (MCTS.cpp:167-176, MonteCarlo.hpp:90-95).
+static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg, std::size_t root_depth) {
+    const float black_value = static_cast<float>(r[2] - r[0]) / static_cast<float>(cfg.c_rollouts);
+    if (!t.terminal) {
+        expand(t, t.leaf, t.board, cfg.eager || (t.leaf == 0 && cfg.noise));
+        if (t.leaf == 0 && cfg.noise) {                              // Default::AddNoise on the root's fresh children
+            const ANode& rt = t.nodes[0];
+            std::gamma_distribution<float> gamma(0.05f, 1.0f);
+            std::vector<float> g(rt.n_children);
+            double n2 = 0;
+            for (float& x : g) { x = gamma(t.rng); n2 += double(x) * x; }
+            const float inv = n2 > 0 ? static_cast<float>(1.0 / std::sqrt(n2)) : 0.0f;
+            for (int k = 0; k < rt.n_children; ++k) {
+                float& pr = t.prior[rt.first_child + k];
+                pr = pr * 0.75f + 0.25f * g[k] * inv;
+            }
+        }
+    }
+    if (t.root_child >= 0) { t.black_wins[t.root_child] += r[2]; t.white_wins[t.root_child] += r[0]; }
+    float v = static_cast<float>(t.nodes[t.leaf].player) * black_value;   // value for who moved into the leaf
+    for (std::int32_t n = t.leaf; n >= 0; n = t.nodes[n].parent, v = -v) {
+        t.visits[n] += 1;
+        t.value[n] += (v - t.value[n]) / static_cast<float>(t.visits[n]);
+    }
+    t.board.revertMove(t.board.m_moveRecord.size() - root_depth);
+}
+
 void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     const auto t_start = std::chrono::steady_clock::now();
     m_stats.fill(0);
@@ -186,9 +319,9 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     const Player root_last = root.m_moveRecord.empty() ? Player::White : -root.m_curPlayer;   // MCTS.h:138-151
     for (int i = 0; i < n_trees; ++i) {
         Tree& t = m->trees[i];
-        t.nodes.clear();
-        t.nodes.reserve(m_cfg.eager ? static_cast<std::size_t>(playouts_per_tree) * 64 + 256 : static_cast<std::size_t>(playouts_per_tree) * 2 + 256);
-        t.nodes.push_back(make_node(-1, -1, 1.0f, static_cast<int>(root_last)));
+        t.clear(m_cfg.eager ? static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 64 + 256
+                            : static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 2 + 256);
+        t.add(-1, -1, 1.0f, static_cast<int>(root_last));
         t.board = root;
         t.black_wins.fill(0);
         t.white_wins.fill(0);
@@ -206,86 +339,85 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     if (probe.checkGameEnd() || playouts_per_tree <= 0) { seconds_total = 0; return; }   // nothing to search from a decided position
     const double c_puct = m_cfg.c_puct;
     const std::size_t root_depth = root.m_moveRecord.size();
-    const int workers = m->pool->size();
+    const int workers = m->team->size() - 1;                        // thread 0 of the team drives the GPU
 
-    for (int round = 0; round < playouts_per_tree; ++round) {
-        // ---- selection: every tree walks to a leaf and packs its position -----------------------------
-        m->pool->run([&](int w) {
-            for (int i = w; i < n_trees; i += workers) {
-                Tree& t = m->trees[i];
-                std::int32_t node = 0;
-                t.root_child = -1;
-                while (t.nodes[node].n_moves > 0) {                  // expanded: descend
-                    if (!t.nodes[node].eager) {
-                        node = select_lazy(t, node, c_puct);
-                    } else {
-                        const ANode& parent = t.nodes[node];
-                        const double sq = std::sqrt(static_cast<double>(parent.visits));
-                        std::int32_t best = parent.first_child;
-                        double best_score = -1.0;
-                        for (std::int32_t c = parent.first_child, e = c + parent.n_children; c < e; ++c) {
-                            const ANode& ch = t.nodes[c];
-                            const double score = ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);   // PUCB, :23-28,57-68
-                            if (score > best_score) { best_score = score; best = c; }
-                        }
-                        node = best;
-                    }
-                    if (t.root_child < 0) t.root_child = t.nodes[node].position;
-                    t.board.applyMove(Position(t.nodes[node].position), false);
-                }
-                t.leaf = node;
-                t.terminal = t.board.checkGameEnd();                  // MCTS.cpp:166
-                t.board.pack(&m->packed[static_cast<std::size_t>(i) * 16]);
+    // The trees are cut into G groups whose leaf batches are in flight at the same time: while the GPU simulates the
+    // leaves of one group, the workers back up and descend the trees of the others.  "Visit" v handles round v / G of
+    // group v % G: back up the group's previous batch, select the next leaves.  The calling thread is the DRIVER: it
+    // never touches a tree; it waits for batches (publishing `ready`) and submits a visit's leaves once every worker
+    // has reported them packed (`done`), so CUDA call latency stays off the workers' critical path.  A tree's Philox
+    // stream is (round, global tree index), whatever G and the thread count are.
+    const int groups = std::max(1, std::min(kMaxGroups, n_trees / 64));
+    std::array<int, kMaxGroups + 1> gs{};
+    for (int g = 0; g <= groups; ++g) gs[g] = static_cast<int>(static_cast<long long>(n_trees) * g / groups);
+    const long long visits_total = static_cast<long long>(playouts_per_tree + 1) * groups;
+    constexpr int kRing = 2 * kMaxGroups;
+    std::atomic<long long> ready{ -1 };          // results of every visit <= ready have arrived
+    std::array<std::atomic<int>, kRing> done{};  // workers that finished selecting for visit v, at v % kRing
+    for (auto& d : done) d.store(0);
+    std::atomic<bool> failed{ false };
+    std::string error;
+    double idle = 0;                             // worker 1's time waiting for results
+
+    auto driver = [&]() {
+        auto arrive = [&](long long v) {                             // results of visit v's previous batch
+            if (v >= visits_total || v / groups == 0 || failed.load()) return;
+            if (gk_rollout_wait(static_cast<int>(v % groups)) != GK_OK) { error = std::string("gk_rollout_wait: ") + gk_last_error(); failed.store(true); }
+            ready.store(v, std::memory_order_release);
+        };
+        auto submit = [&](long long u) {                             // leaves selected at visit u
+            if (u < 0 || u / groups >= playouts_per_tree || failed.load()) return;
+            Backoff wait;
+            while (done[u % kRing].load(std::memory_order_acquire) != workers && !failed.load(std::memory_order_relaxed)) wait();
+            done[u % kRing].store(0, std::memory_order_relaxed);
+            const int g = static_cast<int>(u % groups), lo = gs[g], hi = gs[g + 1];
+            if (!failed.load() &&
+                gk_rollout_submit_host(g, m->packed + static_cast<std::size_t>(lo) * 16, hi - lo, m_cfg.c_rollouts, m_cfg.seed,
+                                       static_cast<std::uint32_t>(u / groups), m_cfg.replica_base + lo,
+                                       m->wdb + static_cast<std::size_t>(lo) * 3) != GK_OK) {
+                error = std::string("gk_rollout_submit_host: ") + gk_last_error();
+                failed.store(true);
             }
-        });
-        // ---- simulation: all leaves in one launch ------------------------------------------------------------
-        const auto g0 = std::chrono::steady_clock::now();
-        if (gk_rollout_batch_host(m->packed, n_trees, m_cfg.c_rollouts, m_cfg.seed, static_cast<std::uint32_t>(round),
-                                  m_cfg.replica_base, m->wdb) != GK_OK)
-            throw std::runtime_error(std::string("gk_rollout_batch_host: ") + gk_last_error());
-        seconds_gpu += std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
-        leaves += n_trees;
-        // ---- expansion + backup -----------------------------------------------------------------------------------
-        m->pool->run([&](int w) {
-            for (int i = w; i < n_trees; i += workers) {
-                Tree& t = m->trees[i];
-                const std::int32_t* r = &m->wdb[static_cast<std::size_t>(i) * 3];
-                const float black_value = static_cast<float>(r[2] - r[0]) / static_cast<float>(m_cfg.c_rollouts);
-                if (!t.terminal) {
-                    expand(t, t.leaf, t.board, m_cfg.eager || (t.leaf == 0 && m_cfg.noise));
-                    if (t.leaf == 0 && m_cfg.noise) {                // Default::AddNoise on the root's fresh children
-                        ANode& rt = t.nodes[0];
-                        std::gamma_distribution<float> gamma(0.05f, 1.0f);
-                        std::vector<float> g(rt.n_children);
-                        double n2 = 0;
-                        for (float& x : g) { x = gamma(t.rng); n2 += double(x) * x; }
-                        const float inv = n2 > 0 ? static_cast<float>(1.0 / std::sqrt(n2)) : 0.0f;
-                        for (int k = 0; k < rt.n_children; ++k) {
-                            ANode& ch = t.nodes[rt.first_child + k];
-                            ch.prior = ch.prior * 0.75f + 0.25f * g[k] * inv;
-                        }
-                    }
-                }
-                if (t.root_child >= 0) { t.black_wins[t.root_child] += r[2]; t.white_wins[t.root_child] += r[0]; }
-                float v = static_cast<float>(t.nodes[t.leaf].player) * black_value;   // value for who moved into the leaf
-                for (std::int32_t n = t.leaf; n >= 0; n = t.nodes[n].parent, v = -v) {
-                    ANode& nd = t.nodes[n];
-                    nd.visits += 1;
-                    nd.value += (v - nd.value) / static_cast<float>(nd.visits);       // MonteCarlo.hpp:90-95
-                }
-                t.board.revertMove(t.board.m_moveRecord.size() - root_depth);
+        };
+        for (long long v = 0; v <= visits_total; ++v) {
+            // with two or more groups the batch visit v waits for was submitted at least one iteration ago, so its
+            // arrival is published BEFORE the (slower) submit of visit v - 1
+            if (groups >= 2) { arrive(v); submit(v - 1); } else { submit(v - 1); arrive(v); }
+        }
+    };
+    auto worker = [&](int w) {                                       // w in [0, workers)
+        for (long long v = 0; v < visits_total && !failed.load(std::memory_order_relaxed); ++v) {
+            const int g = static_cast<int>(v % groups), round = static_cast<int>(v / groups);
+            if (round > 0 && ready.load(std::memory_order_acquire) < v) {
+                const auto t0 = std::chrono::steady_clock::now();
+                Backoff wait;
+                while (ready.load(std::memory_order_acquire) < v && !failed.load(std::memory_order_relaxed)) wait();
+                if (w == 0) idle += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             }
-        });
+            for (int i = gs[g] + w; i < gs[g + 1]; i += workers) {
+                Tree& t = m->trees[i];
+                if (round > 0) backup(t, &m->wdb[static_cast<std::size_t>(i) * 3], m_cfg, root_depth);
+                if (round < playouts_per_tree) select_leaf(t, c_puct, &m->packed[static_cast<std::size_t>(i) * 16]);
+            }
+            if (round < playouts_per_tree) done[v % kRing].fetch_add(1, std::memory_order_acq_rel);
+        }
+    };
+    m->team->run([&](int id) { if (id == 0) driver(); else worker(id - 1); });
+    if (failed.load()) {
+        for (int g = 0; g < groups; ++g) gk_rollout_wait(g);
+        throw std::runtime_error(error);
     }
+    seconds_gpu = idle;
+    leaves = static_cast<std::int64_t>(n_trees) * playouts_per_tree;
     // ---- root statistics: integers, summed over trees ---------------------------------------------------------------
     nodes = 0;
     for (Tree& t : m->trees) {
         nodes += static_cast<std::int64_t>(t.nodes.size());
         const ANode& rt = t.nodes[0];
         if (rt.eager) {
-            for (std::int32_t c = rt.first_child, e = c + rt.n_children; c < e; ++c) m_stats[t.nodes[c].position] += t.nodes[c].visits;
+            for (std::int32_t c = rt.first_child, e = c + rt.n_children; c < e; ++c) m_stats[t.nodes[c].position] += t.visits[c];
         } else {
-            for (std::int32_t c = rt.first_child; c >= 0; c = t.nodes[c].next_sibling) m_stats[t.nodes[c].position] += t.nodes[c].visits;
+            for (std::int32_t c = rt.first_child; c >= 0; c = t.nodes[c].next_sibling) m_stats[t.nodes[c].position] += t.visits[c];
         }
         for (int c = 0; c < BOARD_SIZE; ++c) {
             m_stats[BOARD_SIZE + c] += t.black_wins[c];

@@ -21,7 +21,7 @@ struct RootParallelConfig {
     double c_puct = 5.0;
     std::uint64_t seed = 1;     // Philox key
     int replica_base = 0;       // first global tree index of this rank (keeps streams disjoint across ranks)
-    int threads = 0;            // host threads for tree work (0 = hardware concurrency)
+    int threads = 0;            // host threads: one drives the GPU, the rest do tree work (0 = hardware concurrency; at least 2)
     bool noise = true;          // Dirichlet noise on root priors (Default::AddNoise, MonteCarlo.hpp:97-108)
     bool eager = false;         // materialise every child at expansion like the reference (slow; kept to test the lazy tree against)
 };
@@ -39,7 +39,7 @@ public:
     const Stats& stats() const { return m_stats; }
     static Position bestMove(const Stats& stats);             // most visited root child, ties -> lowest cell (MCTS.cpp:129-134)
 
-    double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / inside gk_rollout_batch_host
+    double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / of it, time the first worker waited for GPU results
     std::int64_t leaves = 0, nodes = 0;
 
 private:

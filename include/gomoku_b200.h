@@ -164,6 +164,15 @@ gk_status gk_rollout_batch(const uint32_t* d_boards, int n, int rollouts_per_pos
                            int32_t* d_wdb, int8_t* d_winners, uint8_t* d_lengths, void* stream);
 gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_per_pos,
                                 uint64_t philox_key, uint32_t ctr_hi, int pos_base, int32_t* h_wdb);
+/* Asynchronous form of gk_rollout_batch_host for callers that keep several small batches in flight (the
+ * root-parallel search: while one group of leaves is simulated, the host descends the trees of the next one).
+ * `slot` in [0, 8) names an independent stream with its own device buffers.  submit enqueues copy-in, rollouts and
+ * copy-out and returns; h_boards and h_wdb must stay valid and untouched until gk_rollout_wait(slot) has returned.
+ * Page-locked buffers (gk_host_alloc) make the call truly asynchronous and let the kernel read the boards in place.
+ * One thread at a time per slot. */
+gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int rollouts_per_pos,
+                                 uint64_t philox_key, uint32_t ctr_hi, int pos_base, int32_t* h_wdb);
+gk_status gk_rollout_wait(int slot);
 /* Same loop, but move k of rollout j of position i takes r = d_r_stream[(i*rollouts_per_pos + j)
  * * stream_stride + k] (values 0..224) -- the injected-stream protocol used to compare bit-exactly
  * with the reference's Board on any external stream (e.g. its own mt19937 draws).  A rollout
