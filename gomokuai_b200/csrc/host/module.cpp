@@ -187,12 +187,14 @@ PYBIND11_MODULE(CorePyExt, mod) {
                  return new RootParallelSearch(cfg);
              }), "trees"_a = 256, "c_rollouts"_a = 5, "c_puct"_a = C_PUCT, "seed"_a = 1, "replica_base"_a = 0, "threads"_a = 0, "noise"_a = true,
              "eager"_a = false)
-        .def("run", [](RootParallelSearch& s, const Board& b, int playouts_per_tree) {
-            { py::gil_scoped_release release; s.run(b, playouts_per_tree); }
+        .def("run", [](RootParallelSearch& s, const Board& b, int playouts_per_tree, py::object seed) {
+            const bool reseed = !seed.is_none();
+            const std::uint64_t key = reseed ? seed.cast<std::uint64_t>() : 0;
+            { py::gil_scoped_release release; if (reseed) s.run(b, playouts_per_tree, key); else s.run(b, playouts_per_tree); }
             py::array_t<std::int64_t> a({ 3, int(BOARD_SIZE) });
             std::copy(s.stats().begin(), s.stats().end(), a.mutable_data());
             return a;
-        }, "board"_a, "playouts_per_tree"_a, "Returns int64[3,225]: visits, black-won rollouts, white-won rollouts per root move.")
+        }, "board"_a, "playouts_per_tree"_a, "seed"_a = py::none(), "Returns int64[3,225]: visits, black-won rollouts, white-won rollouts per root move.")
         .def_static("best_move", [](py::array_t<std::int64_t, py::array::c_style | py::array::forcecast> a) {
             if (a.size() != 3 * BOARD_SIZE) throw std::invalid_argument("stats must be int64[3,225]");
             RootParallelSearch::Stats st;
@@ -201,6 +203,7 @@ PYBIND11_MODULE(CorePyExt, mod) {
         })
         .def_readonly("seconds_total", &RootParallelSearch::seconds_total)
         .def_readonly("seconds_gpu", &RootParallelSearch::seconds_gpu)
+        .def_property_readonly("driver_seconds", [](const RootParallelSearch& s) { return py::make_tuple(s.driver_seconds[0], s.driver_seconds[1], s.driver_seconds[2]); })
         .def_readonly("leaves", &RootParallelSearch::leaves)
         .def_readonly("nodes", &RootParallelSearch::nodes);
 }

@@ -310,6 +310,11 @@ static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg
     t.board.revertMove(t.board.m_moveRecord.size() - root_depth);
 }
 
+void RootParallelSearch::run(const Board& root, int playouts_per_tree, std::uint64_t seed) {
+    m_cfg.seed = seed;
+    run(root, playouts_per_tree);
+}
+
 void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     const auto t_start = std::chrono::steady_clock::now();
     m_stats.fill(0);
@@ -317,15 +322,21 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     leaves = 0;
     const int n_trees = m_cfg.trees;
     const Player root_last = root.m_moveRecord.empty() ? Player::White : -root.m_curPlayer;   // MCTS.h:138-151
-    for (int i = 0; i < n_trees; ++i) {
-        Tree& t = m->trees[i];
-        t.clear(m_cfg.eager ? static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 64 + 256
-                            : static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 2 + 256);
-        t.add(-1, -1, 1.0f, static_cast<int>(root_last));
-        t.board = root;
-        t.black_wins.fill(0);
-        t.white_wins.fill(0);
-        t.rng.seed(static_cast<std::uint32_t>(m_cfg.seed * 2654435761u + static_cast<std::uint32_t>(m_cfg.replica_base + i)));
+    const std::size_t reserve = m_cfg.eager ? static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 64 + 256
+                                            : static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 2 + 256;
+    {
+        std::atomic<int> next{ 0 };                                  // fresh trees, set up by the whole team (first-touch allocation)
+        m->team->run([&](int) {
+            for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < n_trees;) {
+                Tree& t = m->trees[i];
+                t.clear(reserve);
+                t.add(-1, -1, 1.0f, static_cast<int>(root_last));
+                t.board = root;
+                t.black_wins.fill(0);
+                t.white_wins.fill(0);
+                t.rng.seed(static_cast<std::uint32_t>(m_cfg.seed * 2654435761u + static_cast<std::uint32_t>(m_cfg.replica_base + i)));
+            }
+        });
     }
     ensure_gpu();
     if (!m->packed) {
@@ -339,7 +350,6 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     if (probe.checkGameEnd() || playouts_per_tree <= 0) { seconds_total = 0; return; }   // nothing to search from a decided position
     const double c_puct = m_cfg.c_puct;
     const std::size_t root_depth = root.m_moveRecord.size();
-    const int workers = m->team->size() - 1;                        // thread 0 of the team drives the GPU
 
     // The trees are cut into G groups whose leaf batches are in flight at the same time: while the GPU simulates the
     // leaves of one group, the workers back up and descend the trees of the others.  "Visit" v handles round v / G of
@@ -351,26 +361,35 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     std::array<int, kMaxGroups + 1> gs{};
     for (int g = 0; g <= groups; ++g) gs[g] = static_cast<int>(static_cast<long long>(n_trees) * g / groups);
     const long long visits_total = static_cast<long long>(playouts_per_tree + 1) * groups;
-    constexpr int kRing = 2 * kMaxGroups;
+    // Trees are handed out in chunks from a per-group counter, so a worker that loses its core for a time slice
+    // delays one chunk, not the whole group.  Both counters only grow: round r of a group owns the chunk numbers
+    // [r * chunks, (r + 1) * chunks), so a worker that arrives late can never claim work of a finished round.
+    constexpr int kChunk = 8;
     std::atomic<long long> ready{ -1 };          // results of every visit <= ready have arrived
-    std::array<std::atomic<int>, kRing> done{};  // workers that finished selecting for visit v, at v % kRing
-    for (auto& d : done) d.store(0);
+    std::array<std::atomic<long long>, kMaxGroups> claimed{}, done{};   // chunks handed out / trees finished, per group, over all rounds
+    for (int g = 0; g < kMaxGroups; ++g) { claimed[g].store(0); done[g].store(0); }
     std::atomic<bool> failed{ false };
     std::string error;
     double idle = 0;                             // worker 1's time waiting for results
+    double t_sync = 0, t_workers = 0, t_submit = 0;   // the driver's time in gk_rollout_wait / waiting for the workers / in gk_rollout_submit_host
 
     auto driver = [&]() {
         auto arrive = [&](long long v) {                             // results of visit v's previous batch
             if (v >= visits_total || v / groups == 0 || failed.load()) return;
+            const auto t0 = std::chrono::steady_clock::now();
             if (gk_rollout_wait(static_cast<int>(v % groups)) != GK_OK) { error = std::string("gk_rollout_wait: ") + gk_last_error(); failed.store(true); }
             ready.store(v, std::memory_order_release);
+            t_sync += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         };
         auto submit = [&](long long u) {                             // leaves selected at visit u
             if (u < 0 || u / groups >= playouts_per_tree || failed.load()) return;
+            const auto t0 = std::chrono::steady_clock::now();
             Backoff wait;
-            while (done[u % kRing].load(std::memory_order_acquire) != workers && !failed.load(std::memory_order_relaxed)) wait();
-            done[u % kRing].store(0, std::memory_order_relaxed);
             const int g = static_cast<int>(u % groups), lo = gs[g], hi = gs[g + 1];
+            const long long want = (u / groups + 1) * static_cast<long long>(hi - lo);
+            while (done[g].load(std::memory_order_acquire) != want && !failed.load(std::memory_order_relaxed)) wait();
+            const auto t1 = std::chrono::steady_clock::now();
+            t_workers += std::chrono::duration<double>(t1 - t0).count();
             if (!failed.load() &&
                 gk_rollout_submit_host(g, m->packed + static_cast<std::size_t>(lo) * 16, hi - lo, m_cfg.c_rollouts, m_cfg.seed,
                                        static_cast<std::uint32_t>(u / groups), m_cfg.replica_base + lo,
@@ -378,6 +397,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
                 error = std::string("gk_rollout_submit_host: ") + gk_last_error();
                 failed.store(true);
             }
+            t_submit += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
         };
         for (long long v = 0; v <= visits_total; ++v) {
             // with two or more groups the batch visit v waits for was submitted at least one iteration ago, so its
@@ -394,12 +414,20 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
                 while (ready.load(std::memory_order_acquire) < v && !failed.load(std::memory_order_relaxed)) wait();
                 if (w == 0) idle += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             }
-            for (int i = gs[g] + w; i < gs[g + 1]; i += workers) {
-                Tree& t = m->trees[i];
-                if (round > 0) backup(t, &m->wdb[static_cast<std::size_t>(i) * 3], m_cfg, root_depth);
-                if (round < playouts_per_tree) select_leaf(t, c_puct, &m->packed[static_cast<std::size_t>(i) * 16]);
+            const int count = gs[g + 1] - gs[g], chunks = (count + kChunk - 1) / kChunk;
+            const long long first = static_cast<long long>(round) * chunks, last = first + chunks;
+            for (;;) {
+                long long c = claimed[g].load(std::memory_order_relaxed);
+                if (c >= last) break;
+                if (!claimed[g].compare_exchange_weak(c, c + 1, std::memory_order_acq_rel)) continue;
+                const int lo = gs[g] + static_cast<int>(c - first) * kChunk, hi = std::min(lo + kChunk, gs[g + 1]);
+                for (int i = lo; i < hi; ++i) {
+                    Tree& t = m->trees[i];
+                    if (round > 0) backup(t, &m->wdb[static_cast<std::size_t>(i) * 3], m_cfg, root_depth);
+                    if (round < playouts_per_tree) select_leaf(t, c_puct, &m->packed[static_cast<std::size_t>(i) * 16]);
+                }
+                done[g].fetch_add(hi - lo, std::memory_order_acq_rel);
             }
-            if (round < playouts_per_tree) done[v % kRing].fetch_add(1, std::memory_order_acq_rel);
         }
     };
     m->team->run([&](int id) { if (id == 0) driver(); else worker(id - 1); });
@@ -408,6 +436,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         throw std::runtime_error(error);
     }
     seconds_gpu = idle;
+    driver_seconds = { t_sync, t_workers, t_submit };
     leaves = static_cast<std::int64_t>(n_trees) * playouts_per_tree;
     // ---- root statistics: integers, summed over trees ---------------------------------------------------------------
     nodes = 0;

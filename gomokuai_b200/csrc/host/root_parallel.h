@@ -35,11 +35,13 @@ public:
 
     // fresh trees from `root`, `playouts_per_tree` playouts on each; fills stats()
     void run(const Board& root, int playouts_per_tree);
+    void run(const Board& root, int playouts_per_tree, std::uint64_t seed);   // same, with a new Philox key / noise seed (the object and its arenas are reused)
 
     const Stats& stats() const { return m_stats; }
     static Position bestMove(const Stats& stats);             // most visited root child, ties -> lowest cell (MCTS.cpp:129-134)
 
     double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / of it, time the first worker waited for GPU results
+    std::array<double, 3> driver_seconds{};                   // the GPU driver thread: in gk_rollout_wait, waiting for the workers, in gk_rollout_submit_host
     std::int64_t leaves = 0, nodes = 0;
 
 private:

@@ -53,14 +53,22 @@ def best_move(stats):
     return int(np.argmax(visits)) if visits.max() > 0 else -1
 
 
+_searchers = {}
+
+
 def search(board, playouts_total, trees_per_rank=256, c_rollouts=5, c_puct=5.0, seed=1, noise=True, threads=0, group=None):
-    """One move of root-parallel search. Returns (best cell, merged stats int64[3,225], local RootParallelSearch)."""
+    """One move of root-parallel search. Returns (best cell, merged stats int64[3,225], local RootParallelSearch).
+    The searcher (worker threads, tree arenas, page-locked buffers) is kept between moves."""
     import torch.distributed as dist
     from .core import RootParallelSearch
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if (dist.is_available() and dist.is_initialized()) else (0, 1)
     per_tree = max(1, math.ceil(playouts_total / (world * trees_per_rank)))
-    s = RootParallelSearch(trees=trees_per_rank, c_rollouts=c_rollouts, c_puct=c_puct, seed=seed,
-                           replica_base=rank * trees_per_rank, threads=threads, noise=noise)
-    local = s.run(board, per_tree)
+    key = (trees_per_rank, c_rollouts, c_puct, rank * trees_per_rank, threads, noise)
+    s = _searchers.get(key)
+    if s is None:
+        _searchers.clear()
+        s = _searchers[key] = RootParallelSearch(trees=trees_per_rank, c_rollouts=c_rollouts, c_puct=c_puct, seed=seed,
+                                                 replica_base=rank * trees_per_rank, threads=threads, noise=noise)
+    local = s.run(board, per_tree, seed)
     merged = allreduce_root_stats(local, group)
     return best_move(merged), merged, s

@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--playouts", type=int, default=1_000_000)
-ap.add_argument("--trees", type=int, default=2048, help="trees per GPU")
+ap.add_argument("--trees", type=int, default=4096, help="trees per GPU")
 ap.add_argument("--rollouts", type=int, default=5)
 ap.add_argument("--moves", type=int, default=3)
 ap.add_argument("--threads", type=int, default=0)
@@ -42,7 +42,8 @@ for mv in range(args.moves):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     played = int(stats[0].sum()) + world * args.trees
     rows.append({"move": int(move), "seconds": float(t.item()), "playouts": played, "playouts_per_s": played / float(t.item()),
-                 "gpu_fraction": s.seconds_gpu / max(s.seconds_total, 1e-9), "nodes_rank0": int(s.nodes)})
+                 "gpu_fraction": s.seconds_gpu / max(s.seconds_total, 1e-9), "nodes_rank0": int(s.nodes),
+                 "search_seconds": s.seconds_total, "driver_seconds": [round(x, 4) for x in s.driver_seconds]})
     b.apply_move(move)
 if rank == 0:
     best = max(rows, key=lambda r: r["playouts_per_s"])
