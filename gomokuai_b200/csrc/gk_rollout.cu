@@ -149,37 +149,40 @@ __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */,
     w |= 1u << (x + sh);
     my[y * kThreads] = w;
     if (((w | (w >> 16)) & 0x7fffu) == 0x7fffu) L.rowmask &= ~(1u << y);
-    uint32_t fives = five_bits(w);
     // column
+    uint32_t vc;
     {
         uint32_t* p = my + (15u + x) * kThreads;
-        const uint32_t v = *p | (1u << (y + sh));
-        *p = v;
-        fives |= five_bits(v);
+        vc = *p | (1u << (y + sh));
+        *p = vc;
     }
     // diagonal (+1,+1): x - y = k, k in [-10, 10]; cells on shorter diagonals use the scratch slot, where
     // the same bit is set over and over and can never form a run
+    uint32_t vd;
     {
         const uint32_t k = x - y + 10u;
         const bool ok = k <= 20u;
         uint32_t* p = my + (ok ? 30u + k : uint32_t(kSlots)) * kThreads;
-        const uint32_t v = *p | (1u << ((ok ? min(x, y) : 0u) + sh));
-        *p = v;
-        fives |= five_bits(v);
+        vd = *p | (1u << ((ok ? min(x, y) : 0u) + sh));
+        *p = vd;
     }
     // anti-diagonal (-1,+1): x + y = s, s in [4, 24]
+    uint32_t va;
     {
         const uint32_t s = x + y - 4u;
         const bool ok = s <= 20u;
         uint32_t* p = my + (ok ? 51u + s : uint32_t(kSlots)) * kThreads;
-        const uint32_t v = *p | (1u << ((ok ? min(14u - x, y) : 0u) + sh));
-        *p = v;
-        fives |= five_bits(v);
+        va = *p | (1u << ((ok ? min(14u - x, y) : 0u) + sh));
+        *p = va;
     }
+    // win test on the mover's halves only, two lines per register: one PRMT packs the 16-bit halves of two slots
+    // (bit 15 of a half is never set, so a run cannot cross from one line into the other)
+    const uint32_t sel = L.colour ? 0x7632u : 0x5410u;
+    const uint32_t fives = five_bits(__byte_perm(w, vc, sel)) | five_bits(__byte_perm(vd, va, sel));
     L.moves += 1;
     L.empties -= 1;
     uint32_t result = 0;
-    if (fives & (0x7fffu << sh)) result = 1u + L.colour;                         // winner = player of the last stone, Game.cpp:125-128
+    if (fives) result = 1u + L.colour;                                           // winner = player of the last stone, Game.cpp:125-128
     else if (L.empties == 0) result = 3u;                                        // Game.cpp:129-132
     L.colour ^= 1u;
     return result;
@@ -260,8 +263,13 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
                         active = true;
                         finish(wc ? wc : 3u);
                     } else {
-#pragma unroll 8
-                        for (int s = 0; s < kSlots; ++s) my[s * kThreads] = __ldg(img + s);
+                        const uint4* img4 = reinterpret_cast<const uint4*>(img);    // 320-byte images: 16-byte aligned
+#pragma unroll 6
+                        for (int s = 0; s < kSlots / 4; ++s) {
+                            const uint4 q = __ldg(img4 + s);
+                            my[(4 * s + 0) * kThreads] = q.x; my[(4 * s + 1) * kThreads] = q.y;
+                            my[(4 * s + 2) * kThreads] = q.z; my[(4 * s + 3) * kThreads] = q.w;
+                        }
                         active = true;
                         if (kInjected) inj = a.r_stream + size_t(g) * a.stream_stride;
                     }
