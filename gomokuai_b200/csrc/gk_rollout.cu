@@ -117,38 +117,55 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 struct Lane {
     uint32_t rowmask;      // rows with at least one empty cell
-    uint32_t empties;
+    uint32_t left;         // empty cells left
     uint32_t colour;       // 0 black to move, 1 white
-    uint32_t moves;        // moves played in this rollout
+    uint32_t start;        // empty cells when the rollout started: moves played = start - left
     uint32_t pos, roll;    // position index (batch-local), rollout index within the position
 };
 
 // raw five-in-a-row detector on a whole slot word: bit i of the result is set iff bits i..i+4 are.
-// Bit 15 of a slot is always 0, so runs never leak between the black half and the white half.
+// Bit 15 of a 16-bit half is never set, so runs never leak from one half into the other.
 __device__ __forceinline__ uint32_t five_bits(uint32_t v) {
     uint32_t t = v & (v >> 1);
     t &= t >> 2;
     return t & (v >> 4);
 }
 
-// One move of an active rollout.  Returns 0 = game goes on, 1 = black won, 2 = white won, 3 = draw.
-__device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */, Lane& L, uint32_t r) {
+// Outcome counters of a lane, packed in one register: black wins in bits 0..9, white wins in 10..19, draws in
+// 20..29 (flushed before a field can reach 1024).
+constexpr uint32_t kIncBlack = 1u, kIncWhite = 1u << 10, kIncDraw = 1u << 20;
+
+// per-cell diagonal addressing, one byte each: slot and bit of the (+1,+1) diagonal, slot and bit of the (-1,+1)
+// diagonal; cells on diagonals shorter than five map to the scratch slot (bit 0), where the same bit is set over
+// and over and can never form a run
+__device__ __forceinline__ uint32_t cell_lut_entry(uint32_t c) {
+    const uint32_t y = c / 15u, x = c - 15u * y;
+    const uint32_t k = x - y + 10u, t = x + y - 4u;
+    const uint32_t dslot = k <= 20u ? 30u + k : uint32_t(kSlots), dbit = k <= 20u ? min(x, y) : 0u;
+    const uint32_t aslot = t <= 20u ? 51u + t : uint32_t(kSlots), abit = t <= 20u ? min(14u - x, y) : 0u;
+    return dslot | dbit << 8 | aslot << 16 | abit << 24;
+}
+
+// One move of an active rollout.  Returns the outcome increment: 0 = game goes on, else kIncBlack / kIncWhite / kIncDraw.
+__device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */, const uint32_t* s_cell, Lane& L, uint32_t r) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
     uint32_t w = my[y * kThreads];
-    uint32_t avail = ~(w | (w >> 16)) & 0x7fffu & (0xffffffffu << x);
+    uint32_t empty = ~(w | (w >> 16)) & 0x7fffu;                                 // empty cells of the row
+    uint32_t avail = empty & (0xffffffffu << x);
     if (avail == 0) {                                                            // first empty cell after r: next row that has one
         uint32_t m = L.rowmask & ~((2u << y) - 1u);
         if (m == 0) m = L.rowmask;
         y = __ffs(m) - 1;
         w = my[y * kThreads];
-        avail = ~(w | (w >> 16)) & 0x7fffu;
+        avail = empty = ~(w | (w >> 16)) & 0x7fffu;
     }
     x = __ffs(avail) - 1;
+    const uint32_t lut = s_cell[y * 15u + x];
     const uint32_t sh = 16u * L.colour;
     // row
     w |= 1u << (x + sh);
     my[y * kThreads] = w;
-    if (((w | (w >> 16)) & 0x7fffu) == 0x7fffu) L.rowmask &= ~(1u << y);
+    if ((empty & (empty - 1u)) == 0) L.rowmask ^= 1u << y;                       // that was the row's last empty cell
     // column
     uint32_t vc;
     {
@@ -156,36 +173,26 @@ __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */,
         vc = *p | (1u << (y + sh));
         *p = vc;
     }
-    // diagonal (+1,+1): x - y = k, k in [-10, 10]; cells on shorter diagonals use the scratch slot, where
-    // the same bit is set over and over and can never form a run
-    uint32_t vd;
+    // the two diagonals
+    uint32_t vd, va;
     {
-        const uint32_t k = x - y + 10u;
-        const bool ok = k <= 20u;
-        uint32_t* p = my + (ok ? 30u + k : uint32_t(kSlots)) * kThreads;
-        vd = *p | (1u << ((ok ? min(x, y) : 0u) + sh));
+        uint32_t* p = my + __byte_perm(lut, 0u, 0x4440u) * kThreads;
+        vd = *p | (1u << (__byte_perm(lut, 0u, 0x4441u) + sh));
         *p = vd;
     }
-    // anti-diagonal (-1,+1): x + y = s, s in [4, 24]
-    uint32_t va;
     {
-        const uint32_t s = x + y - 4u;
-        const bool ok = s <= 20u;
-        uint32_t* p = my + (ok ? 51u + s : uint32_t(kSlots)) * kThreads;
-        va = *p | (1u << ((ok ? min(14u - x, y) : 0u) + sh));
+        uint32_t* p = my + __byte_perm(lut, 0u, 0x4442u) * kThreads;
+        va = *p | (1u << (__byte_perm(lut, 0u, 0x4443u) + sh));
         *p = va;
     }
     // win test on the mover's halves only, two lines per register: one PRMT packs the 16-bit halves of two slots
-    // (bit 15 of a half is never set, so a run cannot cross from one line into the other)
-    const uint32_t sel = L.colour ? 0x7632u : 0x5410u;
+    const uint32_t sel = 0x5410u + 0x2222u * L.colour;
     const uint32_t fives = five_bits(__byte_perm(w, vc, sel)) | five_bits(__byte_perm(vd, va, sel));
-    L.moves += 1;
-    L.empties -= 1;
-    uint32_t result = 0;
-    if (fives) result = 1u + L.colour;                                           // winner = player of the last stone, Game.cpp:125-128
-    else if (L.empties == 0) result = 3u;                                        // Game.cpp:129-132
+    L.left -= 1;
+    uint32_t inc = L.left == 0 ? kIncDraw : 0u;                                  // Game.cpp:129-132
+    if (fives) inc = kIncBlack + (kIncWhite - kIncBlack) * L.colour;             // winner = player of the last stone, Game.cpp:125-128
     L.colour ^= 1u;
-    return result;
+    return inc;
 }
 
 template <bool kInjected, int kRefill>
@@ -193,7 +200,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots + 1][kThreads]
     __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_cell[kCells];
     if (threadIdx.x == 0) s_ticket = 0;
+    if (threadIdx.x < kCells) s_cell[threadIdx.x] = cell_lut_entry(threadIdx.x);
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
@@ -203,34 +212,34 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
 
     Lane L{};
     bool active = false, dead = false;
-    uint32_t acc_white = 0, acc_draw = 0, acc_black = 0;                         // outcomes so far of position acc_pos
+    uint32_t acc = 0, acc_n = 0;                                                 // packed outcomes / rollouts started since the last flush, of position acc_pos
     const bool trace = a.winners != nullptr || a.lengths != nullptr;
     uint32_t acc_pos = 0xffffffffu;
     uint32_t rnd[4] = { 0, 0, 0, 0 };
     const uint8_t* inj = nullptr;
 
-    // result: 0 game goes on, 1 black won, 2 white won, 3 draw.  Branch-free on the hot path: three predicated
-    // adds per step for every lane; the per-rollout trace is written only when the caller asked for it.
-    auto finish = [&](uint32_t result) {
-        acc_black += result == 1u;
-        acc_white += result == 2u;
-        acc_draw += result == 3u;
-        if (result) {
+    // Branch-free on the hot path: one add per step for every lane; the per-rollout trace is written only when the
+    // caller asked for it.
+    auto finish = [&](uint32_t inc) {
+        acc += inc;
+        if (inc) {
             if (trace) {
                 const size_t g = size_t(L.pos) * a.rollouts_per_pos + L.roll;
-                if (a.winners) a.winners[g] = (int8_t)(result == 1u ? 1 : result == 2u ? -1 : 0);
-                if (a.lengths) a.lengths[g] = (uint8_t)L.moves;
+                if (a.winners) a.winners[g] = (int8_t)(inc == kIncBlack ? 1 : inc == kIncWhite ? -1 : 0);
+                if (a.lengths) a.lengths[g] = (uint8_t)(L.start - L.left);
             }
             active = false;
         }
     };
     auto flush = [&]() {
         if (a.wdb && acc_pos != 0xffffffffu) {
-            if (acc_white) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 0, int(acc_white));
-            if (acc_draw) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 1, int(acc_draw));
-            if (acc_black) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 2, int(acc_black));
+            const uint32_t white = (acc >> 10) & 1023u, draw = acc >> 20, black = acc & 1023u;
+            if (white) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 0, int(white));
+            if (draw) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 1, int(draw));
+            if (black) atomicAdd(a.wdb + size_t(acc_pos) * 3 + 2, int(black));
         }
-        acc_white = acc_draw = acc_black = 0;
+        acc = 0;
+        acc_n = 0;
     };
 
     for (;;) {
@@ -251,17 +260,17 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
                     const uint32_t g = uint32_t(g64);
                     L.pos = g / uint32_t(a.rollouts_per_pos);
                     L.roll = g - L.pos * uint32_t(a.rollouts_per_pos);
-                    if (L.pos != acc_pos) { flush(); acc_pos = L.pos; }
+                    if (L.pos != acc_pos || acc_n >= 1000u) { flush(); acc_pos = L.pos; }
+                    acc_n += 1;
                     const uint32_t* img = images + size_t(L.pos) * kImageWords;
                     const uint32_t info = __ldg(img + kMetaInfo);
-                    L.empties = info & 0xffu;
+                    L.left = L.start = info & 0xffu;
                     L.colour = (info >> 8) & 1u;
                     L.rowmask = __ldg(img + kMetaRows);
-                    L.moves = 0;
                     if ((info >> 9) & 1u) {                                      // already decided: 0 moves
                         const uint32_t wc = (info >> 10) & 3u;
                         active = true;
-                        finish(wc ? wc : 3u);
+                        finish(wc == 1u ? kIncBlack : wc == 2u ? kIncWhite : kIncDraw);
                     } else {
                         const uint4* img4 = reinterpret_cast<const uint4*>(img);    // 320-byte images: 16-byte aligned
 #pragma unroll 6
@@ -285,23 +294,24 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
         for (int quad = 0; quad < kRefill / 4; ++quad) {
             if (!kInjected) {
                 if (active)
-                    philox4x32_10(L.moves >> 2, L.roll, uint32_t(a.pos_base) + L.pos, a.ctr_hi, a.key_lo, a.key_hi, rnd);
+                    philox4x32_10((L.start - L.left) >> 2, L.roll, uint32_t(a.pos_base) + L.pos, a.ctr_hi, a.key_lo, a.key_hi, rnd);
             }
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 if (active) {
                     uint32_t r;
                     if (kInjected) {
-                        if (int(L.moves) >= a.stream_stride) {                   // stream exhausted: report length 255, winner 0
-                            L.moves = 255;
-                            finish(3u);
+                        const uint32_t played = L.start - L.left;
+                        if (int(played) >= a.stream_stride) {                    // stream exhausted: report length 255, winner 0
+                            L.start = L.left + 255u;
+                            finish(kIncDraw);
                             continue;
                         }
-                        r = inj[L.moves];
+                        r = inj[played];
                     } else {
                         r = __umulhi(rnd[s], uint32_t(kCells));
                     }
-                    finish(play_move(my, L, r));
+                    finish(play_move(my, s_cell, L, r));
                 }
             }
         }
