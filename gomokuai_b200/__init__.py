@@ -387,6 +387,22 @@ def rollout_batch_host(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_ba
     return wdb
 
 
+def rollout_submit_host(slot, boards, rollouts_per_pos, wdb, key=SYNTH_KEY, ctr_hi=0, pos_base=0):
+    """Asynchronous gk_rollout_batch_host on stream `slot` (0..7): returns at once; `boards` (uint32[n,16]) and `wdb`
+    (int32[n,3]) are numpy arrays that must stay alive and untouched until rollout_wait(slot)."""
+    _require_init()
+    b = boards.view(np.uint32).reshape(-1, BOARD_WORDS)
+    if not (b.flags.c_contiguous and wdb.flags.c_contiguous and wdb.dtype == np.int32 and wdb.size == 3 * b.shape[0]):
+        raise GomokuB200Error("boards must be contiguous uint32[n,16] and wdb contiguous int32[n,3]")
+    _check(lib().gk_rollout_submit_host(int(slot), b.ctypes.data_as(ctypes.c_void_p), b.shape[0], int(rollouts_per_pos),
+                                        ctypes.c_uint64(key), ctypes.c_uint32(ctr_hi), int(pos_base),
+                                        wdb.ctypes.data_as(ctypes.c_void_p)))
+
+
+def rollout_wait(slot):
+    _check(lib().gk_rollout_wait(int(slot)))
+
+
 def rollout_injected(boards, r_stream, stream=None):
     """Playouts driven by an explicit start-index stream r_stream[n, R, stride] (uint8, values 0..224)."""
     torch = _torch()

@@ -123,30 +123,33 @@ struct Lane {
     uint32_t pos, roll;    // position index (batch-local), rollout index within the position
 };
 
-// raw five-in-a-row detector on a whole slot word: bit i of the result is set iff bits i..i+4 are.
-// Bit 15 of a 16-bit half is never set, so runs never leak from one half into the other.
+// raw five-in-a-row detector on a whole slot word: bit i of the result is set iff bits i-4..i are.
+// Bit 15 of a 16-bit half is never set, so runs never leak from one half into the other.  Left shifts on purpose:
+// they compile to IMAD.SHL on the FMA pipe, and this kernel is bound by the ALU pipe (LOP3 / SHF / PRMT).
 __device__ __forceinline__ uint32_t five_bits(uint32_t v) {
-    uint32_t t = v & (v >> 1);
-    t &= t >> 2;
-    return t & (v >> 4);
+    uint32_t t = v & (v << 1);
+    t &= t << 2;
+    return t & (v << 4);
 }
 
 // Outcome counters of a lane, packed in one register: black wins in bits 0..9, white wins in 10..19, draws in
 // 20..29 (flushed before a field can reach 1024).
 constexpr uint32_t kIncBlack = 1u, kIncWhite = 1u << 10, kIncDraw = 1u << 20;
 
-// per-cell diagonal addressing, one byte each: slot and bit of the (+1,+1) diagonal, slot and bit of the (-1,+1)
-// diagonal; cells on diagonals shorter than five map to the scratch slot (bit 0), where the same bit is set over
-// and over and can never form a run
+// per-cell diagonal addressing, one byte each: slot of the (+1,+1) diagonal, slot of the (-1,+1) diagonal; cells on
+// diagonals shorter than five map to the scratch slot.  Their bit positions min(x, y) / min(14 - x, y) are <= 3
+// there, so the scratch slot only ever holds bits 0..3 of each half and can never show a run of five.
 __device__ __forceinline__ uint32_t cell_lut_entry(uint32_t c) {
     const uint32_t y = c / 15u, x = c - 15u * y;
     const uint32_t k = x - y + 10u, t = x + y - 4u;
-    const uint32_t dslot = k <= 20u ? 30u + k : uint32_t(kSlots), dbit = k <= 20u ? min(x, y) : 0u;
-    const uint32_t aslot = t <= 20u ? 51u + t : uint32_t(kSlots), abit = t <= 20u ? min(14u - x, y) : 0u;
-    return dslot | dbit << 8 | aslot << 16 | abit << 24;
+    const uint32_t dslot = k <= 20u ? 30u + k : uint32_t(kSlots);
+    const uint32_t aslot = t <= 20u ? 51u + t : uint32_t(kSlots);
+    return dslot | aslot << 8;
 }
 
 // One move of an active rollout.  Returns the outcome increment: 0 = game goes on, else kIncBlack / kIncWhite / kIncDraw.
+// Stone masks are built as (1 << position) * base with base = 1 (black half) or 65536 (white half): the multiply
+// runs on the FMA pipe.
 __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */, const uint32_t* s_cell, Lane& L, uint32_t r) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
     uint32_t w = my[y * kThreads];
@@ -159,30 +162,31 @@ __device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */,
         w = my[y * kThreads];
         avail = empty = ~(w | (w >> 16)) & 0x7fffu;
     }
-    x = __ffs(avail) - 1;
+    const uint32_t xbit = avail & (0u - avail), ybit = 1u << y;                  // 1 << x, 1 << y
+    x = 31u - __clz(xbit);
     const uint32_t lut = s_cell[y * 15u + x];
-    const uint32_t sh = 16u * L.colour;
+    const uint32_t base = 1u + 0xffffu * L.colour;
     // row
-    w |= 1u << (x + sh);
+    w |= xbit * base;
     my[y * kThreads] = w;
-    if ((empty & (empty - 1u)) == 0) L.rowmask ^= 1u << y;                       // that was the row's last empty cell
+    if ((empty & (empty - 1u)) == 0) L.rowmask ^= ybit;                          // that was the row's last empty cell
     // column
     uint32_t vc;
     {
         uint32_t* p = my + (15u + x) * kThreads;
-        vc = *p | (1u << (y + sh));
+        vc = *p | ybit * base;
         *p = vc;
     }
-    // the two diagonals
+    // the two diagonals: bit min(x, y) of (+1,+1), bit min(14 - x, y) of (-1,+1)
     uint32_t vd, va;
     {
         uint32_t* p = my + __byte_perm(lut, 0u, 0x4440u) * kThreads;
-        vd = *p | (1u << (__byte_perm(lut, 0u, 0x4441u) + sh));
+        vd = *p | min(xbit, ybit) * base;
         *p = vd;
     }
     {
-        uint32_t* p = my + __byte_perm(lut, 0u, 0x4442u) * kThreads;
-        va = *p | (1u << (__byte_perm(lut, 0u, 0x4443u) + sh));
+        uint32_t* p = my + __byte_perm(lut, 0u, 0x4441u) * kThreads;
+        va = *p | min(0x4000u >> x, ybit) * base;
         *p = va;
     }
     // win test on the mover's halves only, two lines per register: one PRMT packs the 16-bit halves of two slots

@@ -140,3 +140,41 @@ def test_win_rates_match_reference_rng_path(gpu, ref):
         worst = max(worst, abs(pg - pc) / tol)
         assert abs(pg - pc) <= tol, (i, pg, pc, tol)
     assert worst > 0.0
+
+
+def test_async_slots_equal_the_synchronous_call(gpu):
+    """gk_rollout_submit_host / gk_rollout_wait: four batches in flight on four slots give the counts of four
+    synchronous calls (Philox streams depend on (position, rollout), not on the slot or the interleaving)."""
+    boards, _, _ = gpu.synth_positions(2000, 4 * 96, want_moves=False)
+    parts = [np.ascontiguousarray(boards[i * 96:(i + 1) * 96]) for i in range(4)]
+    outs = [np.full((96, 3), -1, np.int32) for _ in range(4)]
+    for rep in range(3):                                    # reuse of the slots' buffers
+        for s in range(4):
+            gpu.rollout_submit_host(s, parts[s], 24, outs[s], key=99, ctr_hi=rep, pos_base=s * 96)
+        for s in (2, 0, 3, 1):
+            gpu.rollout_wait(s)
+        want = gpu.rollout_batch_host(boards, 24, key=99, ctr_hi=rep)
+        assert np.array_equal(np.concatenate(outs), want)
+        assert (want.sum(1) == 24).all()
+    with pytest.raises(gpu.GomokuB200Error):
+        gpu.rollout_submit_host(8, parts[0], 24, outs[0])
+    gpu.rollout_wait(5)                                     # a slot never used: nothing to wait for
+
+
+def test_concurrent_streams_do_not_share_scratch(gpu):
+    """Rollout launches in flight on different streams each use their own slot-image scratch."""
+    import torch
+    sets = [gpu.synth_positions(3000 + 512 * i, 512, want_moves=False)[0] for i in range(3)]
+    serial = [_np(gpu.rollout_batch(b, 64, pos_base=512 * i)["wdb"]) for i, b in enumerate(sets)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in sets]
+    dev = [torch.from_numpy(b.view(np.int32)).cuda() for b in sets]
+    torch.cuda.synchronize()
+    for rep in range(4):
+        res = []
+        for i, (st, b) in enumerate(zip(streams, dev)):
+            with torch.cuda.stream(st):
+                res.append(gpu.rollout_batch(b, 64, pos_base=512 * i, stream=st)["wdb"])
+        torch.cuda.synchronize()
+        for got, want in zip(res, serial):
+            assert np.array_equal(_np(got), want)
