@@ -14,7 +14,7 @@
 // Legal-move selection works on the row slots plus a 15-bit "row still has an empty cell" mask
 // kept in a register: at most two shared-memory probes per move, no loop.
 //
-// Threads are persistent: a finished lane waits for the next refill point (every kRefill = 12
+// Threads are persistent: a finished lane waits for the next refill point (every kRefill = 16
 // steps, a multiple of 4 so that all lanes draw a fresh Philox4x32-10 block on the same steps),
 // takes the next rollout ticket and re-copies the position's 72-word slot image.
 #include <cuda_runtime.h>
@@ -34,7 +34,7 @@ constexpr int kImageWords = 80;          // 72 slots + meta, 320 B per position
 constexpr int kMetaInfo = 72;            // empties | to_move << 8 | decided << 9 | winner code << 10
 constexpr int kMetaRows = 73;            // rows that still have an empty cell
 constexpr int kThreads = 256;            // per CTA: 256 x 73 x 4 B = 73 KiB of slot state, 3 CTAs per SM
-constexpr int kRefillDefault = 12;       // move steps between refill points (multiple of 4)
+constexpr int kRefillDefault = 16;       // move steps between refill points (multiple of 4)
 constexpr int kTicketBlock = 256;        // consecutive rollouts a CTA claims at a time
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -150,45 +150,50 @@ __device__ __forceinline__ uint32_t cell_lut_entry(uint32_t c) {
 // One move of an active rollout.  Returns the outcome increment: 0 = game goes on, else kIncBlack / kIncWhite / kIncDraw.
 // Stone masks are built as (1 << position) * base with base = 1 (black half) or 65536 (white half): the multiply
 // runs on the FMA pipe.
-__device__ __forceinline__ uint32_t play_move(uint32_t* my /* &slots[0][tid] */, const uint32_t* s_cell, Lane& L, uint32_t r) {
+// shared-window loads / stores on 32-bit addresses held in registers (a generic pointer into shared memory makes the
+// compiler re-derive the window base with four uniform-datapath instructions per access)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+
+constexpr uint32_t kSlotStride = kThreads * 4u;                                   // bytes between consecutive slots of one thread
+
+__device__ __forceinline__ uint32_t play_move(uint32_t my /* shared address of slots[0][tid] */, uint32_t cell_addr /* of the cell LUT */,
+                                              Lane& L, uint32_t r) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
-    uint32_t w = my[y * kThreads];
+    uint32_t w = lds32(my + y * kSlotStride);
     uint32_t empty = ~(w | (w >> 16)) & 0x7fffu;                                 // empty cells of the row
     uint32_t avail = empty & (0xffffffffu << x);
     if (avail == 0) {                                                            // first empty cell after r: next row that has one
         uint32_t m = L.rowmask & ~((2u << y) - 1u);
         if (m == 0) m = L.rowmask;
         y = __ffs(m) - 1;
-        w = my[y * kThreads];
+        w = lds32(my + y * kSlotStride);
         avail = empty = ~(w | (w >> 16)) & 0x7fffu;
     }
     const uint32_t xbit = avail & (0u - avail), ybit = 1u << y;                  // 1 << x, 1 << y
     x = 31u - __clz(xbit);
-    const uint32_t lut = s_cell[y * 15u + x];
+    uint32_t lut;                                                                // s_cell[15 y + x]; the table is read-only after the CTA's first barrier
+    asm("ld.shared.u32 %0, [%1];" : "=r"(lut) : "r"(cell_addr + (y * 15u + x) * 4u));
     const uint32_t base = 1u + 0xffffu * L.colour;
     // row
     w |= xbit * base;
-    my[y * kThreads] = w;
+    sts32(my + y * kSlotStride, w);
     if ((empty & (empty - 1u)) == 0) L.rowmask ^= ybit;                          // that was the row's last empty cell
     // column
-    uint32_t vc;
-    {
-        uint32_t* p = my + (15u + x) * kThreads;
-        vc = *p | ybit * base;
-        *p = vc;
-    }
+    const uint32_t pc = my + (15u + x) * kSlotStride;
+    const uint32_t vc = lds32(pc) | ybit * base;
+    sts32(pc, vc);
     // the two diagonals: bit min(x, y) of (+1,+1), bit min(14 - x, y) of (-1,+1)
-    uint32_t vd, va;
-    {
-        uint32_t* p = my + __byte_perm(lut, 0u, 0x4440u) * kThreads;
-        vd = *p | min(xbit, ybit) * base;
-        *p = vd;
-    }
-    {
-        uint32_t* p = my + __byte_perm(lut, 0u, 0x4441u) * kThreads;
-        va = *p | min(0x4000u >> x, ybit) * base;
-        *p = va;
-    }
+    const uint32_t pd = my + __byte_perm(lut, 0u, 0x4440u) * kSlotStride;
+    const uint32_t vd = lds32(pd) | min(xbit, ybit) * base;
+    sts32(pd, vd);
+    const uint32_t pa = my + __byte_perm(lut, 0u, 0x4441u) * kSlotStride;
+    const uint32_t va = lds32(pa) | min(0x4000u >> x, ybit) * base;
+    sts32(pa, va);
     // win test on the mover's halves only, two lines per register: one PRMT packs the 16-bit halves of two slots
     const uint32_t sel = 0x5410u + 0x2222u * L.colour;
     const uint32_t fives = five_bits(__byte_perm(w, vc, sel)) | five_bits(__byte_perm(vd, va, sel));
@@ -210,8 +215,11 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
-    uint32_t* my = s_slots + threadIdx.x;
-    my[kSlots * kThreads] = 0;                                                   // scratch slot: must never hold a run
+    uint32_t cell_addr = (uint32_t)__cvta_generic_to_shared(s_cell);             // kept in a register: re-deriving it costs 5 uniform
+    asm volatile("" : "+r"(cell_addr));                                          // instructions per move
+    uint32_t my = (uint32_t)__cvta_generic_to_shared(s_slots + threadIdx.x);     // shared address of slots[0][tid]
+    asm volatile("" : "+r"(my));
+    sts32(my + kSlots * kSlotStride, 0u);                                        // scratch slot: must never hold a run
     const uint32_t total = uint32_t(a.n) * uint32_t(a.rollouts_per_pos);
 
     Lane L{};
@@ -280,8 +288,8 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
 #pragma unroll 6
                         for (int s = 0; s < kSlots / 4; ++s) {
                             const uint4 q = __ldg(img4 + s);
-                            my[(4 * s + 0) * kThreads] = q.x; my[(4 * s + 1) * kThreads] = q.y;
-                            my[(4 * s + 2) * kThreads] = q.z; my[(4 * s + 3) * kThreads] = q.w;
+                            sts32(my + (4 * s + 0) * kSlotStride, q.x); sts32(my + (4 * s + 1) * kSlotStride, q.y);
+                            sts32(my + (4 * s + 2) * kSlotStride, q.z); sts32(my + (4 * s + 3) * kSlotStride, q.w);
                         }
                         active = true;
                         if (kInjected) inj = a.r_stream + size_t(g) * a.stream_stride;
@@ -315,7 +323,7 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
                     } else {
                         r = __umulhi(rnd[s], uint32_t(kCells));
                     }
-                    finish(play_move(my, s_cell, L, r));
+                    finish(play_move(my, cell_addr, L, r));
                 }
             }
         }
@@ -352,7 +360,7 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images,
     switch (refill) {
         case 4: return launch(rollout_kernel<false, 4>);
         case 8: return launch(rollout_kernel<false, 8>);
-        case 16: return launch(rollout_kernel<false, 16>);
+        case 12: return launch(rollout_kernel<false, 12>);
         default: return launch(rollout_kernel<false, kRefillDefault>);
     }
 }

@@ -5,7 +5,7 @@
 The first launch of every distinct kernel is kept; ac_eval_kernel<0, 0> and rollout_kernel<0, 12> are
 stored under the plain names bench.py looks up.
 """
-import csv, json, os, sys
+import csv, json, os, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 h, u = rows[0], rows[1]
 col = {x: i for i, x in enumerate(h)}
@@ -23,7 +23,8 @@ def num(r, name, unit_scaled=False):
 out = {}
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    key = name.split("::")[-1].split("(")[0]
+    m = re.search(r"([A-Za-z_]\w*(?:<[^<>()]*>)?)\s*\(", name)          # function name (+ template arguments) before the argument list
+    key = m.group(1) if m else name
     key = "ac_eval_kernel" if key.startswith("ac_eval_kernel<0, 0>") else "rollout_kernel" if key.startswith("rollout_kernel") else key
     if key in out:
         continue

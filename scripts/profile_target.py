@@ -9,11 +9,12 @@ gk.init(0)
 n = int(os.environ.get("GK_PROFILE_BOARDS", 1 << 18))
 boards, _, _ = gk.synth_positions(0, n, want_moves=False)
 bt = torch.from_numpy(boards.view(np.int32)).cuda()
+once = bool(os.environ.get("GK_PROFILE_ONCE"))          # one launch per kernel: keeps an `ncu --set full` report small
 out = gk.eval_batch(bt)
-for _ in range(2):
+for _ in range(0 if once else 2):
     gk.eval_batch(bt, out=out)
 r = None
-for _ in range(2):
+for _ in range(1 if once else 2):
     r = gk.rollout_batch(bt[:4096].contiguous(), int(os.environ.get("GK_PROFILE_ROLLOUTS", 1024)))
 if os.environ.get("GK_PROFILE_ALL"):
     m = min(n, 1 << 18)
@@ -22,6 +23,7 @@ if os.environ.get("GK_PROFILE_ALL"):
     g = gk.guided_rollout_batch(torch.zeros((8192, 16), dtype=torch.int32, device="cuda"), mode="sample")
     last = torch.full((m, 2), -1, dtype=torch.int16, device="cuda")
     enc = gk.encode_states_batch(bt[:m], last, augment=True)
-    enc1 = gk.encode_states_batch(bt[:m], last)
+    if not once:
+        enc1 = gk.encode_states_batch(bt[:m], last)
 torch.cuda.synchronize()
 print("ok", int(out["pat_totals"].sum()), int(r["wdb"].sum()))
