@@ -269,28 +269,32 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
     const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
     const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
     const int p = n_black == n_white ? 1 : 0;                      // Group(player to move): black moves first (Game.h:128)
-    float n2w = 0.f, n2b = 0.f;
-    GK_UNROLL(GK_HEADS_UNROLL)
-    for (int k = 0; k < 8; ++k) {
-        const int c = lane + 32 * k, cc = c < kCells ? c : kCells - 1;
-        const int y = cc / kWidth, x = cc - y * kWidth;
-        const bool open = c < kCells && cell_value(ws.board, cc) == 0u;
-        uint32_t acc_w = 0, acc_b = 0;
-#pragma unroll
-        for (int dy = -3; dy <= 3; ++dy) {
-            const int yy = min(max(y + dy, 0), kHeight - 1);
-            const bool in = y + dy >= 0 && y + dy < kHeight;
-            const uint32_t row_w = __shfl_sync(0xffffffffu, mine, yy), row_b = __shfl_sync(0xffffffffu, mine, 15 + yy);
-            const uint16_t* lut = s_lut + (dy < 0 ? -dy : dy) * 128;
-            const uint32_t tw = lut[((row_w << 3) >> x) & 0x7fu], tb = lut[((row_b << 3) >> x) & 0x7fu];
-            if (in) { acc_w += tw; acc_b += tb; }
+    // Density by columns: lane (colour, x) walks the rows once.  A row's 7-bit slice around x is looked up for
+    // |dy| = 0..3 (4 table loads) and added to a sliding window of accumulators (rows y - 3 .. y + 2 in w0 .. w5); the
+    // oldest row is complete after each step and is turned into 3 W / (1 + 2 N) at once.  60 table loads per lane
+    // instead of 8 cells x 7 rows x 2 colours = 112, no per-cell row shuffles, and a loop body of ~45 instructions
+    // (this variant of the kernel is sensitive to code size, see above).
+    const int dc = lane >= 15, dx = lane - 15 * dc;                // lanes 0..14 white, 15..29 black (lanes 30, 31 idle along)
+    const uint32_t occ = mine | __shfl_sync(0xffffffffu, mine, lane < 15 ? lane + 15 : lane - 15);   // occupancy of row y on lanes y and 15 + y
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+    float n2 = 0.f;
+#pragma unroll 1
+    for (int y = 0; y < kHeight + 3; ++y) {
+        uint32_t row = __shfl_sync(0xffffffffu, mine, 15 * dc + min(y, kHeight - 1));
+        if (y >= kHeight) row = 0;                                  // flushing steps: slice 0 looks up { 0, 0 }
+        const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;             // cells dx - 3 .. dx + 3 of row y
+        const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
+        const uint32_t full = w0 + t3;                              // row y - 3 has seen rows y - 6 .. y
+        w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
+        if (y >= 3) {
+            const uint32_t orow = __shfl_sync(0xffffffffu, occ, y - 3);
+            const bool open = lane < 30 && ((orow >> dx) & 1u) == 0u;
+            const float v = open ? (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu)) : 0.f;
+            if (lane < 30) dwv[dc * kCells + (y - 3) * kWidth + dx] = v;
+            n2 += v * v;
         }
-        const float vw = open ? (3.f * float(acc_w >> 8)) / (1.f + 2.f * float(acc_w & 0xffu)) : 0.f;
-        const float vb = open ? (3.f * float(acc_b >> 8)) / (1.f + 2.f * float(acc_b & 0xffu)) : 0.f;
-        if (c < kCells) { dwv[c] = vw; dwv[kCells + c] = vb; }
-        n2w += vw * vw;
-        n2b += vb * vb;
     }
+    float n2w = lane < 15 ? n2 : 0.f, n2b = lane >= 15 ? n2 : 0.f;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         n2w += __shfl_xor_sync(0xffffffffu, n2w, d);
