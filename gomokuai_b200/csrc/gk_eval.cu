@@ -779,15 +779,10 @@ size_t eval_smem_bytes(const EvalArgs& a) {
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
-    int warps = eval_warps(a);
+    const int warps = eval_warps(a);
     if (warps == 0 || a.list_cap * 32 < 2 * kCells || a.tape_steps > kMaxTapeSteps)
         return cudaErrorInvalidConfiguration;                               // table too large for shared memory
-    // A small batch is spread over all SMs (fewer warps per CTA) instead of filling a few: a warp is a serial chain,
-    // so 7 warps on each of 148 SMs finish sooner than 28 warps on each of 37 (1 024 self-play games: 1.9x).
-    const long long per_sm = (a.n + sm_count - 1) / sm_count;
-    if (per_sm < warps) warps = (int)per_sm;
-    const size_t smem = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) +
-                        size_t(warps) * warp_bytes(a.list_cap, wants_heads(a));
+    const size_t smem = eval_smem_bytes(a);
     const long long want = (a.n + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? want : sm_count);               // persistent: one CTA per SM
     auto launch = [&](auto kernel) -> cudaError_t {
