@@ -346,7 +346,9 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images,
     const size_t smem = size_t(kSlots + 1) * kThreads * sizeof(uint32_t);   // + one scratch slot per thread
     const unsigned long long total = (unsigned long long)a.n * a.rollouts_per_pos;
     unsigned long long blocks = (total + kTicketBlock - 1) / kTicketBlock;
-    const unsigned long long resident = (unsigned long long)sm_count * 3;
+    int per_sm = 3;
+    if (const char* env = std::getenv("GK_ROLLOUT_CTAS")) per_sm = std::atoi(env);   // experiment knob
+    const unsigned long long resident = (unsigned long long)sm_count * per_sm;
     const int grid = int(blocks < resident ? blocks : resident);
     int refill = kRefillDefault;
     if (const char* env = std::getenv("GK_ROLLOUT_REFILL")) refill = std::atoi(env);   // tuning knob (4, 8, 12 or 16)
