@@ -213,17 +213,32 @@ def ncu_summary(kernel):
     return {}
 
 
+_ISSUE_PEAKS = {}
+
+
+def measure_issue_peaks(gk):
+    """Live microbenchmark (gk_measure_issue_peak, csrc/gk_peaks.cu): G warp-inst/s of register-only LOP3, IMAD and 1:1 streams."""
+    if not _ISSUE_PEAKS:
+        for name, mode in (("alu_only_lop3", 0), ("fma_only_imad", 1), ("mixed_lop3_imad", 2)):
+            _ISSUE_PEAKS[name] = max(gk.measure_issue_peak(mode) for _ in range(3)) / 1e9
+    return _ISSUE_PEAKS
+
+
 def issue_roofline(kernel, launch_ms, sm_mhz, sm_count=148):
-    """Integer-issue roofline (the one that binds): warp instructions of one launch (from the
-    committed ncu capture) / (SMs x 4 schedulers x 1 inst/clk x measured SM clock)."""
+    """Integer-issue roofline (the one that binds): warp instructions of one launch (from the committed ncu
+    capture) / the rate a balanced LOP3 + IMAD stream sustains on this GPU, measured live by the microbenchmark
+    (nominally SMs x 4 schedulers x 1 inst/clk x SM clock; a stream that uses only the ALU pipe gets half of that)."""
     summ = ncu_summary(kernel)
     if not summ.get("warp_inst_per_launch") or not sm_mhz:
         return None
-    peak = sm_count * 4 * sm_mhz * 1e6
-    achieved = summ["warp_inst_per_launch"] / (launch_ms * 1e-3)
-    return {"bound": "int32 issue slots", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s",
-            "frac": achieved / peak, "active_lanes_per_inst": summ.get("threads_per_inst"),
-            "source": "warp instructions per launch from profiles/ncu_summary.json, time and clock measured live"}
+    nominal = sm_count * 4 * sm_mhz * 1e6 / 1e9
+    peak = _ISSUE_PEAKS.get("mixed_lop3_imad") or nominal
+    achieved = summ["warp_inst_per_launch"] / (launch_ms * 1e-3) / 1e9
+    return {"bound": "int32 issue slots", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s",
+            "frac": achieved / peak, "peak_source": "measured live: LOP3 + IMAD 1:1 register-only stream" if _ISSUE_PEAKS else "nominal",
+            "peak_nominal": nominal, "peaks_measured": dict(_ISSUE_PEAKS),
+            "alu_pipe_pct_ncu": summ.get("alu_pipe_pct"), "active_lanes_per_inst": summ.get("threads_per_inst"),
+            "source": "warp instructions per launch from profiles/ncu_summary.json, time and peak measured live"}
 
 
 def run_gpu_arm(args, rank, world, local_rank):
@@ -241,6 +256,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     stream = torch.cuda.current_stream()
     table = gk.default_table()
+    if rank == 0:
+        measure_issue_peaks(gk)                                           # a few ms, before the timed regions
 
     def barrier():
         if dist is not None:

@@ -74,6 +74,14 @@ def device_info():
 
 
 # ---- tables ------------------------------------------------------------------------------------------
+def measure_issue_peak(mode):
+    """Sustained warp instructions / s of a register-only stream (0: LOP3 only, 1: IMAD only, 2: both 1:1)."""
+    _require_init()
+    v = ctypes.c_double()
+    _check(lib().gk_measure_issue_peak(int(mode), ctypes.byref(v)))
+    return v.value
+
+
 class Table:
     """Compiled pattern automaton (``gk_table``). ``Table()`` is the reference's default pattern set."""
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libgomoku_b200.so")
-SOURCES = ["gk_table.cpp", "gk_eval.cu", "gk_rollout.cu", "gk_encode.cu", "gk_capi.cu"]
+SOURCES = ["gk_table.cpp", "gk_eval.cu", "gk_rollout.cu", "gk_encode.cu", "gk_peaks.cu", "gk_capi.cu"]
 HEADERS = ["gk_format.h", "gk_table.h", "gk_kernels.h", os.path.join("..", "..", "include", "gomoku_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "--use_fast_math"]

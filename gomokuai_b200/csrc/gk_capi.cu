@@ -220,6 +220,13 @@ gk_status gk_device_info(int* device, int* sm_count, int* cc_major, int* cc_mino
     return GK_OK;
 }
 
+gk_status gk_measure_issue_peak(int mode, double* warp_inst_per_s) {
+    if (gk_status s = require_device()) return s;
+    if (mode < 0 || mode > 2 || !warp_inst_per_s) return fail(GK_ERR_INVALID, "mode must be 0, 1 or 2");
+    GK_CUDA(gk::measure_issue_peak(mode, g_sm_count, 4096, warp_inst_per_s, nullptr));
+    return GK_OK;
+}
+
 // ---- tables ------------------------------------------------------------------------------------
 gk_status gk_table_default(gk_table** out) {
     if (!out) return fail(GK_ERR_INVALID, "out is null");

@@ -55,4 +55,7 @@ struct EncodeArgs {
 };
 cudaError_t launch_encode(const EncodeArgs& a, int sm_count, cudaStream_t stream);
 
+// gk_peaks.cu: sustained warp instructions per second of a register-only stream (mode 0 LOP3, 1 IMAD, 2 both 1:1)
+cudaError_t measure_issue_peak(int mode, int sm_count, int iters, double* warp_inst_per_s, cudaStream_t stream);
+
 }  // namespace gk

@@ -63,6 +63,11 @@ gk_status gk_shutdown(void);
 const char* gk_last_error(void);
 gk_status gk_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor);
 const char* gk_version(void);
+/* Microbenchmark behind the integer-issue roofline: sustained warp instructions per second of a
+ * register-only stream on this GPU at its current clocks -- mode 0: LOP3 only (the ALU pipe, which LOP3 / SHF /
+ * IADD3 / PRMT / ISETP share), mode 1: IMAD only (the FMA pipe), mode 2: both 1 : 1 (the ceiling of a balanced
+ * integer kernel).  Takes a few milliseconds. */
+gk_status gk_measure_issue_peak(int mode, double* warp_inst_per_s);
 
 /* ---- pattern automaton --------------------------------------------------------------
  * Replaces the static `PatternSearch Evaluator::Patterns` (src/Pattern.cpp:554-596) and

@@ -53,3 +53,15 @@ def test_board_lines_with_minimal_padding(gpu, port):
     mask = np.arange(16)[None, :] < ca[:, None]
     assert np.array_equal(oa[mask] - 1, ob[mask] - 6)
     assert run(short)[2].sum() == 0
+
+
+def test_issue_peak_microbenchmark(gpu):
+    """gk_measure_issue_peak (the denominator of bench.py's integer-issue roofline): a LOP3-only stream is held to the
+    ALU pipe's rate, a balanced LOP3 + IMAD stream gets close to one instruction per scheduler and clock."""
+    info = gpu.device_info()
+    alu, fma, mixed = (max(gpu.measure_issue_peak(m) for _ in range(2)) for m in (0, 1, 2))
+    nominal = info["sm_count"] * 4 * 1.9e9
+    assert 0.3 * nominal < alu < 0.75 * nominal and 0.3 * nominal < fma < 0.75 * nominal
+    assert 0.7 * nominal < mixed < 1.15 * nominal and mixed > 1.4 * alu
+    with pytest.raises(gpu.GomokuB200Error):
+        gpu.measure_issue_peak(3)
