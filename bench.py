@@ -30,6 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 EVAL_POSITIONS = 1 << 20          # configs[1]
+N_EVAL_PER_GPU = EVAL_POSITIONS
+EVAL_WORKLOAD = ("configs[1]: batched AC pattern evaluation of 1,048,576 synthetic random mid-game 15x15 positions per GPU, "
+                 "bit-exact scores")
+EVAL_OUTPUTS = "int32 scores[4][225] + u16 totals[2][8] + u16 compounds[2][3] + winner per position"
 ROLL_POSITIONS = 4096             # configs[2]
 ROLL_PER_POS = 4096
 EVAL_BYTES_IN, EVAL_BYTES_OUT = 64, 3648       # algorithmic bytes per board
@@ -175,8 +179,8 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "board evals/sec (15x15)", "value": value, "unit": "boards/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_eval / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "configs[1]: AC pattern evaluation of synthetic random mid-game 15x15 positions, "
-                               "bounded CPU sample per step", "positions_per_step": n_eval},
+        "config": {"workload": EVAL_WORKLOAD, "positions_per_gpu": N_EVAL_PER_GPU, "outputs": EVAL_OUTPUTS,
+                   "sample": f"each step replays the first {n_eval} positions of that set on the host cores"},
         "cpu_baseline": {"value": value, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": "boards/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -402,9 +406,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "metric": "board evals/sec (15x15)", "value": eval_value, "unit": "boards/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": eval_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "configs[1]: batched AC pattern evaluation of 1,048,576 synthetic random mid-game 15x15 "
-                               "positions per GPU, bit-exact scores", "positions_per_gpu": n_eval,
-                   "outputs": "int32 scores[4][225] + u16 totals[2][8] + u16 compounds[2][3] + winner per position",
+        "config": {"workload": EVAL_WORKLOAD, "positions_per_gpu": n_eval, "outputs": EVAL_OUTPUTS,
                    "l2": "256 MB write between timed iterations; each step also streams 3.9 GB, > L2",
                    "line_scans_per_sec": eval_value * 72},
         "clocks": clocks,
