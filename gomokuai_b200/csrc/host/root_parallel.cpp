@@ -34,22 +34,25 @@ namespace {
 // first selected -- in increasing cell order, kept in a sibling list -- and the untouched ones are represented by a
 // cursor.  Selection visits exactly the nodes the eager tree would (tests/test_gpu_mcts.py compares the two).
 // The root keeps a materialised block of children when Dirichlet noise makes their priors differ.
-// A node is split in two: what Default::Select reads of every child (value, prior, visits: 12 bytes) lives in three
-// parallel arrays, so the scan of the root's 200+ children streams 2.6 KB instead of 9 KB and vectorises; the links
-// stay in ANode.
+// A node carries its statistics inline (one cache line per child when a sibling list is walked: the search is bound
+// by memory latency, ~110 MB of trees per rank).  Only the root's materialised block of 200+ children keeps them in
+// three parallel arrays instead, so that its scan streams 2.6 KB and vectorises.
 struct ANode {
     std::int32_t parent, first_child, last_child, next_sibling;
     std::int16_t n_children;        // children that exist as nodes
     std::int16_t n_moves;           // legal moves here (empty cells); > 0 once the node has been expanded
     std::int16_t position, cursor;  // the move into this node; highest cell materialised so far (-1 none)
+    float value, prior;             // running mean from the view of who moved into the node; prior of the move
+    std::int32_t visits;
     std::int8_t player;             // who played `position`
     std::int8_t eager;              // children are one contiguous block [first_child, first_child + n_children)
 };
 
 struct Tree {
     std::vector<ANode> nodes;
-    std::vector<float> value, prior;    // running mean from the view of who moved into the node; prior of the move
-    std::vector<std::int32_t> visits;
+    std::vector<float> rvalue, rprior;  // statistics of the root's eager block, nodes [rfirst, rfirst + rn)
+    std::vector<std::int32_t> rvisits;
+    std::int32_t rfirst = 0, rn = 0;
     Board board;
     std::int32_t leaf = 0;          // selected this round
     std::int16_t root_child = -1;   // root move of the current path (-1: the leaf is the root itself)
@@ -61,15 +64,18 @@ struct Tree {
         ANode n{};
         n.parent = parent; n.first_child = n.last_child = n.next_sibling = -1;
         n.position = static_cast<std::int16_t>(position); n.cursor = -1;
+        n.prior = pr;
         n.player = static_cast<std::int8_t>(player);
         nodes.push_back(n);
-        value.push_back(0.0f); prior.push_back(pr); visits.push_back(0);
         return static_cast<std::int32_t>(nodes.size()) - 1;
     }
     void clear(std::size_t reserve) {
-        nodes.clear(); value.clear(); prior.clear(); visits.clear();
-        nodes.reserve(reserve); value.reserve(reserve); prior.reserve(reserve); visits.reserve(reserve);
+        nodes.clear(); rvalue.clear(); rprior.clear(); rvisits.clear();
+        rfirst = rn = 0;
+        nodes.reserve(reserve);
     }
+    bool in_root_block(std::int32_t i) const { return static_cast<std::uint32_t>(i - rfirst) < static_cast<std::uint32_t>(rn); }
+    std::int32_t visits_of(std::int32_t i) const { return in_root_block(i) ? rvisits[i - rfirst] : nodes[i].visits; }
 };
 
 inline void cpu_relax() {
@@ -174,12 +180,16 @@ static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
     t.nodes[node].first_child = first;
     t.nodes[node].n_children = static_cast<std::int16_t>(empties);
     t.nodes[node].eager = 1;
+    if (node == 0) {                                                 // the root's block: statistics in parallel arrays
+        t.rfirst = first; t.rn = empties;
+        t.rvalue.assign(empties, 0.0f); t.rprior.assign(empties, prior); t.rvisits.assign(empties, 0);
+    }
 }
 
 // PUCB score of node c under a parent with sqrt(visits) = sq: state_value + c_puct * P * sqrt(N) / (n + 1), the
 // product evaluated left to right in double like the reference (MonteCarlo.hpp:23-28,62)
-static inline double pucb(const Tree& t, std::int32_t c, double c_puct, double sq) {
-    return t.value[c] + c_puct * t.prior[c] * sq / static_cast<double>(t.visits[c] + 1);
+static inline double pucb(const ANode& ch, double c_puct, double sq) {
+    return ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);
 }
 
 // Default::Select (MonteCarlo.hpp:57-68) over a contiguous block of children: the first child with the highest score.
@@ -232,23 +242,32 @@ __attribute__((target("avx2"))) static int select_block_avx2(const float* v, con
 #endif
 
 static std::int32_t select_block(const Tree& t, std::int32_t first, int n, double c_puct, double sq) {
+    if (first != t.rfirst || n != t.rn) {                            // a block below the root (eager mode only): plain loop
+        std::int32_t best = first;
+        double best_score = -1.0;
+        for (std::int32_t c = first; c < first + n; ++c) {
+            const double score = pucb(t.nodes[c], c_puct, sq);
+            if (score > best_score) { best_score = score; best = c; }
+        }
+        return best;
+    }
 #if defined(__x86_64__)
     static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) return first + select_block_avx2(&t.value[first], &t.prior[first], &t.visits[first], n, c_puct, sq);
+    if (avx2) return first + select_block_avx2(t.rvalue.data(), t.rprior.data(), t.rvisits.data(), n, c_puct, sq);
 #endif
-    return first + select_block_scalar(&t.value[first], &t.prior[first], &t.visits[first], n, c_puct, sq);
+    return first + select_block_scalar(t.rvalue.data(), t.rprior.data(), t.rvisits.data(), n, c_puct, sq);
 }
 
 // Default::Select on a lazily expanded node: the best materialised child, or -- when the common score of the
 // never-visited children is strictly higher -- the lowest never-visited cell, created now.
 static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
     const ANode parent = t.nodes[node];
-    const double sq = std::sqrt(static_cast<double>(t.visits[node]));
+    const double sq = std::sqrt(static_cast<double>(t.visits_of(node)));
     const float prior = 1.0f / static_cast<float>(parent.n_moves);
     std::int32_t best = parent.first_child;                          // as the reference: the first child unless one scores above -1
     double best_score = -1.0;
     for (std::int32_t c = parent.first_child; c >= 0; c = t.nodes[c].next_sibling) {   // increasing cell order
-        const double score = pucb(t, c, c_puct, sq);
+        const double score = pucb(t.nodes[c], c_puct, sq);
         if (score > best_score) { best_score = score; best = c; }
     }
     if (parent.n_children < parent.n_moves) {                       // someone has never been visited: value 0, visits 0
@@ -274,7 +293,7 @@ static void select_leaf(Tree& t, double c_puct, std::uint32_t* packed) {
     t.root_child = -1;
     while (t.nodes[node].n_moves > 0) {                              // expanded: descend
         const ANode& parent = t.nodes[node];
-        node = parent.eager ? select_block(t, parent.first_child, parent.n_children, c_puct, std::sqrt(static_cast<double>(t.visits[node])))
+        node = parent.eager ? select_block(t, parent.first_child, parent.n_children, c_puct, std::sqrt(static_cast<double>(t.visits_of(node))))
                             : select_lazy(t, node, c_puct);
         if (t.root_child < 0) t.root_child = t.nodes[node].position;
         t.board.applyMove(Position(t.nodes[node].position), false);
@@ -297,7 +316,7 @@ static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg
             for (float& x : g) { x = gamma(t.rng); n2 += double(x) * x; }
             const float inv = n2 > 0 ? static_cast<float>(1.0 / std::sqrt(n2)) : 0.0f;
             for (int k = 0; k < rt.n_children; ++k) {
-                float& pr = t.prior[rt.first_child + k];
+                float& pr = t.rprior[k];
                 pr = pr * 0.75f + 0.25f * g[k] * inv;
             }
         }
@@ -305,8 +324,15 @@ static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg
     if (t.root_child >= 0) { t.black_wins[t.root_child] += r[2]; t.white_wins[t.root_child] += r[0]; }
     float v = static_cast<float>(t.nodes[t.leaf].player) * black_value;   // value for who moved into the leaf
     for (std::int32_t n = t.leaf; n >= 0; n = t.nodes[n].parent, v = -v) {
-        t.visits[n] += 1;
-        t.value[n] += (v - t.value[n]) / static_cast<float>(t.visits[n]);
+        if (t.in_root_block(n)) {
+            const std::int32_t k = n - t.rfirst;
+            t.rvisits[k] += 1;
+            t.rvalue[k] += (v - t.rvalue[k]) / static_cast<float>(t.rvisits[k]);
+        } else {
+            ANode& nd = t.nodes[n];
+            nd.visits += 1;
+            nd.value += (v - nd.value) / static_cast<float>(nd.visits);       // MonteCarlo.hpp:90-95
+        }
     }
     t.board.revertMove(t.board.m_moveRecord.size() - root_depth);
 }
@@ -452,9 +478,9 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         nodes += static_cast<std::int64_t>(t.nodes.size());
         const ANode& rt = t.nodes[0];
         if (rt.eager) {
-            for (std::int32_t c = rt.first_child, e = c + rt.n_children; c < e; ++c) m_stats[t.nodes[c].position] += t.visits[c];
+            for (std::int32_t c = rt.first_child, e = c + rt.n_children; c < e; ++c) m_stats[t.nodes[c].position] += t.visits_of(c);
         } else {
-            for (std::int32_t c = rt.first_child; c >= 0; c = t.nodes[c].next_sibling) m_stats[t.nodes[c].position] += t.visits[c];
+            for (std::int32_t c = rt.first_child; c >= 0; c = t.nodes[c].next_sibling) m_stats[t.nodes[c].position] += t.nodes[c].visits;
         }
         for (int c = 0; c < BOARD_SIZE; ++c) {
             m_stats[BOARD_SIZE + c] += t.black_wins[c];
