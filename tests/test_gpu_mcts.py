@@ -139,3 +139,26 @@ def test_root_allreduce_through_the_c_abi(gpu):
             gpu.root_allreduce(torch.zeros(10, dtype=torch.int64, device="cuda"))
     finally:
         gpu.nccl_shutdown()
+
+
+def test_root_parallel_pipeline_is_invisible_in_the_statistics(core, monkeypatch):
+    """Four tree groups in flight, chunked work distribution, a helping driver thread: none of it may show in the
+    result -- a tree's Philox stream is (round, global tree index), its noise stream is seeded per tree."""
+    b = core.Board()
+    for c in (112, 113, 97):
+        b.apply_move(c)
+    ref = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=2).run(b, 60)      # 4 groups of 75 trees
+    assert ref[0].sum() == 300 * 59
+    for threads in (3, 7):
+        assert np.array_equal(core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=threads).run(b, 60), ref)
+    monkeypatch.setenv("GK_RP_DRIVER_HELPS", "0")
+    assert np.array_equal(core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=4).run(b, 60), ref)
+    monkeypatch.delenv("GK_RP_DRIVER_HELPS")
+    s = core.RootParallelSearch(trees=300, c_rollouts=5, seed=5, threads=4)
+    first = s.run(b, 30)
+    assert np.array_equal(s.run(b, 60, 21), ref)                    # the searcher is reusable and reseedable
+    assert not np.array_equal(first[0], ref[0])
+    # replica_base shifts the tree indices: two ranks' halves are disjoint streams of one 600-tree search
+    lo = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=4, replica_base=0).run(b, 20)
+    hi = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=4, replica_base=300).run(b, 20)
+    assert not np.array_equal(lo, hi) and (lo + hi)[0].sum() == 600 * 19
