@@ -507,6 +507,14 @@ gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_
                           d_lengths, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// small synchronous batches (one MCTS leaf at a time, config 1) are pure call latency: they go through page-locked
+// staging that the kernel reads in place (no copy-in operation) and a true DMA copy-out
+constexpr int kSmallBatch = 1024;
+uint32_t* g_stage_boards = nullptr;     // page-locked, kSmallBatch x 16 words
+int32_t* g_stage_wdb = nullptr;         // page-locked, kSmallBatch x 3
+}  // namespace
+
 gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_per_pos, uint64_t philox_key,
                                 uint32_t ctr_hi, int pos_base, int32_t* h_wdb) {
     if (gk_status s = require_device()) return s;
@@ -515,6 +523,20 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
     std::lock_guard<std::mutex> lock(g_mutex);
     Pipe& p = g_pipes[0];
     if (gk_status s = pipe_reserve(p, std::max(n, 1))) return s;
+    if (n <= kSmallBatch) {
+        if (!g_stage_boards) {
+            GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_boards), size_t(kSmallBatch) * 64, cudaHostAllocDefault));
+            GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_wdb), size_t(kSmallBatch) * 12, cudaHostAllocDefault));
+        }
+        std::memcpy(g_stage_boards, h_boards, size_t(n) * 64);
+        if (gk_status s = rollout_common(g_stage_boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, p.d_wdb,
+                                         nullptr, nullptr, p.stream))
+            return s;
+        GK_CUDA(cudaMemcpyAsync(g_stage_wdb, p.d_wdb, size_t(n) * 12, cudaMemcpyDeviceToHost, p.stream));
+        GK_CUDA(cudaStreamSynchronize(p.stream));
+        std::memcpy(h_wdb, g_stage_wdb, size_t(n) * 12);
+        return GK_OK;
+    }
     GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, p.stream));
     if (gk_status s = rollout_common(p.d_boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, p.d_wdb,
                                      nullptr, nullptr, p.stream))
