@@ -16,6 +16,7 @@ ap.add_argument("--trees", type=int, default=4096, help="trees per GPU")
 ap.add_argument("--rollouts", type=int, default=5)
 ap.add_argument("--moves", type=int, default=3)
 ap.add_argument("--threads", type=int, default=0)
+ap.add_argument("--check", action="store_true", help="rank 0 repeats every search alone with world x trees trees and compares the statistics")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -43,7 +44,16 @@ for mv in range(args.moves):
     played = int(stats[0].sum()) + world * args.trees
     rows.append({"move": int(move), "seconds": float(t.item()), "playouts": played, "playouts_per_s": played / float(t.item()),
                  "gpu_fraction": s.seconds_gpu / max(s.seconds_total, 1e-9), "nodes_rank0": int(s.nodes),
+                 "playouts_per_tree": int(s.leaves // args.trees),
                  "search_seconds": s.seconds_total, "driver_seconds": [round(x, 4) for x in s.driver_seconds]})
+    if args.check and rank == 0:
+        # the same search on ONE GPU: world x trees trees with tree indices 0 .. world*trees-1 -- identical by construction
+        alone = core.RootParallelSearch(trees=world * args.trees, c_rollouts=args.rollouts, seed=11 + mv, threads=threads)
+        rows[-1]["equals_single_gpu_search"] = bool(np.array_equal(alone.run(b, rows[-1]["playouts_per_tree"]), stats))
+        rows[-1]["single_gpu_move"] = int(core.RootParallelSearch.best_move(alone.run(b, rows[-1]["playouts_per_tree"])))
+        del alone
+    if world > 1:
+        dist.barrier()
     b.apply_move(move)
 if rank == 0:
     best = max(rows, key=lambda r: r["playouts_per_s"])
