@@ -162,3 +162,5 @@ def test_root_parallel_pipeline_is_invisible_in_the_statistics(core, monkeypatch
     lo = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=4, replica_base=0).run(b, 20)
     hi = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=4, replica_base=300).run(b, 20)
     assert not np.array_equal(lo, hi) and (lo + hi)[0].sum() == 600 * 19
+    whole = core.RootParallelSearch(trees=600, c_rollouts=5, seed=21, threads=4).run(b, 20)
+    assert np.array_equal(lo + hi, whole)                           # what the allreduce of two ranks yields = one rank with all the trees
