@@ -369,6 +369,26 @@ def guided_rollout_batch(boards, mode="max", key=SYNTH_KEY, ctr_hi=0, game_base=
     return out
 
 
+def expand_games(boards, games, stream=None):
+    """Every position the games of a guided_rollout_batch result went through (the position BEFORE each ply).
+    Returns dict(boards[p,16] i32, last_moves[p,2] i16, z[p] i8 outcome for the side to move, game[p] i64, starts[n] i64)."""
+    torch = _torch()
+    boards = _as_board_tensor(boards)
+    n = boards.shape[0]
+    lengths = games["length"]
+    starts = torch.cumsum(lengths.to(torch.int64), 0) - lengths.to(torch.int64)
+    total = int(lengths.to(torch.int64).sum().item())
+    dev = boards.device
+    out = {"boards": torch.empty((total, BOARD_WORDS), dtype=torch.int32, device=dev),
+           "last_moves": torch.empty((total, 2), dtype=torch.int16, device=dev),
+           "z": torch.empty((total,), dtype=torch.int8, device=dev), "starts": starts,
+           "game": torch.repeat_interleave(torch.arange(n, device=dev), lengths.to(torch.int64))}
+    moves = games["moves"]
+    _check(lib().gk_expand_games(_ptr(boards), _ptr(moves), _ptr(lengths), _ptr(games["winner"]), n, int(moves.shape[1]), _ptr(starts),
+                                 _ptr(out["boards"]), _ptr(out["last_moves"]), _ptr(out["z"]), _stream_ptr(stream)))
+    return out
+
+
 def rollout_batch(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_base=0, want_trace=False, stream=None):
     """Random playouts. Returns dict(wdb[n,3] i32 = {white, draw, black}, winners[n,R] i8, lengths[n,R] u8)."""
     torch = _torch()

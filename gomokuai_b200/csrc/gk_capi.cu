@@ -613,6 +613,18 @@ gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last
     return GK_OK;
 }
 
+gk_status gk_expand_games(const uint32_t* d_boards0, const int16_t* d_moves, const int16_t* d_lengths, const int8_t* d_winners,
+                          int n, int max_moves, const int64_t* d_starts, uint32_t* d_out_boards, int16_t* d_out_last_moves,
+                          int8_t* d_out_z, void* stream) {
+    if (gk_status s = require_device()) return s;
+    if (n < 0 || max_moves <= 0 || (n > 0 && (!d_boards0 || !d_moves || !d_lengths || !d_starts || !d_out_boards)))
+        return fail(GK_ERR_INVALID, "bad arguments");
+    gk::ExpandArgs a{ d_boards0, d_moves, d_lengths, d_winners, n, max_moves, reinterpret_cast<const long long*>(d_starts),
+                      d_out_boards, d_out_last_moves, d_out_z };
+    GK_CUDA(gk::launch_expand_games(a, static_cast<cudaStream_t>(stream)));
+    return GK_OK;
+}
+
 // ---- NCCL, resolved at run time ---------------------------------------------------------------------------
 namespace {
 struct NcclId128 { char b[128]; };                                    // ncclUniqueId: passed by value (nccl.h)

@@ -154,7 +154,41 @@ encode_states_kernel(EncodeArgs a) {
     }
 }
 
+// Self-play bookkeeping: the positions a batch of games went through.  Game g started from boards0[g] and played
+// moves[g][0 .. length[g]); the position BEFORE ply k goes to out_boards[starts[g] + k], with the two moves that led
+// to it in out_last (what Board.encoded_states() reads from the move record, game_ext.hpp:96-101) and the game's
+// outcome from the view of the side to move in out_z (the z of an AlphaZero-style sample).  One warp per game.
+__global__ void expand_games_kernel(ExpandArgs a) {
+    const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= a.n) return;
+    uint32_t w = lane < kBoardWords ? __ldg(a.boards0 + g * kBoardWords + lane) : 0u;
+    const int nb = __reduce_add_sync(0xffffffffu, __popc(w & 0x55555555u & ~(w >> 1)));
+    const int nw = __reduce_add_sync(0xffffffffu, __popc((w >> 1) & 0x55555555u & ~w));
+    uint32_t colour = nb == nw ? 1u : 2u;                                   // black moves first (Game.h:128)
+    const int len = a.lengths[g];
+    const long long start = a.starts[g];
+    const int winner = a.winners ? a.winners[g] : 0;
+    int last1 = -1, last2 = -1;
+    for (int k = 0; k < len; ++k) {
+        const long long o = start + k;
+        if (lane < kBoardWords) a.out_boards[o * kBoardWords + lane] = w;
+        if (a.out_last && lane < 2) a.out_last[o * 2 + lane] = (int16_t)(lane == 0 ? last1 : last2);
+        if (a.out_z && lane == 0) a.out_z[o] = (int8_t)(colour == 1u ? winner : -winner);
+        const int cell = a.moves[g * a.max_moves + k];
+        if (lane == (cell >> 4)) w |= colour << ((cell & 15) * 2);
+        last2 = last1; last1 = cell;
+        colour ^= 3u;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_expand_games(const ExpandArgs& a, cudaStream_t stream) {
+    if (a.n <= 0) return cudaSuccess;
+    expand_games_kernel<<<(unsigned)((a.n + 7) / 8), 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_encode(const EncodeArgs& a, int sm_count, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;

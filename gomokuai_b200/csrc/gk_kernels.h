@@ -55,6 +55,13 @@ struct EncodeArgs {
 };
 cudaError_t launch_encode(const EncodeArgs& a, int sm_count, cudaStream_t stream);
 
+struct ExpandArgs {
+    const uint32_t* boards0; const int16_t* moves; const int16_t* lengths; const int8_t* winners;   // winners may be null
+    long long n; int max_moves; const long long* starts;                                            // starts: exclusive prefix sum of lengths
+    uint32_t* out_boards; int16_t* out_last; int8_t* out_z;                                          // out_last / out_z may be null
+};
+cudaError_t launch_expand_games(const ExpandArgs& a, cudaStream_t stream);
+
 // gk_peaks.cu: sustained warp instructions per second of a register-only stream (mode 0 LOP3, 1 IMAD, 2 both 1:1)
 cudaError_t measure_issue_peak(int mode, int sm_count, int iters, double* warp_inst_per_s, cudaStream_t stream);
 

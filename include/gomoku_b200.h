@@ -199,6 +199,16 @@ gk_status gk_rollout_injected(const uint32_t* d_boards, int n, int rollouts_per_
 gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last_moves, int n, int augment,
                                  uint8_t* d_planes, const float* d_probs, float* d_probs_out, void* stream);
 
+/* The positions a batch of finished games went through, ready for gk_encode_states_batch (self-play samples; the
+ * reference collects them move by move in network/data_helper.py:11-33).  Game g started from d_boards0[g] and
+ * played d_moves[g][0 .. d_lengths[g]) (the outputs of gk_guided_rollout_batch); d_starts int64[n] is the exclusive
+ * prefix sum of the lengths.  The position before ply k of game g is written to d_out_boards[d_starts[g] + k],
+ * d_out_last_moves (nullable) receives {last move, second-to-last move} of that position (-1 = none, counted from the
+ * start position) and d_out_z (nullable, needs d_winners) the game's outcome from the view of its side to move. */
+gk_status gk_expand_games(const uint32_t* d_boards0, const int16_t* d_moves, const int16_t* d_lengths, const int8_t* d_winners,
+                          int n, int max_moves, const int64_t* d_starts, uint32_t* d_out_boards, int16_t* d_out_last_moves,
+                          int8_t* d_out_z, void* stream);
+
 /* ---- root-parallel exchange (BASELINE config 4) -------------------------------------------------------
  * The only collective of the path: one allreduce(sum) of the int64[3][225] root statistics per move
  * ([0] visits, [1] black-won, [2] white-won rollouts per root child) over NCCL (NVLink / NVSwitch).

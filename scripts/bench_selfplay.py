@@ -1,6 +1,6 @@
 """BASELINE config 5: self-play data generation with pattern-guided rollouts -- G concurrent games per GPU,
-every game played to its end inside one kernel (gk_guided_rollout_batch, mode "sample"), then the feature
-planes of every visited position (gk_encode_states_batch).  Reports games/s and moves/s; weak scaling, no
+every game played to its end inside one kernel (gk_guided_rollout_batch, mode "sample"), then every visited
+position with its outcome (gk_expand_games) and its feature planes (gk_encode_states_batch).  Reports games/s and moves/s; weak scaling, no
 collective on the data path.
 
     python scripts/bench_selfplay.py --games 8192
@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--games", type=int, default=8192, help="concurrent games per GPU")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--mode", default="sample")
+ap.add_argument("--augment", action="store_true", help="emit the 8 rotations / reflections of every sample")
 ap.add_argument("--from-synth", action="store_true", help="start from the synthetic mid-game set instead of empty boards")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -37,7 +38,8 @@ for it in range(args.steps + 2):
             dist.barrier()
         torch.cuda.synchronize(); ev[0].record()
     res = gk.guided_rollout_batch(d_boards, mode=args.mode, key=gk.SYNTH_KEY + it, game_base=rank * args.games)
-    planes = gk.encode_states_batch(res["final_boards"], res["moves"][:, :2].contiguous())   # terminal positions' planes
+    ex = gk.expand_games(d_boards, res)                                      # every visited position, its last moves, its z
+    planes = gk.encode_states_batch(ex["boards"], ex["last_moves"], augment=args.augment)   # the training samples' planes
 ev[1].record(); torch.cuda.synchronize()
 ms = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], dtype=torch.float64, device="cuda")
 moves = torch.tensor([float(res["length"].float().sum().item())], dtype=torch.float64, device="cuda")
@@ -48,7 +50,9 @@ if rank == 0:
     print(json.dumps({"metric": "self-play games/sec (pattern-guided, 15x15)", "n_gpus": world, "games_per_gpu": args.games, "mode": args.mode,
                       "start": "synthetic mid-game" if args.from_synth else "empty board", "ms_per_batch": float(ms.item()),
                       "value": world * args.games / float(ms.item()) * 1e3, "unit": "games/s",
-                      "moves_per_s": float(moves.item()) / float(ms.item()) * 1e3, "mean_game_length": float(moves.item()) / (world * args.games),
+                      "moves_per_s": float(moves.item()) / float(ms.item()) * 1e3,
+                      "samples_per_s": float(moves.item()) * (8 if args.augment else 1) / float(ms.item()) * 1e3,
+                      "pipeline": "guided_rollout_batch -> expand_games -> encode_states_batch (planes of every visited position)", "mean_game_length": float(moves.item()) / (world * args.games),
                       "black_win_rate_rank0": float((w == 1).mean()), "white_win_rate_rank0": float((w == -1).mean())}))
 if world > 1:
     dist.destroy_process_group()

@@ -67,3 +67,38 @@ def test_gpu_guided_max_moves_and_determinism(gpu):
     c = gpu.guided_rollout_batch(boards[32:], mode="sample", key=KEY, game_base=32)
     assert np.array_equal(b["moves"].cpu().numpy()[32:], c["moves"].cpu().numpy())   # independent of batch split
     assert np.array_equal(b["winner"].cpu().numpy()[32:], c["winner"].cpu().numpy())
+
+
+def test_gpu_expand_games_replays_every_ply(gpu):
+    """gk_expand_games: the position before every ply of every game, its two last moves and the outcome for the side
+    to move -- against a plain replay of the move lists; the planes of those positions are Board.encoded_states()."""
+    import torch
+    from oracle import pyoracle as po
+    boards = gpu.synth_positions(40, 48, want_moves=False)[0]
+    boards[:8] = 0                                              # some games from the empty board
+    g = gpu.guided_rollout_batch(boards, mode="sample", key=5)
+    ex = gpu.expand_games(boards, g)
+    torch.cuda.synchronize()
+    lengths = g["length"].cpu().numpy().astype(int); moves = g["moves"].cpu().numpy(); winner = g["winner"].cpu().numpy()
+    out_b = ex["boards"].cpu().numpy().view(np.uint32); out_l = ex["last_moves"].cpu().numpy(); out_z = ex["z"].cpu().numpy()
+    assert len(out_b) == lengths.sum() and ex["game"].cpu().numpy().tolist() == np.repeat(np.arange(48), lengths).tolist()
+    row = 0
+    for i in range(48):
+        cells = gpu.unpack_boards(boards[i:i + 1])[0].astype(int).copy()
+        black = int((cells == 1).sum() == (cells == 2).sum())
+        last = [-1, -1]
+        for k in range(lengths[i]):
+            assert np.array_equal(gpu.unpack_boards(out_b[row:row + 1])[0], cells)
+            assert out_l[row].tolist() == last and out_z[row] == (winner[i] if black else -winner[i])
+            c = int(moves[i, k])
+            assert cells[c] == 0
+            cells[c] = 1 if black else 2
+            last = [c, last[0]]
+            black ^= 1
+            row += 1
+        assert np.array_equal(gpu.unpack_boards(g["final_boards"][i:i + 1].cpu().numpy().view(np.uint32))[0], cells)
+    # the planes of one game from the empty board equal the restated Board.encoded_states() of its prefixes
+    planes = gpu.encode_states_batch(ex["boards"], ex["last_moves"]).cpu().numpy()
+    s0 = int(ex["starts"][0])
+    for k in range(min(lengths[0], 12)):
+        assert np.array_equal(planes[s0 + k].reshape(6, 15, 15), po.encoded_states([int(m) for m in moves[0, :k]]))
