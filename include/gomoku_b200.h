@@ -200,7 +200,7 @@ gk_status gk_encode_states_batch(const uint32_t* d_boards, const int16_t* d_last
                                  uint8_t* d_planes, const float* d_probs, float* d_probs_out, void* stream);
 
 /* The positions a batch of finished games went through, ready for gk_encode_states_batch (self-play samples; the
- * reference collects them move by move in network/data_helper.py:11-33).  Game g started from d_boards0[g] and
+ * reference collects them move by move in dual_play, agents/utils.py:29-57).  Game g started from d_boards0[g] and
  * played d_moves[g][0 .. d_lengths[g]) (the outputs of gk_guided_rollout_batch); d_starts int64[n] is the exclusive
  * prefix sum of the lengths.  The position before ply k of game g is written to d_out_boards[d_starts[g] + k],
  * d_out_last_moves (nullable) receives {last move, second-to-last move} of that position (-1 = none, counted from the
