@@ -278,19 +278,26 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
     const uint32_t occ = mine | __shfl_sync(0xffffffffu, mine, lane < 15 ? lane + 15 : lane - 15);   // occupancy of row y on lanes y and 15 + y
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
     float n2 = 0.f;
+    // branch-free body: every lane computes and stores (lanes 30, 31 into the two spare words behind the maps)
+    const bool live = lane < 30;
+    const uint32_t xbit = live ? 1u << dx : 0u;                    // 0: lanes 30, 31 always read "open" but their w7 slices are empty
+    float* dst = live ? dwv + dc * kCells + dx : dwv + 2 * kCells + (lane - 30);
+    const int dst_step = live ? kWidth : 0;
+    const int src0 = 15 * dc;
 #pragma unroll 1
     for (int y = 0; y < kHeight + 3; ++y) {
-        uint32_t row = __shfl_sync(0xffffffffu, mine, 15 * dc + min(y, kHeight - 1));
-        if (y >= kHeight) row = 0;                                  // flushing steps: slice 0 looks up { 0, 0 }
+        uint32_t row = __shfl_sync(0xffffffffu, mine, src0 + y);    // y >= 15 reads some other lane: replaced by an empty row
+        row = (y < kHeight && live) ? row : 0u;                     // flushing steps: slice 0 looks up { 0, 0 }
         const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;             // cells dx - 3 .. dx + 3 of row y
         const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
         const uint32_t full = w0 + t3;                              // row y - 3 has seen rows y - 6 .. y
         w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
-        if (y >= 3) {
+        if (y >= 3) {                                               // warp-uniform
             const uint32_t orow = __shfl_sync(0xffffffffu, occ, y - 3);
-            const bool open = lane < 30 && ((orow >> dx) & 1u) == 0u;
-            const float v = open ? (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu)) : 0.f;
-            if (lane < 30) dwv[dc * kCells + (y - 3) * kWidth + dx] = v;
+            float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
+            v = (orow & xbit) ? 0.f : v;                            // occupied cells are filtered to 0 (DensityWeight's max(x, 0))
+            *dst = v;
+            dst += dst_step;
             n2 += v * v;
         }
     }
