@@ -174,11 +174,11 @@ __device__ __forceinline__ void anti_cells(const uint32_t* board, uint32_t* dfla
             const PatRec rec = s_patrec[pid];
             const int off = i - int(er_prev(er, k)) - 6;                        // `cell` is the off-th char from the pattern's end
             if (pr_cclass(rec.w0) != cclass || off < 0 || off >= int(pr_len(rec.w0))) continue;   // HasCovered, :22-25
-            bool on_key = false;                                                // `cell` must sit on a '_'
+            // `cell` must sit on a '_': one of the four cell nibbles equals 8 | off (unused nibbles are 0 and cannot match);
+            // a nibble of x is zero iff it matches -- the has-a-zero-nibble test replaces a loop over the cells
+            const uint32_t x = (rec.w0 & 0xffffu) ^ ((8u | uint32_t(off)) * 0x1111u);
+            if (((x - 0x1111u) & ~x & 0x8888u) == 0) continue;
             uint32_t cells = rec.w0;
-            for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) on_key = on_key || (cells & 15u) == (8u | uint32_t(off));
-            if (!on_key) continue;
-            cells = rec.w0;
             for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) {
                 const int j = int(cells & 7u);
                 if (j != off) {
