@@ -15,7 +15,7 @@
 //   phase 3  emission scatter: the lists are concatenated by a prefix sum and entry i of the
 //            concatenation goes to lane i % 32 (binary search over 32 prefix counts), so the
 //            work is balanced whatever lines the stones sit on; pattern scores go to the '_' / '^'
-//            cells with shared-memory atomics, totals are bumped, saturating per-cell flags set
+//            cells with shared-memory atomics, totals are bumped, per-cell pattern counts kept
 //   phase 4  compounds (double-three / four-three / double-four, Pattern.cpp:418-550) from the flags;
 //            the 13-symbol window rescans of Compound::updateAntis are spread one per lane
 //   phase 5  coalesced 128-bit store of the four 225-cell score maps + totals + winner
@@ -51,7 +51,7 @@ constexpr int kPrefixHalves = 40;              // 33 used: prefix[j] = emissions
 // Per-warp shared-memory block; the emission lists (32 lanes x list_cap uint16) follow it.
 struct WarpSmem {
     int scores[kScoreWords];                   // [group][cell]
-    uint32_t flags[kFlagWords];                // [cell][player grp]: 3 classes x 4 dirs x 2-bit unary count
+    uint32_t flags[kFlagWords];                // [cell][player grp]: 3 classes x 4 dirs x 2-bit count (0..2)
     uint32_t board[kBoardSmem];
     uint32_t totals[kTotalWords];
     uint16_t prefix[kPrefixHalves];
@@ -104,7 +104,8 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
     int* self = ws.scores + black * 3 * kCells;                                 // Group(f, f)
     int* rival = ws.scores + (black + 1) * kCells;                              // Group(f, -f)
     const uint32_t ncells = pr_ncells(rec.w0);
-    // compound classes keep saturating per-cell flags (Record::set: 00 -> 01 -> 11, :395-400); lo = 0 for the other patterns
+    // compound classes count their '_' cells per direction (Record::set's saturating 00 -> 01 -> 11, :395-400, as a binary
+    // count: an exhaustive enumeration of lines shows it never passes 2); lo = 0 for the other patterns
     const uint32_t cclass = pr_cclass(rec.w0);
     const uint32_t lo = cclass ? 1u << (cclass * 8 - 8 + dir * 2) : 0u;
 #pragma unroll
@@ -117,7 +118,7 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
                 atomicAdd(&self[cell], score);
                 if (lo) {
                     uint32_t* word = &ws.flags[cell * 2 + black];
-                    if (atomicOr(word, lo) & lo) atomicOr(word, lo << 1);
+                    atomicAdd(word, lo);                                        // 2-bit BINARY count per (class, direction); it never exceeds 2 (theorem T2)
                 }
             }
         }
@@ -210,7 +211,7 @@ __device__ __forceinline__ void compound_at(int* scores, uint32_t* totals32, int
         const uint32_t cls = c1 ? 1u : c2 ? 2u : c3 ? 3u : 0u;                  // LiveThree > DeadThree > LiveTwo
         if (!cls) continue;
         const uint32_t bits = cls == 1u ? c1 : cls == 2u ? c2 : c3;
-        const int count = bits == 3u ? 2 : 1, cond = cls == 3u ? 1 : 2;
+        const int count = bits == 2u ? 2 : 1, cond = cls == 3u ? 1 : 2;   // bits: binary count 1 or 2 (Record::set's unary 01 / 11)
         l3 += cls == 1u;
         const uint32_t task = uint32_t(cell) | black << 8 | dir << 9 | cls << 11 | 1u << 13;
 #pragma unroll
@@ -632,11 +633,14 @@ ac_eval_kernel(EvalArgs a) {
                 const int cell = r * 32 + lane;
                 // cheap necessary condition first: a word with fewer than two raw bits cannot pass Compound::Test
                 const uint2 f = f2[cell < kCells ? cell : kCells];                  // flags[450..451] stay zero
-                const bool maybe = ((f.x & (f.x - 1)) | (f.y & (f.y - 1))) != 0;
+                const bool maybe = (((f.x & (f.x - 1)) | (f.y & (f.y - 1))) | ((f.x | f.y) & 0xaaaaaau)) != 0;   // two fields set, or a count of 2
                 const uint32_t m = __ballot_sync(0xffffffffu, maybe);
                 if (m) {                                                            // rare: a few cells per board
-                    const uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu;   // Compound::Test, Pattern.cpp:424-433
-                    const uint32_t bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
+                    // Compound::Test, Pattern.cpp:424-433: per direction the classes' counts are OR-ed (01 | 10 = 11 reads as
+                    // "two", like the reference's unary 11) and a binary 10 is widened to 11 before the two-bits test
+                    uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu, bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
+                    bw0 |= (bw0 >> 1) & 0x55u;
+                    bw1 |= (bw1 >> 1) & 0x55u;
                     const bool h0 = (bw0 & (bw0 - 1)) != 0, h1 = (bw1 & (bw1 - 1)) != 0;
                     const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
                     if (h0) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
