@@ -46,7 +46,6 @@ constexpr int kScoreWords = 4 * kCells;        // 900
 constexpr int kFlagWords = 2 * kCells + 2;     // 452 (16-byte multiple)
 constexpr int kBoardSmem = 20;                 // 17 words used (cells up to 271 read as pad)
 constexpr int kTotalWords = 24;                // 16 pattern + 6 compound + spare
-constexpr int kPrefixHalves = 40;              // 33 used: prefix[j] = emissions held by lanes < j
 
 // Per-warp shared-memory block; the emission lists (32 lanes x list_cap uint16) follow it.
 struct WarpSmem {
@@ -54,7 +53,6 @@ struct WarpSmem {
     uint32_t flags[kFlagWords];                // [cell][player grp]: 3 classes x 4 dirs x 2-bit count (0..2)
     uint32_t board[kBoardSmem];
     uint32_t totals[kTotalWords];
-    uint16_t prefix[kPrefixHalves];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp block must keep 16-byte alignment");
 
@@ -601,17 +599,19 @@ ac_eval_kernel(EvalArgs a) {
                 const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += up;
             }
-            ws.prefix[lane + 1] = (uint16_t)incl;
-            if (lane == 0) ws.prefix[0] = 0;
             const int total = int(__shfl_sync(0xffffffffu, incl, 31));
-            __syncwarp();
-            for (int i = lane; i < total; i += 32) {
-                int j = ws.prefix[16] <= i ? 16 : 0;                            // owner lane: prefix[j] <= i < prefix[j + 1]
-                if (ws.prefix[j + 8] <= i) j += 8;
-                if (ws.prefix[j + 4] <= i) j += 4;
-                if (ws.prefix[j + 2] <= i) j += 2;
-                if (ws.prefix[j + 1] <= i) j += 1;
-                const uint32_t ent = lists[j * cap + (i - int(ws.prefix[j]))];
+            const int excl = int(incl) - int((lp - list_addr) >> 1);            // emissions held by the lanes below this one
+            __syncwarp();                                                       // the lanes' lists are complete
+            for (int i0 = 0; i0 < total; i0 += 32) {                            // warp-uniform trip count: the search shuffles
+                const int i = i0 + lane;
+                int j = __shfl_sync(0xffffffffu, excl, 16) <= i ? 16 : 0;       // owner lane: excl[j] <= i < excl[j + 1], by binary
+                if (__shfl_sync(0xffffffffu, excl, j + 8) <= i) j += 8;         // search over the prefix counts in the lanes' registers
+                if (__shfl_sync(0xffffffffu, excl, j + 4) <= i) j += 4;
+                if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
+                if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
+                const int first = __shfl_sync(0xffffffffu, excl, j);
+                if (i >= total) continue;
+                const uint32_t ent = lists[j * cap + (i - first)];
                 const uint32_t er = s_erec[ent >> 6];
                 const uint32_t inf = __ldg(a.tape_info + (ent & 63u) * 32u + uint32_t(j));
                 const uint32_t dir = (inf >> 9) & 3u;
