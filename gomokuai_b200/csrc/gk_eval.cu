@@ -106,12 +106,16 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
     // count: an exhaustive enumeration of lines shows it never passes 2); lo = 0 for the other patterns
     const uint32_t cclass = pr_cclass(rec.w0);
     const uint32_t lo = cclass ? 1u << (cclass * 8 - 8 + dir * 2) : 0u;
+    // decisive flags (policy-head variants): update_pose marks '_' cells for both perspectives, '^' cells for the rival's, :153-161
+    const uint32_t d_rival = (dflags && type >= 4u) ? 1u << ((type - 4u) * 4u + black + 1u) : 0u;
+    const uint32_t d_both = d_rival | ((dflags && type >= 4u) ? 1u << ((type - 4u) * 4u + black * 3u) : 0u);
 #pragma unroll
     for (uint32_t s = 0; s < 4; ++s) {                                          // at most four scored cells: straight-line, predicated
         const uint32_t nib = (rec.w0 >> (4 * s)) & 15u;
         const int cell = vend - int(nib & 7u) * stride;
         if (s < ncells) {
             atomicAdd(&rival[cell], score);                                     // '_' and '^', :158-161
+            if (d_rival) atomicOr(&dflags[cell], (nib & 8u) ? d_both : d_rival);
             if (nib & 8u) {
                 atomicAdd(&self[cell], score);
                 if (lo) {
@@ -120,12 +124,6 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
                 }
             }
         }
-    }
-    if (dflags && type >= 4u) {                                                 // update_pose: '_' both perspectives, '^' the rival's, :153-161
-        const uint32_t rival_bit = 1u << ((type - 4u) * 4u + black + 1u), self_bit = 1u << ((type - 4u) * 4u + black * 3u);
-        uint32_t cells = rec.w0;
-        for (uint32_t n = ncells; n != 0; --n, cells >>= 4)
-            atomicOr(&dflags[vend - int(cells & 7u) * stride], (cells & 8u) ? (rival_bit | self_bit) : rival_bit);
     }
     return 0;
 }
