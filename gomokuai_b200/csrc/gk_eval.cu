@@ -414,26 +414,31 @@ __device__ GK_HEADS_INLINE int select_move(const float* prob, int lane, int mode
         }
         return best > 0.f ? arg : -1;
     }
-    uint32_t total = 0;
-#pragma unroll 1
-    for (int c = lane; c < kCells; c += 32) total += uint32_t(prob[c] * 1048576.f + 0.5f);
-    total = __reduce_add_sync(0xffffffffu, total);
+    // lane l owns the eight consecutive cells 8 l .. 8 l + 7, so ONE warp scan of the lanes' sums orders all 225 weights
+    const int c0 = lane * 8;
+    uint32_t w[8], mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        w[k] = c0 + k < kCells ? uint32_t(prob[c0 + k] * 1048576.f + 0.5f) : 0u;
+        mine += w[k];
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (total == 0) return -1;
     const uint32_t r = __umulhi(rnd, total);
-    uint32_t base = 0;
     int chosen = 0x7fffffff;
-#pragma unroll 1
-    for (int k = 0; k < 8; ++k) {                                  // cells 32 k .. 32 k + 31 in index order
-        const int c = lane + 32 * k;
-        const uint32_t w = c < kCells ? uint32_t(prob[c] * 1048576.f + 0.5f) : 0u;
-        uint32_t incl = w;
+    uint32_t run = incl - mine;                                    // weight of all cells below this lane's
+    if (run <= r && r < incl) {                                    // exactly one lane
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
+        for (int k = 0; k < 8; ++k) {                              // the first cell whose running sum exceeds r
+            run += w[k];
+            if (run > r && chosen == 0x7fffffff) chosen = c0 + k;
         }
-        if (w != 0 && base + incl > r && base + incl - w <= r) chosen = c;
-        base += __shfl_sync(0xffffffffu, incl, 31);
     }
     return __reduce_min_sync(0xffffffffu, chosen);
 }
