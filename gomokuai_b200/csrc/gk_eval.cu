@@ -240,6 +240,7 @@ __device__ __forceinline__ void compound_at(int* scores, uint32_t* totals32, int
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 constexpr int kDflagWords = 228;                                               // 225 used (16-byte multiple)
+// guided playouts do not filter (no decisive flags): the same 912 bytes hold their density accumulators, uint16 [2][225] + idle-lane slots
 __host__ __device__ inline size_t warp_bytes(int list_cap, bool heads) {
     return sizeof(WarpSmem) + size_t(list_cap) * 64 + (heads ? kDflagWords * 4 : 0);
 }
@@ -260,7 +261,7 @@ __host__ __device__ inline size_t warp_bytes(int list_cap, bool heads) {
 //   dwv  [2][225] floats over ws.flags: DensityWeight numerators 3W / (1 + 2N), then normalised
 //   prob [225]    floats over the emission lists: the move probabilities
 __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const uint16_t* s_lut, uint32_t mine, int lane,
-                                          float* value_out, int& n_stones, int& to_move) {
+                                          float* value_out, int& n_stones, int& to_move, uint16_t* dacc, bool dacc_valid) {
     float* dwv = reinterpret_cast<float*>(ws.flags);
     const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
     const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
@@ -281,21 +282,40 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
     float* dst = live ? dwv + dc * kCells + dx : dwv + 2 * kCells + (lane - 30);
     const int dst_step = live ? kWidth : 0;
     const int src0 = 15 * dc;
+    // Guided playouts keep the packed (count, weight) accumulators of every cell in shared memory (`dacc`): a game adds
+    // one stone per evaluation, so after the first full pass only the 7 x 7 neighbourhood of the new stone is updated
+    // (by the kernel, when the move is made) and this pass just turns the accumulators into weights.
+    uint16_t* acc_p = dacc ? dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30)) : nullptr;
+    if (dacc != nullptr && dacc_valid) {
 #pragma unroll 1
-    for (int y = 0; y < kHeight + 3; ++y) {
-        uint32_t row = __shfl_sync(0xffffffffu, mine, src0 + y);    // y >= 15 reads some other lane: replaced by an empty row
-        row = (y < kHeight && live) ? row : 0u;                     // flushing steps: slice 0 looks up { 0, 0 }
-        const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;             // cells dx - 3 .. dx + 3 of row y
-        const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
-        const uint32_t full = w0 + t3;                              // row y - 3 has seen rows y - 6 .. y
-        w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
-        if (y >= 3) {                                               // warp-uniform
-            const uint32_t orow = __shfl_sync(0xffffffffu, occ, y - 3);
+        for (int y = 0; y < kHeight; ++y) {
+            const uint32_t full = live ? uint32_t(*acc_p) : 0u;
+            acc_p += dst_step;
+            const uint32_t orow = __shfl_sync(0xffffffffu, occ, y);
             float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
-            v = (orow & xbit) ? 0.f : v;                            // occupied cells are filtered to 0 (DensityWeight's max(x, 0))
+            v = (orow & xbit) ? 0.f : v;
             *dst = v;
             dst += dst_step;
             n2 += v * v;
+        }
+    } else {
+#pragma unroll 1
+        for (int y = 0; y < kHeight + 3; ++y) {
+            uint32_t row = __shfl_sync(0xffffffffu, mine, src0 + y);    // y >= 15 reads some other lane: replaced by an empty row
+            row = (y < kHeight && live) ? row : 0u;                     // flushing steps: slice 0 looks up { 0, 0 }
+            const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;             // cells dx - 3 .. dx + 3 of row y
+            const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
+            const uint32_t full = w0 + t3;                              // row y - 3 has seen rows y - 6 .. y
+            w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
+            if (y >= 3) {                                               // warp-uniform
+                const uint32_t orow = __shfl_sync(0xffffffffu, occ, y - 3);
+                float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
+                v = (orow & xbit) ? 0.f : v;                            // occupied cells are filtered to 0 (DensityWeight's max(x, 0))
+                *dst = v;
+                dst += dst_step;
+                n2 += v * v;
+                if (dacc != nullptr) { *acc_p = uint16_t(full); acc_p += dst_step; }
+            }
         }
     }
     float n2w = lane < 15 ? n2 : 0.f, n2b = lane >= 15 ? n2 : 0.f;
@@ -476,7 +496,8 @@ ac_eval_kernel(EvalArgs a) {
     const int cap = a.list_cap;
     WarpSmem& ws = *reinterpret_cast<WarpSmem*>(s_warps + size_t(warp) * warp_bytes(cap, kHeads));
     uint16_t* lists = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(&ws) + sizeof(WarpSmem));   // [lane][cap]
-    uint32_t* dflags = kHeads ? reinterpret_cast<uint32_t*>(lists + 32 * cap) : nullptr;
+    uint32_t* dflags = (kHeads && !kGuided) ? reinterpret_cast<uint32_t*>(lists + 32 * cap) : nullptr;
+    uint16_t* dacc = kGuided ? reinterpret_cast<uint16_t*>(lists + 32 * cap) : nullptr;   // guided: density accumulators instead
     const uint32_t lt = lanemask_lt();
     const uint32_t emit_thr = uint32_t(a.n_clones) * 8u;
     // shared-window addresses, made opaque so the compiler keeps them in registers instead of
@@ -538,7 +559,7 @@ ac_eval_kernel(EvalArgs a) {
             int4* z = reinterpret_cast<int4*>(ws.scores);
             for (int i = lane; i < (kScoreWords + kFlagWords) / 4; i += 32) z[i] = make_int4(0, 0, 0, 0);   // scores + flags are contiguous
             if (lane < kTotalWords) ws.totals[lane] = 0;
-            if (kHeads) for (int i = lane; i < kDflagWords; i += 32) dflags[i] = 0;
+            if (kHeads && !kGuided) for (int i = lane; i < kDflagWords; i += 32) dflags[i] = 0;
         }
         __syncwarp();
 
@@ -693,7 +714,7 @@ ac_eval_kernel(EvalArgs a) {
         if (kHeads) {
             float* prob = reinterpret_cast<float*>(lists);                   // 225 floats over the (dead) emission lists
             int n_stones, to_move;
-            policy_heads(ws, prob, s_lut, mine, lane, (a.value && !kGuided) ? a.value + b : nullptr, n_stones, to_move);
+            policy_heads(ws, prob, s_lut, mine, lane, (a.value && !kGuided) ? a.value + b : nullptr, n_stones, to_move, dacc, kGuided && played > 0);
             if (!kGuided) {
                 if (a.decisive) decisive_filter(ws, dflags, prob, to_move, lane);  // TraditionalPolicy::hybridSimulate, Traditional.h:52-53
                 if (a.probs)
@@ -715,6 +736,16 @@ ac_eval_kernel(EvalArgs a) {
                 if (cell >= 0) {
                     if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
                     if (lane == (cell >> 4)) bw |= (to_move ? 1u : 2u) << ((cell & 15) * 2);
+                    {   // the new stone's contribution to the density accumulators of its colour: cells within 3 rows and columns
+                        const int my = cell / kWidth, mx = cell - my * kWidth, dc = lane >= 15, dx = lane - 15 * dc, j = mx - dx + 3;
+                        if (lane < 30 && dc == to_move && j >= 0 && j < 7) {
+#pragma unroll 1
+                            for (int d = -3; d <= 3; ++d) {
+                                const int y = my + d;
+                                if (y >= 0 && y < kHeight) dacc[dc * kCells + y * kWidth + dx] += s_lut[(d < 0 ? -d : d) * 128 + (1 << j)];
+                            }
+                        }
+                    }
                     ++played;
                     __syncwarp();
                     goto next_move;
