@@ -164,15 +164,20 @@ constexpr uint32_t kSlotStride = kThreads * 4u;                                 
 __device__ __forceinline__ uint32_t play_move(uint32_t my /* shared address of slots[0][tid] */, uint32_t cell_addr /* of the cell LUT */,
                                               Lane& L, uint32_t r) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
+    // Both candidate rows are read up front -- row y, and the next row after it that still has an empty cell (known from the
+    // row mask, cyclically) -- so the fallback needs no second, dependent probe and no divergent branch: in most steps
+    // SOME lane of the warp lands behind its row's last empty cell.
+    uint32_t m = L.rowmask & ~((2u << y) - 1u);
+    if (m == 0) m = L.rowmask;
+    const uint32_t y2 = 31u - __clz(m & (0u - m));
     uint32_t w = lds32(my + y * kSlotStride);
+    const uint32_t w2 = lds32(my + y2 * kSlotStride);
     uint32_t empty = ~(w | (w >> 16)) & 0x7fffu;                                 // empty cells of the row
     uint32_t avail = empty & (0xffffffffu << x);
-    if (avail == 0) {                                                            // first empty cell after r: next row that has one
-        uint32_t m = L.rowmask & ~((2u << y) - 1u);
-        if (m == 0) m = L.rowmask;
-        y = __ffs(m) - 1;
-        w = lds32(my + y * kSlotStride);
-        avail = empty = ~(w | (w >> 16)) & 0x7fffu;
+    if (avail == 0) {                                                            // first empty cell after r: all of row y2's
+        y = y2;
+        w = w2;
+        avail = empty = ~(w2 | (w2 >> 16)) & 0x7fffu;
     }
     const uint32_t xbit = avail & (0u - avail), ybit = 1u << y;                  // 1 << x, 1 << y
     x = 31u - __clz(xbit);
