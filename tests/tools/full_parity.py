@@ -4,10 +4,10 @@
   config 3: ALL 4096 x 4096 rollouts -- per-position win/draw/loss counts against the C restatement of
             Board::getRandomMove / applyMove / checkGameEnd consuming the same Philox stream.
 CPU work is spread over the host cores (workers are forked before CUDA is initialised).
-    python scripts/full_parity.py [--positions N] [--rollout-positions P] [--rollouts R] > profiles/rXX_full_parity.json
+    python tests/tools/full_parity.py [--positions N] [--rollout-positions P] [--rollouts R] > profiles/rXX_full_parity.json
 """
 import argparse, json, multiprocessing as mp, os, sys, time, zlib
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 
 

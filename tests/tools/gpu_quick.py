@@ -1,7 +1,7 @@
 """Quick GPU sanity run (development aid): parity of both kernels against the oracle + first timings."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import gomokuai_b200 as gk
 from oracle import pyoracle as po

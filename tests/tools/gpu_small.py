@@ -1,7 +1,7 @@
 """Tiny end-to-end run of every kernel (for compute-sanitizer)."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import gomokuai_b200 as gk
 from oracle import pyoracle as po
