@@ -69,6 +69,7 @@ def test_gpu_guided_max_moves_and_determinism(gpu):
     assert np.array_equal(b["winner"].cpu().numpy()[32:], c["winner"].cpu().numpy())
 
 
+@pytest.mark.gpu
 def test_gpu_expand_games_replays_every_ply(gpu):
     """gk_expand_games: the position before every ply of every game, its two last moves and the outcome for the side
     to move -- against a plain replay of the move lists; the planes of those positions are Board.encoded_states()."""
