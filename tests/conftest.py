@@ -17,6 +17,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_itemcollected(item):
+    """A test that asks for the `gpu` (or the GPU-backed `core`) fixture IS a gpu test, marked or not: `-m "not gpu"` must
+    never reach it (collection hooks run before the -m filter)."""
+    names = getattr(item, "fixturenames", ())
+    if ("gpu" in names or "core" in names) and item.get_closest_marker("gpu") is None:
+        item.add_marker(pytest.mark.gpu)
+
+
 def encode(s):
     return np.array([ENC[c] for c in s], np.uint8)
 
