@@ -18,10 +18,10 @@ def pytest_configure(config):
 
 
 def pytest_itemcollected(item):
-    """A test that asks for the `gpu` (or the GPU-backed `core`) fixture IS a gpu test, marked or not: `-m "not gpu"` must
-    never reach it (collection hooks run before the -m filter)."""
+    """A test that asks for the `gpu` fixture IS a gpu test, marked or not: `-m "not gpu"` must never reach it
+    (collection hooks run before the -m filter)."""
     names = getattr(item, "fixturenames", ())
-    if ("gpu" in names or "core" in names) and item.get_closest_marker("gpu") is None:
+    if "gpu" in names and item.get_closest_marker("gpu") is None:
         item.add_marker(pytest.mark.gpu)
 
 
