@@ -209,7 +209,8 @@ __device__ __forceinline__ uint32_t play_move(uint32_t my /* shared address of s
     return inc;
 }
 
-template <bool kInjected, int kRefill>
+// kTrace: the caller wants per-rollout winners / lengths (tests, tooling); the counting-only kernel has none of that code
+template <bool kInjected, int kRefill, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 3)
 rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots + 1][kThreads]
@@ -230,7 +231,6 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     Lane L{};
     bool active = false, dead = false;
     uint32_t acc = 0, acc_n = 0;                                                 // packed outcomes / rollouts started since the last flush, of position acc_pos
-    const bool trace = a.winners != nullptr || a.lengths != nullptr;
     uint32_t acc_pos = 0xffffffffu;
     uint32_t rnd[4] = { 0, 0, 0, 0 };
     const uint8_t* inj = nullptr;
@@ -240,7 +240,7 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     auto finish = [&](uint32_t inc) {
         acc += inc;
         if (inc) {
-            if (trace) {
+            if (kTrace) {
                 const size_t g = size_t(L.pos) * a.rollouts_per_pos + L.roll;
                 if (a.winners) a.winners[g] = (int8_t)(inc == kIncBlack ? 1 : inc == kIncWhite ? -1 : 0);
                 if (a.lengths) a.lengths[g] = (uint8_t)(L.start - L.left);
@@ -363,12 +363,13 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images,
         kernel<<<grid, kThreads, smem, stream>>>(a, images);
         return cudaGetLastError();
     };
-    if (a.r_stream) return launch(rollout_kernel<true, kRefillDefault>);
+    if (a.r_stream) return launch(rollout_kernel<true, kRefillDefault, true>);
+    if (a.winners != nullptr || a.lengths != nullptr) return launch(rollout_kernel<false, kRefillDefault, true>);
     switch (refill) {
-        case 4: return launch(rollout_kernel<false, 4>);
-        case 8: return launch(rollout_kernel<false, 8>);
-        case 12: return launch(rollout_kernel<false, 12>);
-        default: return launch(rollout_kernel<false, kRefillDefault>);
+        case 4: return launch(rollout_kernel<false, 4, false>);
+        case 8: return launch(rollout_kernel<false, 8, false>);
+        case 12: return launch(rollout_kernel<false, 12, false>);
+        default: return launch(rollout_kernel<false, kRefillDefault, false>);
     }
 }
 
