@@ -22,6 +22,45 @@ Policy::Policy(SelectFunc f1, ExpandFunc f2, EvalFunc f3, UpdateFunc f4, double 
       backPropogate(f4 ? f4 : [this](Node* node, Board& board, double value) { Default::BackPropogate(this, node, board, value); }),
       c_puct(c_puct) {}
 
+// ---- Node pool ---------------------------------------------------------------------------------------------
+namespace {
+struct NodePool {
+    union Slot { Slot* next; alignas(Node) unsigned char bytes[sizeof(Node)]; };
+    static constexpr std::size_t kBlock = 8192;          // nodes per slab (never returned: trees are rebuilt all the time)
+    std::atomic_flag busy = ATOMIC_FLAG_INIT;            // the engine is single-threaded like the reference; the lock only
+    Slot* free_list = nullptr;                           // makes a stray use from another thread safe
+    std::vector<std::unique_ptr<Slot[]>> slabs;
+    void lock() { while (busy.test_and_set(std::memory_order_acquire)) {} }
+    void unlock() { busy.clear(std::memory_order_release); }
+    void* take() {
+        lock();
+        if (!free_list) {
+            slabs.emplace_back(new Slot[kBlock]);
+            Slot* slab = slabs.back().get();
+            for (std::size_t i = 0; i < kBlock; ++i) { slab[i].next = free_list; free_list = &slab[i]; }
+        }
+        Slot* s = free_list;
+        free_list = s->next;
+        unlock();
+        return s;
+    }
+    void give(void* p) {
+        Slot* s = static_cast<Slot*>(p);
+        lock();
+        s->next = free_list;
+        free_list = s;
+        unlock();
+    }
+};
+NodePool& node_pool() { static NodePool* pool = new NodePool; return *pool; }   // leaked on purpose: nodes may outlive static destruction
+}  // namespace
+
+void* Node::operator new(std::size_t size) { return size == sizeof(Node) ? node_pool().take() : ::operator new(size); }
+void Node::operator delete(void* p, std::size_t size) noexcept {
+    if (!p) return;
+    if (size == sizeof(Node)) node_pool().give(p); else ::operator delete(p);
+}
+
 std::unique_ptr<Node> Policy::createNode(Node* parent, Position pose, Player player, float value, float prob) {
     return std::make_unique<Node>(parent, pose, player, value, prob);
 }

@@ -38,6 +38,12 @@ struct Node {                                        // MCTS.h:25-66
         : parent(parent), position(position), player(player), state_value(value), action_prob(prob) {}
     bool isLeaf() const { return children.empty(); }
     bool isFull(const Board& board) const { return children.size() == board.moveCounts(Player::None); }
+
+    // Nodes come from a pooled free list (row f2 of SURVEY 8f: the reference spends 40-50 % of a playout in operator new,
+    // one make_unique per child, MonteCarlo.hpp:71-80).  Same ownership model -- unique_ptr<Node> children created
+    // through Policy::createNode -- only the allocation behind it changes.
+    static void* operator new(std::size_t size);
+    static void operator delete(void* p, std::size_t size) noexcept;
 };
 
 class Policy {                                       // MCTS.h:69-132
