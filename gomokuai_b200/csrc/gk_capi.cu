@@ -407,6 +407,11 @@ gk_status gk_eval_policy_batch_host(const gk_table* t, const uint32_t* h_boards,
     return policy_host(t, h_boards, n, h_probs, h_value, h_win, 0);
 }
 
+namespace {
+constexpr int kSmallPolicyBatch = 64;
+unsigned char* g_policy_stage = nullptr;     // page-locked: kSmallPolicyBatch x (64 B board + 905 B of results, padded)
+}  // namespace
+
 static gk_status policy_host(const gk_table* t, const uint32_t* h_boards, int n, float* h_probs, float* h_value,
                              int8_t* h_win, int decisive) {
     if (gk_status s = require_device()) return s;
@@ -416,6 +421,27 @@ static gk_status policy_host(const gk_table* t, const uint32_t* h_boards, int n,
     if (chunk == 0) return GK_OK;
     std::lock_guard<std::mutex> lock(g_mutex);
     for (Pipe& p : g_pipes) if (gk_status s = pipe_reserve(p, chunk)) return s;
+    if (n <= kSmallPolicyBatch) {
+        // one MCTS leaf at a time (TraditionalPolicy::hybridSimulate): pure call latency.  The board is read by the kernel
+        // from page-locked staging, probs | value | winner come back in ONE copy, one synchronisation.
+        if (!g_policy_stage) GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_policy_stage), size_t(kSmallPolicyBatch) * (64 + 912), cudaHostAllocDefault));
+        uint32_t* st_boards = reinterpret_cast<uint32_t*>(g_policy_stage);
+        unsigned char* st_out = g_policy_stage + size_t(kSmallPolicyBatch) * 64;
+        std::memcpy(st_boards, h_boards, size_t(n) * 64);
+        Pipe& p = g_pipes[0];
+        float* d_probs = reinterpret_cast<float*>(p.d_scores);
+        float* d_value = d_probs + size_t(n) * 225;
+        int8_t* d_winner = reinterpret_cast<int8_t*>(d_value + n);
+        gk::EvalArgs a = eval_args(t, st_boards, n, nullptr, nullptr, nullptr, d_winner);
+        a.probs = d_probs; a.value = d_value; a.decisive = decisive;
+        GK_CUDA(gk::launch_eval(a, g_sm_count, p.stream));
+        GK_CUDA(cudaMemcpyAsync(st_out, d_probs, size_t(n) * 905, cudaMemcpyDeviceToHost, p.stream));
+        GK_CUDA(cudaStreamSynchronize(p.stream));
+        if (h_probs) std::memcpy(h_probs, st_out, size_t(n) * 900);
+        if (h_value) std::memcpy(h_value, st_out + size_t(n) * 900, size_t(n) * 4);
+        if (h_win) std::memcpy(h_win, st_out + size_t(n) * 904, size_t(n));
+        return GK_OK;
+    }
     int k = 0;
     for (int at = 0; at < n; at += chunk, ++k) {                      // the score buffer of the pipe doubles as probs + value
         Pipe& p = g_pipes[k % kPipes];
