@@ -108,6 +108,9 @@ def _cpu_worker(args):
         r = orc.eval_batch(moves, starts, want_scores=False)        # Evaluator::applyMove replay, the reference's algorithm
         assert r["bad"] == 0
         units = len(starts) - 1
+    elif what == "linescan":
+        orc.linescan_batch(moves, starts)                            # PatternSearch::execute over all 88 line strings of each position
+        units = 88 * (len(starts) - 1)
     else:
         units = 0
         n_roll = extra
@@ -385,11 +388,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     if arm is not None:
         n_c = 6144 * arm.cores                                           # ~4 s per core of evaluator replay
         v, w = arm.run("eval", moves, starts, n_c)
-        cpu_eval = {"value": v, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind,
+        cpu_eval = {"value": v, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind, "per_core": v / arm.cores,
                     "sample": f"first {n_c} of the {n_eval} positions, replayed through Evaluator::applyMove, {w:.1f} s wall"}
+        lv, lw = arm.run("linescan", moves, starts, n_c)                  # the other CPU figure of SURVEY 8d: whole-line scans
+        cpu_eval["full_line_scans_per_s"] = lv
+        cpu_eval["full_line_scan_sample"] = (f"PatternSearch::execute over the 88 padded line strings of the same {n_c} positions "
+                                             f"(no score bookkeeping), {lw:.1f} s wall")
         n_p = 16 * arm.cores                                             # ~3 s per core of rollouts
         v, w = arm.run("rollout", moves, starts, n_p, 32768)
-        cpu_roll = {"value": v, "unit": "rollouts/s", "cores": arm.cores, "kind": arm.kind,
+        cpu_roll = {"value": v, "unit": "rollouts/s", "cores": arm.cores, "kind": arm.kind, "per_core": v / arm.cores,
                     "sample": f"first {n_p} positions x 32768 rollouts, {w:.1f} s wall"}
         arm.close()
 
