@@ -178,3 +178,35 @@ def test_concurrent_streams_do_not_share_scratch(gpu):
         torch.cuda.synchronize()
         for got, want in zip(res, serial):
             assert np.array_equal(_np(got), want)
+
+
+def test_c_abi_argument_errors(gpu):
+    """The C-ABI never throws and never touches memory on bad arguments: negative status + gk_last_error() text."""
+    import ctypes
+    L = gpu.lib()
+    boards = np.zeros((4, 16), np.uint32)
+    wdb = np.zeros((4, 3), np.int32)
+    bp, wp = boards.ctypes.data_as(ctypes.c_void_p), wdb.ctypes.data_as(ctypes.c_void_p)
+    INVALID = -1
+    assert L.gk_rollout_batch_host(None, 4, 8, ctypes.c_uint64(1), 0, 0, wp) == INVALID
+    assert L.gk_rollout_batch_host(bp, -1, 8, ctypes.c_uint64(1), 0, 0, wp) == INVALID
+    assert L.gk_rollout_batch_host(bp, 4, 0, ctypes.c_uint64(1), 0, 0, wp) == INVALID                 # no rollouts
+    assert L.gk_rollout_batch_host(bp, 0, 8, ctypes.c_uint64(1), 0, 0, None) == 0                      # empty batch: nothing to do
+    assert L.gk_rollout_submit_host(-1, bp, 4, 8, ctypes.c_uint64(1), 0, 0, wp) == INVALID
+    assert L.gk_rollout_submit_host(0, bp, 4, 8, ctypes.c_uint64(1), 0, 0, None) == INVALID
+    assert L.gk_rollout_wait(99) == INVALID
+    assert b"slot" in L.gk_last_error()
+    # n * rollouts_per_pos must stay below 2^31 per call (rollout tickets are 32-bit)
+    import torch
+    d = torch.zeros((2, 16), dtype=torch.int32, device="cuda")
+    out = torch.zeros((2, 3), dtype=torch.int32, device="cuda")
+    assert L.gk_rollout_batch(ctypes.c_void_p(d.data_ptr()), 2, 1 << 30, ctypes.c_uint64(1), 0, 0,
+                              ctypes.c_void_p(out.data_ptr()), None, None, None) == INVALID
+    assert L.gk_expand_games(None, None, None, None, 3, 225, None, None, None, None, None) == INVALID
+    assert L.gk_expand_games(None, None, None, None, 0, 225, None, None, None, None, None) == 0
+    v = ctypes.c_double()
+    assert L.gk_measure_issue_peak(7, ctypes.byref(v)) == INVALID and L.gk_measure_issue_peak(0, None) == INVALID
+    st = torch.zeros(10, dtype=torch.int64, device="cuda")
+    assert L.gk_root_allreduce(None, ctypes.c_void_p(st.data_ptr()), None) in (-5, -6)                  # no communicator yet (or no NCCL)
+    # after all that the library still works
+    assert (gpu.rollout_batch_host(boards, 8).sum(1) == 8).all()
