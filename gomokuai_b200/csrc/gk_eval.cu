@@ -13,7 +13,7 @@
 //            (predicated store, no votes); the lists cannot overflow (capacity proven by the
 //            table compiler over all boards)
 //   phase 3  emission scatter: the lists are concatenated by a prefix sum and entry i of the
-//            concatenation goes to lane i % 32 (binary search over 32 prefix counts), so the
+//            concatenation goes to lane i % 32 (binary search by shuffle over the 32 prefix counts), so the
 //            work is balanced whatever lines the stones sit on; pattern scores go to the '_' / '^'
 //            cells with shared-memory atomics, totals are bumped, per-cell pattern counts kept
 //   phase 4  compounds (double-three / four-three / double-four, Pattern.cpp:418-550) from the flags;
@@ -24,7 +24,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstdlib>
 
 #include "gk_format.h"
 #include "gk_kernels.h"
