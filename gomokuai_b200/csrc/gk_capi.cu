@@ -537,6 +537,7 @@ namespace {
 // small synchronous batches (one MCTS leaf at a time, config 1) are pure call latency: they go through page-locked
 // staging that the kernel reads in place (no copy-in operation) and a true DMA copy-out
 constexpr int kSmallBatch = 1024;
+constexpr int kFusedBatch = 16;         // up to this many positions: one fused launch (one CTA per position)
 uint32_t* g_stage_boards = nullptr;     // page-locked, kSmallBatch x 16 words
 int32_t* g_stage_wdb = nullptr;         // page-locked, kSmallBatch x 3
 }  // namespace
@@ -555,6 +556,16 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
             GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_wdb), size_t(kSmallBatch) * 12, cudaHostAllocDefault));
         }
         std::memcpy(g_stage_boards, h_boards, size_t(n) * 64);
+        if (n <= kFusedBatch && rollouts_per_pos > 0 && rollouts_per_pos <= 256) {
+            // one leaf of a single-tree search: ONE launch that reads the staged boards and writes the staged counts
+            gk::RolloutArgs a{};
+            a.boards = g_stage_boards; a.n = n; a.rollouts_per_pos = rollouts_per_pos;
+            a.key_lo = uint32_t(philox_key); a.key_hi = uint32_t(philox_key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos_base;
+            GK_CUDA(gk::launch_rollout_small(a, g_stage_wdb, p.stream));
+            GK_CUDA(cudaStreamSynchronize(p.stream));
+            std::memcpy(h_wdb, g_stage_wdb, size_t(n) * 12);
+            return GK_OK;
+        }
         if (gk_status s = rollout_common(g_stage_boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, p.d_wdb,
                                          nullptr, nullptr, p.stream))
             return s;

@@ -44,6 +44,9 @@ struct RolloutArgs {
 // (one buffer per stream in flight)
 size_t rollout_scratch_bytes(int n);
 cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images, cudaStream_t stream);
+// a handful of positions with at most 256 rollouts each in ONE launch: a.boards and `out` (int32[n][3]) may be page-locked
+// host memory; same streams and counts as launch_rollout
+cudaError_t launch_rollout_small(const RolloutArgs& a, int32_t* out, cudaStream_t stream);
 // number of kernels one launch_rollout call enqueues (slot images + wdb clear, rollouts)
 int rollout_launches(const RolloutArgs& a);
 

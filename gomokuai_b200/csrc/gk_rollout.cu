@@ -51,13 +51,8 @@ __device__ __forceinline__ bool has_five(uint32_t m) {      // five or more cons
 
 // ---- position -> slot image ------------------------------------------------------------------
 // one warp per position; lane l builds slots l, l+32, l+64 (and clears the position's wdb counters)
-__global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, uint32_t* __restrict__ images,
-                                    int32_t* __restrict__ wdb) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    if (wdb && lane < 3) wdb[(size_t)warp * 3 + lane] = 0;
-    const uint32_t* b = boards + (size_t)warp * kBoardWords;
-    uint32_t* img = images + (size_t)warp * kImageWords;
+// `b`: the 16 board words (global or shared memory); `img`: kImageWords words (global or shared)
+__device__ __forceinline__ void build_image(const uint32_t* b, uint32_t* img, int lane) {
     uint32_t any_five = 0;                                   // bit 0: black, bit 1: white
     for (int slot = lane; slot < kSlots; slot += 32) {
         int cell0, stride, len;
@@ -68,7 +63,7 @@ __global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, 
         uint32_t w = 0;
         for (int i = 0; i < len; ++i) {
             const int c = cell0 + i * stride;
-            const uint32_t v = (__ldg(b + (c >> 4)) >> ((c & 15) * 2)) & 3u;
+            const uint32_t v = (b[c >> 4] >> ((c & 15) * 2)) & 3u;
             if (v == 1u) w |= 1u << i;
             else if (v == 2u) w |= 1u << (16 + i);
         }
@@ -83,7 +78,7 @@ __global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, 
         uint32_t w = 0;
         for (int i = 0; i < 15; ++i) {
             const int c = lane * 15 + i;
-            const uint32_t v = (__ldg(b + (c >> 4)) >> ((c & 15) * 2)) & 3u;
+            const uint32_t v = (b[c >> 4] >> ((c & 15) * 2)) & 3u;
             if (v == 1u) { w |= 1u << i; ++blk; }
             else if (v == 2u) { w |= 1u << i; ++wht; }
         }
@@ -100,6 +95,14 @@ __global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, 
         img[kMetaInfo] = empties | to_move << 8 | decided << 9 | wcode << 10;
         img[kMetaRows] = rowmask;
     }
+}
+
+__global__ void build_images_kernel(const uint32_t* __restrict__ boards, int n, uint32_t* __restrict__ images,
+                                    int32_t* __restrict__ wdb) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    if (wdb && lane < 3) wdb[(size_t)warp * 3 + lane] = 0;
+    build_image(boards + (size_t)warp * kBoardWords, images + (size_t)warp * kImageWords, lane);
 }
 
 // ---- Philox4x32-10 ---------------------------------------------------------------------------
@@ -159,10 +162,10 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 
-constexpr uint32_t kSlotStride = kThreads * 4u;                                   // bytes between consecutive slots of one thread
+constexpr uint32_t kSlotStride = kThreads * 4u;                                   // bytes between consecutive slots of one thread (the big kernel)
 
 __device__ __forceinline__ uint32_t play_move(uint32_t my /* shared address of slots[0][tid] */, uint32_t cell_addr /* of the cell LUT */,
-                                              Lane& L, uint32_t r) {
+                                              Lane& L, uint32_t r, const uint32_t kSlotStride = kThreads * 4u /* bytes between a thread's slots */) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
     // Both candidate rows are read up front -- row y, and the next row after it that still has an empty cell (known from the
     // row mask, cyclically) -- so the fallback needs no second, dependent probe and no divergent branch: in most steps
@@ -336,7 +339,70 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
     flush();
 }
 
+// ---- a handful of positions, one launch ----------------------------------------------------------
+// The MCTS mirror simulates ONE leaf per call (RandomPolicy: 5 rollouts): pure latency.  One CTA per position builds the
+// slot image in shared memory, plays one rollout per thread (same Philox streams and the same move code as the big
+// kernel, so the counts are identical) and writes the three counts with plain stores -- `boards` and `out` may be
+// page-locked host memory, so that the whole call is one launch and one synchronisation.
+__global__ void __launch_bounds__(kThreads) rollout_small_kernel(RolloutArgs a, int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots + 1][blockDim.x]
+    __shared__ uint32_t s_board[kBoardWords], s_img[kImageWords], s_cell[kCells], s_cnt[3];
+    const int pos = blockIdx.x, tid = threadIdx.x;
+    if (tid < kBoardWords) s_board[tid] = a.boards[(size_t)pos * kBoardWords + tid];
+    if (tid < 3) s_cnt[tid] = 0;
+    for (int c = tid; c < kCells; c += blockDim.x) s_cell[c] = cell_lut_entry(c);
+    __syncthreads();
+    if (tid < 32) build_image(s_board, s_img, tid);
+    __syncthreads();
+    const uint32_t info = s_img[kMetaInfo];
+    const uint32_t stride = blockDim.x * 4u;
+    uint32_t cell_addr = (uint32_t)__cvta_generic_to_shared(s_cell);
+    uint32_t my = (uint32_t)__cvta_generic_to_shared(s_slots + tid);
+    asm volatile("" : "+r"(cell_addr), "+r"(my));
+    uint32_t inc = 0;
+    if (tid < a.rollouts_per_pos) {
+        if ((info >> 9) & 1u) {                                                  // already decided: 0 moves
+            const uint32_t wc = (info >> 10) & 3u;
+            inc = wc == 1u ? kIncBlack : wc == 2u ? kIncWhite : kIncDraw;
+        } else {
+            Lane L{};
+            L.left = L.start = info & 0xffu;
+            L.colour = (info >> 8) & 1u;
+            L.rowmask = s_img[kMetaRows];
+            L.pos = pos; L.roll = tid;
+            for (int s = 0; s < kSlots; ++s) sts32(my + s * stride, s_img[s]);
+            sts32(my + kSlots * stride, 0u);
+            uint32_t rnd[4];
+            while (inc == 0) {
+                philox4x32_10((L.start - L.left) >> 2, L.roll, uint32_t(a.pos_base) + L.pos, a.ctr_hi, a.key_lo, a.key_hi, rnd);
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (inc == 0) inc = play_move(my, cell_addr, L, __umulhi(rnd[s], uint32_t(kCells)), stride);
+            }
+        }
+        atomicAdd(&s_cnt[inc == kIncWhite ? 0 : inc == kIncDraw ? 1 : 2], 1u);
+    }
+    __syncthreads();
+    if (tid < 3) out[(size_t)pos * 3 + tid] = int(s_cnt[tid]);
+}
+
 }  // namespace
+
+cudaError_t launch_rollout_small(const RolloutArgs& a, int32_t* out, cudaStream_t stream) {
+    if (a.n <= 0 || a.rollouts_per_pos <= 0) return cudaSuccess;
+    if (a.rollouts_per_pos > kThreads) return cudaErrorInvalidValue;
+    const int threads = (a.rollouts_per_pos + 31) / 32 * 32;
+    const size_t smem = size_t(kSlots + 1) * threads * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(size_t(kSlots + 1) * kThreads * sizeof(uint32_t)));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    rollout_small_kernel<<<a.n, threads, smem, stream>>>(a, out);
+    return cudaGetLastError();
+}
 
 int rollout_launches(const RolloutArgs& a) { return a.n > 0 ? 2 : 0; }
 size_t rollout_scratch_bytes(int n) { return size_t(n > 0 ? n : 0) * kImageWords * sizeof(uint32_t); }

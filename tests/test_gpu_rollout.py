@@ -210,3 +210,21 @@ def test_c_abi_argument_errors(gpu):
     assert L.gk_root_allreduce(None, ctypes.c_void_p(st.data_ptr()), None) in (-5, -6)                  # no communicator yet (or no NCCL)
     # after all that the library still works
     assert (gpu.rollout_batch_host(boards, 8).sum(1) == 8).all()
+
+
+def test_fused_small_batch_launch_equals_the_big_kernel(gpu, port, kats):
+    """gk_rollout_batch_host with a handful of positions runs ONE fused launch (image build + rollouts, one CTA per
+    position): same Philox streams, same counts as the batched kernels and as the oracle -- including decided,
+    full and nearly full boards, and every rollout count that changes the block shape."""
+    tie = [y * 15 + x for y in kats["tie_row_order"] for x in range(15)]
+    lists = [[], tie[:-1], tie[:-7], tie, [y * 15 + x for x, y in kats["black_win"]], [112, 113, 97, 98]]
+    lists += [list(map(int, m)) for m in (gpu.synth_positions(900 + i, 1)[1] for i in range(6))]
+    mv, st = po.pack_moves(lists)
+    boards = gpu.pack_moves(mv, st)
+    for R, base in ((1, 0), (5, 3), (32, 100), (33, 7), (256, 1 << 20)):
+        small = gpu.rollout_batch_host(boards, R, key=77, ctr_hi=R, pos_base=base)          # 12 positions: fused path
+        big = _np(gpu.rollout_batch(boards, R, key=77, ctr_hi=R, pos_base=base)["wdb"])     # device path: batched kernels
+        _, _, want = port.rollout_philox_batch(mv, st, R, 77, ctr_hi=R, pos_base=base)
+        assert np.array_equal(small, big) and np.array_equal(small, want), R
+    one = gpu.rollout_batch_host(boards[5:6], 5, key=1, pos_base=9)
+    assert np.array_equal(one, _np(gpu.rollout_batch(boards[5:6], 5, key=1, pos_base=9)["wdb"]))
