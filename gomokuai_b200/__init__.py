@@ -60,6 +60,13 @@ def init(device=None):
     return _device
 
 
+def shutdown():
+    """Give back the library's streams, device buffers, page-locked staging and NCCL communicator (gk_shutdown)."""
+    global _device
+    _check(lib().gk_shutdown())
+    _device = None
+
+
 def _require_init():
     if _device is None:
         init()

@@ -200,8 +200,11 @@ gk_status gk_init(int device) {
     return GK_OK;
 }
 
+static void release_late_resources();       // buffers owned by the entry points further down (defined at the end of the file)
+
 gk_status gk_shutdown(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
+    release_late_resources();
     for (Pipe& p : g_pipes) {
         if (p.stream) cudaStreamDestroy(p.stream);
         cudaFree(p.d_boards); cudaFree(p.d_scores); cudaFree(p.d_pat); cudaFree(p.d_cmp); cudaFree(p.d_win); cudaFree(p.d_wdb);
@@ -783,3 +786,22 @@ gk_status gk_synth_positions(int64_t first, int n, uint32_t* h_boards, int16_t* 
 }
 
 }  // extern "C"
+
+// everything gk_shutdown() has to give back besides the pipes: streams, device and page-locked buffers of the entry
+// points above, and the library's own NCCL communicator (caller holds g_mutex)
+static void release_late_resources() {
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mutex);
+        for (auto& kv : g_rollout_scratch) cudaFree(kv.second.images);
+        g_rollout_scratch.clear();
+    }
+    for (AsyncSlot& a : g_async) {
+        std::lock_guard<std::mutex> lock(a.mutex);
+        if (a.stream) { cudaStreamSynchronize(a.stream); cudaStreamDestroy(a.stream); }
+        cudaFree(a.d_boards); cudaFree(a.d_wdb);
+        a.stream = nullptr; a.d_boards = nullptr; a.d_wdb = nullptr; a.cap = 0;
+    }
+    cudaFreeHost(g_stage_boards); cudaFreeHost(g_stage_wdb); cudaFreeHost(g_policy_stage);
+    g_stage_boards = nullptr; g_stage_wdb = nullptr; g_policy_stage = nullptr;
+    if (g_nccl_comm) { g_nccl.CommDestroy(g_nccl_comm); g_nccl_comm = nullptr; }
+}

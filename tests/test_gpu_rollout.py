@@ -228,3 +228,25 @@ def test_fused_small_batch_launch_equals_the_big_kernel(gpu, port, kats):
         assert np.array_equal(small, big) and np.array_equal(small, want), R
     one = gpu.rollout_batch_host(boards[5:6], 5, key=1, pos_base=9)
     assert np.array_equal(one, _np(gpu.rollout_batch(boards[5:6], 5, key=1, pos_base=9)["wdb"]))
+
+
+def test_shutdown_and_reinit_in_a_fresh_process():
+    """gk_shutdown gives everything back (pipes, async slots, staging, scratch) and the library can be bound again."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, gomokuai_b200 as gk\n"
+        "gk.init(0)\n"
+        "b = gk.synth_positions(0, 300, want_moves=False)[0]\n"
+        "a = gk.rollout_batch_host(b, 8); s = gk.rollout_batch_host(b[:4], 5)\n"
+        "out = np.zeros((300, 3), np.int32); gk.rollout_submit_host(2, b, 8, out); gk.rollout_wait(2)\n"
+        "e = gk.eval_policy_batch_host(b[:3]); h = gk.eval_batch_host(b)\n"
+        "gk.shutdown()\n"
+        "assert gk.lib().gk_rollout_wait(0) == -5\n"                      # GK_ERR_NOT_INIT: nothing works until the next gk_init
+        "gk.init(0)\n"
+        "assert np.array_equal(gk.rollout_batch_host(b, 8), a) and np.array_equal(out, a)\n"
+        "assert np.array_equal(gk.rollout_batch_host(b[:4], 5), s)\n"
+        "assert np.array_equal(gk.eval_batch_host(b)['scores'], h['scores'])\n"
+        "gk.shutdown(); print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
