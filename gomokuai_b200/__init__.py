@@ -422,6 +422,20 @@ def rollout_batch_host(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_ba
     return wdb
 
 
+def rollout_trace_host(board, rollouts, key=SYNTH_KEY, ctr_hi=0, pos=0):
+    """gk_rollout_trace_host: `rollouts` (<= 256) playouts of ONE position with their move lists.
+    Returns dict(winners i8[R], lengths u8[R], moves u8[R,225])."""
+    _require_init()
+    b = np.ascontiguousarray(board).view(np.uint32).reshape(BOARD_WORDS)
+    winners = np.zeros(rollouts, np.int8)
+    lengths = np.zeros(rollouts, np.uint8)
+    moves = np.zeros((rollouts, CELLS), np.uint8)
+    _check(lib().gk_rollout_trace_host(b.ctypes.data_as(ctypes.c_void_p), int(rollouts), ctypes.c_uint64(key), ctypes.c_uint32(ctr_hi),
+                                       int(pos), winners.ctypes.data_as(ctypes.c_void_p), lengths.ctypes.data_as(ctypes.c_void_p),
+                                       moves.ctypes.data_as(ctypes.c_void_p)))
+    return {"winners": winners, "lengths": lengths, "moves": moves}
+
+
 def rollout_submit_host(slot, boards, rollouts_per_pos, wdb, key=SYNTH_KEY, ctr_hi=0, pos_base=0):
     """Asynchronous gk_rollout_batch_host on stream `slot` (0..7): returns at once; `boards` (uint32[n,16]) and `wdb`
     (int32[n,3]) are numpy arrays that must stay alive and untouched until rollout_wait(slot)."""

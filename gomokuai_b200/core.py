@@ -10,7 +10,7 @@ if not os.path.exists(_build.ext_path()):
 
 from .CorePyExt import GameConfig, Player, Position, Board          # noqa: E402,F401
 from .CorePyExt import Node, Policy, MCTS                           # noqa: E402,F401
-from .CorePyExt import RandomPolicy, TraditionalPolicy              # noqa: E402,F401
-from .CorePyExt import RootParallelSearch, init                     # noqa: E402,F401
+from .CorePyExt import RandomPolicy, PoolRAVEPolicy, TraditionalPolicy   # noqa: E402,F401
+from .CorePyExt import RootParallelSearch, init, seed               # noqa: E402,F401
 
 __doc__ = f"C++ extension 'core' (B200 hot path) at '{_build.ext_path()}'"

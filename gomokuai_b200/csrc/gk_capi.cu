@@ -43,9 +43,22 @@ gk_status cuda_fail(cudaError_t e, const char* what) {
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
     } while (0)
+// inside a pipelined host call: work already enqueued on the caller's buffers finishes before the error returns
+#define GK_CUDA_PIPE(call)                                                      \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) return drain_pipes(cuda_fail(e_, #call));        \
+    } while (0)
 
+// The CUDA current device is per THREAD: every entry point rebinds its calling thread to the library's device (a
+// Python worker thread, the root-parallel driver's team, ...), so that a process bound to GPU k never touches GPU 0.
+thread_local int t_bound_device = -1;
 gk_status require_device() {
     if (g_device < 0) return fail(GK_ERR_NOT_INIT, "gk_init() has not been called");
+    if (t_bound_device != g_device) {
+        GK_CUDA(cudaSetDevice(g_device));
+        t_bound_device = g_device;
+    }
     return GK_OK;
 }
 
@@ -65,6 +78,13 @@ gk_status upload(gk_table* t) {
     if (gk_status s = to_device(&t->d_tape_info, h.tape_info)) return s;
     if (gk_status s = to_device(&t->d_flush, h.flush)) return s;
     return to_device(&t->d_trans, h.trans);    // last: its presence marks the table as uploaded
+}
+
+void free_device_copies(gk_table* t) {
+    cudaFree(t->d_trans); cudaFree(t->d_next16); cudaFree(t->d_erec); cudaFree(t->d_patrec); cudaFree(t->d_tape_src);
+    cudaFree(t->d_tape_info); cudaFree(t->d_flush);
+    t->d_trans = nullptr; t->d_next16 = nullptr; t->d_erec = nullptr; t->d_patrec = nullptr; t->d_tape_src = nullptr;
+    t->d_tape_info = nullptr; t->d_flush = nullptr;
 }
 
 // device copies are created lazily so that tables can be compiled and inspected without a GPU
@@ -157,24 +177,51 @@ struct Pipe {
     cudaStream_t stream = nullptr;
     uint32_t* d_boards = nullptr; int32_t* d_scores = nullptr; uint16_t* d_pat = nullptr; uint16_t* d_cmp = nullptr;
     int8_t* d_win = nullptr; int32_t* d_wdb = nullptr;
-    int cap = 0;
+    int cap = 0;            // positions the evaluation buffers hold
+    int cap_rollout = 0;    // positions d_boards / d_wdb hold (>= cap)
 };
 constexpr int kPipes = 3;
 Pipe g_pipes[kPipes];
 
+void pipe_release(Pipe& p) {                         // buffers only; the stream stays
+    if (p.stream) cudaStreamSynchronize(p.stream);
+    cudaFree(p.d_boards); cudaFree(p.d_scores); cudaFree(p.d_pat); cudaFree(p.d_cmp); cudaFree(p.d_win); cudaFree(p.d_wdb);
+    p.d_boards = nullptr; p.d_scores = nullptr; p.d_pat = nullptr; p.d_cmp = nullptr; p.d_win = nullptr; p.d_wdb = nullptr;
+    p.cap = p.cap_rollout = 0;
+}
+
+// buffers of the evaluation pipes (3.7 KB per position)
 gk_status pipe_reserve(Pipe& p, int chunk) {
     if (!p.stream) GK_CUDA(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
     if (p.cap >= chunk) return GK_OK;
-    cudaFree(p.d_boards); cudaFree(p.d_scores); cudaFree(p.d_pat); cudaFree(p.d_cmp); cudaFree(p.d_win); cudaFree(p.d_wdb);
-    p.cap = 0;
-    GK_CUDA(cudaMalloc(&p.d_boards, size_t(chunk) * 64));
-    GK_CUDA(cudaMalloc(&p.d_scores, size_t(chunk) * 3600));
-    GK_CUDA(cudaMalloc(&p.d_pat, size_t(chunk) * 32));
-    GK_CUDA(cudaMalloc(&p.d_cmp, size_t(chunk) * 12));
-    GK_CUDA(cudaMalloc(&p.d_win, size_t(chunk)));
-    GK_CUDA(cudaMalloc(&p.d_wdb, size_t(chunk) * 12));
-    p.cap = chunk;
+    pipe_release(p);
+    cudaError_t e = cudaMalloc(&p.d_boards, size_t(chunk) * 64);
+    if (e == cudaSuccess) e = cudaMalloc(&p.d_scores, size_t(chunk) * 3600);
+    if (e == cudaSuccess) e = cudaMalloc(&p.d_pat, size_t(chunk) * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&p.d_cmp, size_t(chunk) * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&p.d_win, size_t(chunk));
+    if (e == cudaSuccess) e = cudaMalloc(&p.d_wdb, size_t(chunk) * 12);
+    if (e != cudaSuccess) { pipe_release(p); return cuda_fail(e, "cudaMalloc (evaluation pipe)"); }
+    p.cap = p.cap_rollout = chunk;
     return GK_OK;
+}
+
+// the rollout host path needs boards and counts only (76 B per position, not the 3.7 KB of an evaluation pipe)
+gk_status pipe_reserve_rollout(Pipe& p, int n) {
+    if (!p.stream) GK_CUDA(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    if (p.cap_rollout >= n) return GK_OK;
+    pipe_release(p);
+    cudaError_t e = cudaMalloc(&p.d_boards, size_t(n) * 64);
+    if (e == cudaSuccess) e = cudaMalloc(&p.d_wdb, size_t(n) * 12);
+    if (e != cudaSuccess) { pipe_release(p); return cuda_fail(e, "cudaMalloc (rollout pipe)"); }
+    p.cap_rollout = n;
+    return GK_OK;
+}
+
+// an error in the middle of a pipelined call: let the work already enqueued on the caller's buffers finish first
+gk_status drain_pipes(gk_status s) {
+    for (Pipe& p : g_pipes) if (p.stream) cudaStreamSynchronize(p.stream);
+    return s;
 }
 
 }  // namespace
@@ -196,6 +243,7 @@ gk_status gk_init(int device) {
     if (prop.major != 10)
         return fail(GK_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100; this library carries sm_100a code only");
     GK_CUDA(cudaSetDevice(device));
+    t_bound_device = device;
     g_device = device; g_sm_count = prop.multiProcessorCount; g_cc_major = prop.major; g_cc_minor = prop.minor;
     return GK_OK;
 }
@@ -206,10 +254,11 @@ gk_status gk_shutdown(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
     release_late_resources();
     for (Pipe& p : g_pipes) {
+        pipe_release(p);
         if (p.stream) cudaStreamDestroy(p.stream);
-        cudaFree(p.d_boards); cudaFree(p.d_scores); cudaFree(p.d_pat); cudaFree(p.d_cmp); cudaFree(p.d_win); cudaFree(p.d_wdb);
         p = Pipe{};
     }
+    if (g_default_table) free_device_copies(g_default_table);        // re-uploaded lazily on the device of the next gk_init
     g_device = -1;
     return GK_OK;
 }
@@ -267,8 +316,7 @@ gk_status gk_table_build(const char* const* protos, const int* types, const int*
 
 gk_status gk_table_free(gk_table* t) {
     if (!t || t->is_default) return GK_OK;
-    cudaFree(t->d_trans); cudaFree(t->d_next16); cudaFree(t->d_erec); cudaFree(t->d_patrec); cudaFree(t->d_tape_src);
-    cudaFree(t->d_tape_info); cudaFree(t->d_flush);
+    free_device_copies(t);
     delete t;
     return GK_OK;
 }
@@ -360,14 +408,14 @@ gk_status gk_eval_batch_host(const gk_table* t, const uint32_t* h_boards, int n,
     for (int at = 0; at < n; at += chunk, ++k) {
         Pipe& p = g_pipes[k % kPipes];
         const int m = std::min(chunk, n - at);
-        GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
+        GK_CUDA_PIPE(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
         const gk::EvalArgs a = eval_args(t, p.d_boards, m, h_scores ? p.d_scores : nullptr, h_pat ? p.d_pat : nullptr,
                                          h_cmp ? p.d_cmp : nullptr, h_win ? p.d_win : nullptr);
-        GK_CUDA(gk::launch_eval(a, g_sm_count, p.stream));
-        if (h_scores) GK_CUDA(cudaMemcpyAsync(h_scores + size_t(at) * 900, p.d_scores, size_t(m) * 3600, cudaMemcpyDeviceToHost, p.stream));
-        if (h_pat) GK_CUDA(cudaMemcpyAsync(h_pat + size_t(at) * 16, p.d_pat, size_t(m) * 32, cudaMemcpyDeviceToHost, p.stream));
-        if (h_cmp) GK_CUDA(cudaMemcpyAsync(h_cmp + size_t(at) * 6, p.d_cmp, size_t(m) * 12, cudaMemcpyDeviceToHost, p.stream));
-        if (h_win) GK_CUDA(cudaMemcpyAsync(h_win + at, p.d_win, size_t(m), cudaMemcpyDeviceToHost, p.stream));
+        GK_CUDA_PIPE(gk::launch_eval(a, g_sm_count, p.stream));
+        if (h_scores) GK_CUDA_PIPE(cudaMemcpyAsync(h_scores + size_t(at) * 900, p.d_scores, size_t(m) * 3600, cudaMemcpyDeviceToHost, p.stream));
+        if (h_pat) GK_CUDA_PIPE(cudaMemcpyAsync(h_pat + size_t(at) * 16, p.d_pat, size_t(m) * 32, cudaMemcpyDeviceToHost, p.stream));
+        if (h_cmp) GK_CUDA_PIPE(cudaMemcpyAsync(h_cmp + size_t(at) * 6, p.d_cmp, size_t(m) * 12, cudaMemcpyDeviceToHost, p.stream));
+        if (h_win) GK_CUDA_PIPE(cudaMemcpyAsync(h_win + at, p.d_win, size_t(m), cudaMemcpyDeviceToHost, p.stream));
     }
     for (Pipe& p : g_pipes) GK_CUDA(cudaStreamSynchronize(p.stream));
     return GK_OK;
@@ -451,14 +499,14 @@ static gk_status policy_host(const gk_table* t, const uint32_t* h_boards, int n,
         const int m = std::min(chunk, n - at);
         float* d_probs = reinterpret_cast<float*>(p.d_scores);
         float* d_value = d_probs + size_t(chunk) * 225;
-        GK_CUDA(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
+        GK_CUDA_PIPE(cudaMemcpyAsync(p.d_boards, h_boards + size_t(at) * 16, size_t(m) * 64, cudaMemcpyHostToDevice, p.stream));
         gk::EvalArgs a = eval_args(t, p.d_boards, m, nullptr, nullptr, nullptr, h_win ? p.d_win : nullptr);
         a.probs = h_probs ? d_probs : nullptr; a.value = h_value ? d_value : nullptr; a.decisive = decisive;
         if (!a.probs && !a.value) a.value = d_value;
-        GK_CUDA(gk::launch_eval(a, g_sm_count, p.stream));
-        if (h_probs) GK_CUDA(cudaMemcpyAsync(h_probs + size_t(at) * 225, d_probs, size_t(m) * 900, cudaMemcpyDeviceToHost, p.stream));
-        if (h_value) GK_CUDA(cudaMemcpyAsync(h_value + at, d_value, size_t(m) * 4, cudaMemcpyDeviceToHost, p.stream));
-        if (h_win) GK_CUDA(cudaMemcpyAsync(h_win + at, p.d_win, size_t(m), cudaMemcpyDeviceToHost, p.stream));
+        GK_CUDA_PIPE(gk::launch_eval(a, g_sm_count, p.stream));
+        if (h_probs) GK_CUDA_PIPE(cudaMemcpyAsync(h_probs + size_t(at) * 225, d_probs, size_t(m) * 900, cudaMemcpyDeviceToHost, p.stream));
+        if (h_value) GK_CUDA_PIPE(cudaMemcpyAsync(h_value + at, d_value, size_t(m) * 4, cudaMemcpyDeviceToHost, p.stream));
+        if (h_win) GK_CUDA_PIPE(cudaMemcpyAsync(h_win + at, p.d_win, size_t(m), cudaMemcpyDeviceToHost, p.stream));
     }
     for (Pipe& p : g_pipes) GK_CUDA(cudaStreamSynchronize(p.stream));
     return GK_OK;
@@ -552,7 +600,7 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
     if (n == 0) return GK_OK;
     std::lock_guard<std::mutex> lock(g_mutex);
     Pipe& p = g_pipes[0];
-    if (gk_status s = pipe_reserve(p, std::max(n, 1))) return s;
+    if (gk_status s = pipe_reserve_rollout(p, std::max(n, 1))) return s;
     if (n <= kSmallBatch) {
         if (!g_stage_boards) {
             GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_boards), size_t(kSmallBatch) * 64, cudaHostAllocDefault));
@@ -583,6 +631,37 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
         return s;
     GK_CUDA(cudaMemcpyAsync(h_wdb, p.d_wdb, size_t(n) * 12, cudaMemcpyDeviceToHost, p.stream));
     GK_CUDA(cudaStreamSynchronize(p.stream));
+    return GK_OK;
+}
+
+namespace {
+unsigned char* g_stage_trace = nullptr;   // page-locked: 256 x (225 moves + length + winner)
+}  // namespace
+
+gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t philox_key, uint32_t ctr_hi, int pos,
+                                int8_t* h_winners, uint8_t* h_lengths, uint8_t* h_moves) {
+    if (gk_status s = require_device()) return s;
+    if (!h_board || rollouts <= 0 || rollouts > 256 || !h_winners || !h_lengths || !h_moves) return fail(GK_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    Pipe& p = g_pipes[0];
+    if (!p.stream) GK_CUDA(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    if (!g_stage_boards) {
+        GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_boards), size_t(kSmallBatch) * 64, cudaHostAllocDefault));
+        GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_wdb), size_t(kSmallBatch) * 12, cudaHostAllocDefault));
+    }
+    if (!g_stage_trace) GK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_stage_trace), size_t(256) * (GK_CELLS + 2), cudaHostAllocDefault));
+    std::memcpy(g_stage_boards, h_board, 64);
+    gk::RolloutArgs a{};
+    a.boards = g_stage_boards; a.n = 1; a.rollouts_per_pos = rollouts;
+    a.key_lo = uint32_t(philox_key); a.key_hi = uint32_t(philox_key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos;
+    a.moves = g_stage_trace;
+    a.lengths = g_stage_trace + size_t(256) * GK_CELLS;
+    a.winners = reinterpret_cast<int8_t*>(g_stage_trace + size_t(256) * (GK_CELLS + 1));
+    GK_CUDA(gk::launch_rollout_small(a, nullptr, p.stream));
+    GK_CUDA(cudaStreamSynchronize(p.stream));
+    std::memcpy(h_lengths, a.lengths, size_t(rollouts));
+    std::memcpy(h_winners, a.winners, size_t(rollouts));
+    for (int r = 0; r < rollouts; ++r) std::memcpy(h_moves + size_t(r) * GK_CELLS, a.moves + size_t(r) * GK_CELLS, h_lengths[r]);
     return GK_OK;
 }
 
@@ -801,7 +880,7 @@ static void release_late_resources() {
         cudaFree(a.d_boards); cudaFree(a.d_wdb);
         a.stream = nullptr; a.d_boards = nullptr; a.d_wdb = nullptr; a.cap = 0;
     }
-    cudaFreeHost(g_stage_boards); cudaFreeHost(g_stage_wdb); cudaFreeHost(g_policy_stage);
-    g_stage_boards = nullptr; g_stage_wdb = nullptr; g_policy_stage = nullptr;
+    cudaFreeHost(g_stage_boards); cudaFreeHost(g_stage_wdb); cudaFreeHost(g_policy_stage); cudaFreeHost(g_stage_trace);
+    g_stage_boards = nullptr; g_stage_wdb = nullptr; g_policy_stage = nullptr; g_stage_trace = nullptr;
     if (g_nccl_comm) { g_nccl.CommDestroy(g_nccl_comm); g_nccl_comm = nullptr; }
 }

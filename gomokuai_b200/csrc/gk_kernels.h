@@ -39,13 +39,14 @@ struct RolloutArgs {
     uint32_t key_lo, key_hi, ctr_hi; int pos_base;
     const uint8_t* r_stream; int stream_stride;     // non-null: injected start indices instead of Philox
     int32_t* wdb; int8_t* winners; uint8_t* lengths; // any may be null
+    uint8_t* moves;                                  // launch_rollout_small only: [n][rollouts_per_pos][225] cells played; may be null
 };
 // `images`: rollout_scratch_bytes(a.n) bytes of device scratch that stay untouched until the launch has finished
 // (one buffer per stream in flight)
 size_t rollout_scratch_bytes(int n);
 cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images, cudaStream_t stream);
-// a handful of positions with at most 256 rollouts each in ONE launch: a.boards and `out` (int32[n][3]) may be page-locked
-// host memory; same streams and counts as launch_rollout
+// a handful of positions with at most 256 rollouts each in ONE launch: a.boards, `out` (int32[n][3], may be null) and
+// a.winners / a.lengths / a.moves may be page-locked host memory; same streams and counts as launch_rollout
 cudaError_t launch_rollout_small(const RolloutArgs& a, int32_t* out, cudaStream_t stream);
 // number of kernels one launch_rollout call enqueues (slot images + wdb clear, rollouts)
 int rollout_launches(const RolloutArgs& a);

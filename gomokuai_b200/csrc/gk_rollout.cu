@@ -20,7 +20,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstdlib>
 
 #include "gk_format.h"
 #include "gk_kernels.h"
@@ -165,7 +164,8 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 constexpr uint32_t kSlotStride = kThreads * 4u;                                   // bytes between consecutive slots of one thread (the big kernel)
 
 __device__ __forceinline__ uint32_t play_move(uint32_t my /* shared address of slots[0][tid] */, uint32_t cell_addr /* of the cell LUT */,
-                                              Lane& L, uint32_t r, const uint32_t kSlotStride = kThreads * 4u /* bytes between a thread's slots */) {
+                                              Lane& L, uint32_t r, const uint32_t kSlotStride = kThreads * 4u /* bytes between a thread's slots */,
+                                              uint32_t* cell_out = nullptr /* the cell played (trace variants only; dead code otherwise) */) {
     uint32_t y = (r * 137u) >> 11, x = r - 15u * y;                              // r / 15, r % 15 for r < 225
     // Both candidate rows are read up front -- row y, and the next row after it that still has an empty cell (known from the
     // row mask, cyclically) -- so the fallback needs no second, dependent probe and no divergent branch: in most steps
@@ -186,6 +186,7 @@ __device__ __forceinline__ uint32_t play_move(uint32_t my /* shared address of s
     x = 31u - __clz(xbit);
     uint32_t lut;                                                                // s_cell[15 y + x]; the table is read-only after the CTA's first barrier
     asm("ld.shared.u32 %0, [%1];" : "=r"(lut) : "r"(cell_addr + (y * 15u + x) * 4u));
+    if (cell_out) *cell_out = y * 15u + x;
     const uint32_t base = 1u + 0xffffu * L.colour;
     // row
     w |= xbit * base;
@@ -344,6 +345,10 @@ rollout_kernel(RolloutArgs a, const uint32_t* __restrict__ images) {
 // slot image in shared memory, plays one rollout per thread (same Philox streams and the same move code as the big
 // kernel, so the counts are identical) and writes the three counts with plain stores -- `boards` and `out` may be
 // page-locked host memory, so that the whole call is one launch and one synchronisation.
+// kMoves: also write every rollout's winner, length and the cells it played (a.winners / a.lengths / a.moves, which
+// may be page-locked host memory too) -- PoolRAVEPolicy::defaultSimulate leaves the board at the END of its playout
+// (policies/PoolRAVE.h:27-48), so the host mirror replays the playout's moves on its Board.
+template <bool kMoves>
 __global__ void __launch_bounds__(kThreads) rollout_small_kernel(RolloutArgs a, int32_t* __restrict__ out) {
     extern __shared__ __align__(16) uint32_t s_slots[];                          // [kSlots + 1][blockDim.x]
     __shared__ uint32_t s_board[kBoardWords], s_img[kImageWords], s_cell[kCells], s_cnt[3];
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(kThreads) rollout_small_kernel(RolloutArgs a, 
         if ((info >> 9) & 1u) {                                                  // already decided: 0 moves
             const uint32_t wc = (info >> 10) & 3u;
             inc = wc == 1u ? kIncBlack : wc == 2u ? kIncWhite : kIncDraw;
+            if (kMoves && a.lengths) a.lengths[size_t(pos) * a.rollouts_per_pos + tid] = 0;
         } else {
             Lane L{};
             L.left = L.start = info & 0xffu;
@@ -373,17 +379,25 @@ __global__ void __launch_bounds__(kThreads) rollout_small_kernel(RolloutArgs a, 
             for (int s = 0; s < kSlots; ++s) sts32(my + s * stride, s_img[s]);
             sts32(my + kSlots * stride, 0u);
             uint32_t rnd[4];
+            uint8_t* trace = kMoves && a.moves ? a.moves + (size_t(pos) * a.rollouts_per_pos + tid) * kCells : nullptr;
             while (inc == 0) {
                 philox4x32_10((L.start - L.left) >> 2, L.roll, uint32_t(a.pos_base) + L.pos, a.ctr_hi, a.key_lo, a.key_hi, rnd);
 #pragma unroll
                 for (int s = 0; s < 4; ++s)
-                    if (inc == 0) inc = play_move(my, cell_addr, L, __umulhi(rnd[s], uint32_t(kCells)), stride);
+                    if (inc == 0) {
+                        uint32_t cell = 0;
+                        const uint32_t k = L.start - L.left;
+                        inc = play_move(my, cell_addr, L, __umulhi(rnd[s], uint32_t(kCells)), stride, kMoves ? &cell : nullptr);
+                        if (kMoves && trace) trace[k] = uint8_t(cell);
+                    }
             }
+            if (kMoves && a.lengths) a.lengths[size_t(pos) * a.rollouts_per_pos + tid] = uint8_t(L.start - L.left);
         }
+        if (kMoves && a.winners) a.winners[size_t(pos) * a.rollouts_per_pos + tid] = int8_t(inc == kIncBlack ? 1 : inc == kIncWhite ? -1 : 0);
         atomicAdd(&s_cnt[inc == kIncWhite ? 0 : inc == kIncDraw ? 1 : 2], 1u);
     }
     __syncthreads();
-    if (tid < 3) out[(size_t)pos * 3 + tid] = int(s_cnt[tid]);
+    if (out && tid < 3) out[(size_t)pos * 3 + tid] = int(s_cnt[tid]);
 }
 
 }  // namespace
@@ -395,12 +409,14 @@ cudaError_t launch_rollout_small(const RolloutArgs& a, int32_t* out, cudaStream_
     const size_t smem = size_t(kSlots + 1) * threads * sizeof(uint32_t);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(size_t(kSlots + 1) * kThreads * sizeof(uint32_t)));
+        const int most = int(size_t(kSlots + 1) * kThreads * sizeof(uint32_t));
+        cudaError_t e = cudaFuncSetAttribute(rollout_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(rollout_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    rollout_small_kernel<<<a.n, threads, smem, stream>>>(a, out);
+    if (a.moves || a.winners || a.lengths) rollout_small_kernel<true><<<a.n, threads, smem, stream>>>(a, out);
+    else rollout_small_kernel<false><<<a.n, threads, smem, stream>>>(a, out);
     return cudaGetLastError();
 }
 
@@ -417,12 +433,8 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images,
     const size_t smem = size_t(kSlots + 1) * kThreads * sizeof(uint32_t);   // + one scratch slot per thread
     const unsigned long long total = (unsigned long long)a.n * a.rollouts_per_pos;
     unsigned long long blocks = (total + kTicketBlock - 1) / kTicketBlock;
-    int per_sm = 3;
-    if (const char* env = std::getenv("GK_ROLLOUT_CTAS")) per_sm = std::atoi(env);   // experiment knob
-    const unsigned long long resident = (unsigned long long)sm_count * per_sm;
+    const unsigned long long resident = (unsigned long long)sm_count * 3;         // 3 CTAs per SM (73 KB of slot state each)
     const int grid = int(blocks < resident ? blocks : resident);
-    int refill = kRefillDefault;
-    if (const char* env = std::getenv("GK_ROLLOUT_REFILL")) refill = std::atoi(env);   // tuning knob (4, 8, 12 or 16)
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -431,12 +443,7 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images,
     };
     if (a.r_stream) return launch(rollout_kernel<true, kRefillDefault, true>);
     if (a.winners != nullptr || a.lengths != nullptr) return launch(rollout_kernel<false, kRefillDefault, true>);
-    switch (refill) {
-        case 4: return launch(rollout_kernel<false, 4, false>);
-        case 8: return launch(rollout_kernel<false, 8, false>);
-        case 12: return launch(rollout_kernel<false, 12, false>);
-        default: return launch(rollout_kernel<false, kRefillDefault, false>);
-    }
+    return launch(rollout_kernel<false, kRefillDefault, false>);
 }
 
 }  // namespace gk

@@ -111,14 +111,46 @@ void ensure_gpu() {
     if (gk_init(lr ? std::atoi(lr) : 0) != GK_OK) throw std::runtime_error(std::string("gk_init: ") + gk_last_error());
 }
 
+// ---- random sources ------------------------------------------------------------------------------------------
+namespace {
+std::atomic<std::uint64_t> g_rollout_key{ 0 };         // 0 = not drawn yet
+std::atomic<std::uint64_t> g_rollout_calls{ 0 };       // every simulate call takes a fresh (ctr_hi, position) pair: independent streams
+std::atomic<std::uint64_t> g_noise_epoch{ 0 }, g_noise_seed{ 0 };
+
+std::uint64_t rollout_key() {
+    std::uint64_t k = g_rollout_key.load(std::memory_order_relaxed);
+    if (k == 0) {
+        std::random_device rd;
+        std::uint64_t fresh = (std::uint64_t(rd()) << 32 | rd()) | 1u;
+        if (g_rollout_key.compare_exchange_strong(k, fresh)) k = fresh;
+    }
+    return k;
+}
+
+std::mt19937& noise_engine() {
+    static thread_local std::mt19937 engine{ std::random_device{}() };
+    static thread_local std::uint64_t epoch = 0;
+    const std::uint64_t e = g_noise_epoch.load(std::memory_order_acquire);
+    if (epoch != e) { engine.seed(static_cast<std::uint32_t>(g_noise_seed.load())); epoch = e; }
+    return engine;
+}
+}  // namespace
+
+void set_seed(std::uint64_t seed) {
+    g_rollout_key.store(seed * 0x9E3779B97F4A7C15ull | 1u);
+    g_rollout_calls.store(0);
+    g_noise_seed.store(seed);
+    g_noise_epoch.fetch_add(1, std::memory_order_release);     // every thread's noise engine reseeds at its next use
+}
+
 float Default::GpuRolloutValue(const Board& board, int rollouts) {
     ensure_gpu();
-    static std::atomic<int> call_counter{ 0 };         // a fresh Philox "position" per call: independent streams
     std::uint32_t packed[16];
     std::int32_t wdb[3] = { 0, 0, 0 };
     board.pack(packed);
-    const int base = call_counter.fetch_add(1) & 0x3fffffff;
-    if (gk_rollout_batch_host(packed, 1, rollouts, 0x4D435453ull /* "MCTS" */, 0x5eedu, base, wdb) != GK_OK)
+    const std::uint64_t call = g_rollout_calls.fetch_add(1);
+    if (gk_rollout_batch_host(packed, 1, rollouts, rollout_key(), static_cast<std::uint32_t>(call >> 30),
+                              static_cast<int>(call & 0x3fffffff), wdb) != GK_OK)
         throw std::runtime_error(std::string("gk_rollout_batch_host: ") + gk_last_error());
     const float black_value = static_cast<float>(wdb[2] - wdb[0]) / static_cast<float>(rollouts);
     return CalcScore(board.m_curPlayer, black_value);
@@ -136,19 +168,28 @@ void Default::BackPropogate(Policy*, Node* node, Board&, double value) {        
     }
 }
 
-void Default::AddNoise(Node* node, float alpha, float epsilon) {                        // :97-108, Statistical.hpp:29-34
-    if (node->children.empty()) return;
-    static thread_local std::mt19937 engine{ std::random_device{}() };
+// MonteCarlo.hpp:97-108 + Stats::DirichletNoise, Statistical.hpp:29-34.  Operation for operation in float like the
+// reference: the priors go into a 225-vector by cell, are scaled by (1 - epsilon), every cell whose scaled prior is
+// non-zero draws gamma(alpha, 1) IN CELL ORDER, the draws are L2-normalised (Eigen's normalized(), not a sum-to-one
+// Dirichlet) and epsilon times them is added.  A root without children draws nothing.
+void Default::AddNoise(Node* node, float alpha, float epsilon) {
+    float prior[BOARD_SIZE] = { 0.0f }, noise[BOARD_SIZE];
+    for (auto& child : node->children) prior[child->position] = child->action_prob;
+    const float keep = 1 - epsilon;
+    for (float& p : prior) p *= keep;
     std::gamma_distribution<float> gamma(alpha, 1.0f);
-    std::vector<float> noise(node->children.size());
-    double norm2 = 0.0;
-    for (std::size_t i = 0; i < noise.size(); ++i) {
-        noise[i] = node->children[i]->action_prob != 0.0f ? gamma(engine) : 0.0f;
-        norm2 += double(noise[i]) * noise[i];
+    std::mt19937& engine = noise_engine();
+    float norm2 = 0.0f;
+    for (int i = 0; i < BOARD_SIZE; ++i) {
+        noise[i] = prior[i] ? gamma(engine) : 0.0f;
+        norm2 += noise[i] * noise[i];
     }
-    const float inv = norm2 > 0.0 ? static_cast<float>(1.0 / std::sqrt(norm2)) : 0.0f;    // Eigen normalized() = L2
-    for (std::size_t i = 0; i < noise.size(); ++i)
-        node->children[i]->action_prob = node->children[i]->action_prob * (1 - epsilon) + epsilon * noise[i] * inv;
+    if (norm2 > 0.0f) {
+        const float norm = std::sqrt(norm2);
+        for (float& x : noise) x /= norm;
+    }
+    for (int i = 0; i < BOARD_SIZE; ++i) prior[i] += epsilon * noise[i];
+    for (auto& child : node->children) child->action_prob = prior[child->position];
 }
 
 // ---- RandomPolicy (policies/Random.h) --------------------------------------------------------------------
@@ -159,17 +200,40 @@ Policy::EvalResult RandomPolicy::averagedSimulate(Board& board) {               
     return { Default::GpuRolloutValue(board, static_cast<int>(c_rollouts)), Default::UniformProbs(board) };
 }
 
-// ---- RAVE select / update without AMAF (MonteCarlo.hpp:150-186) --------------------------------------------------
+// ---- RAVE (MonteCarlo.hpp:112-186) ------------------------------------------------------------------------------
+double RAVE::HandSelect(const AMAFNode* node, std::size_t eqv_param) {                     // :126-130
+    const double n = static_cast<double>(node->node_visits), k = static_cast<double>(eqv_param);
+    return std::sqrt(k / (3 * n + k));
+}
+double RAVE::MinMSE(const AMAFNode* node, double c_bias) {                                 // :132-137
+    const double n = static_cast<double>(node->node_visits + 1), n_ = static_cast<double>(node->amaf_visits);
+    return n_ / (n + n_ + n * n_ * c_bias * c_bias);
+}
+double RAVE::WeightedValue(const AMAFNode* node, double) {                                 // :139-143: the hand-tuned schedule is the live one
+    const double weight = HandSelect(node);
+    return (1 - weight) * node->state_value + weight * node->amaf_value;
+}
+
 Node* RAVE::Select(Policy*, const Node* node) { return node->children[0].get(); }          // :150-153
 
-void RAVE::BackPropogate(Policy* policy, Node* node, Board&, double value) {               // :156-186 with UseRave = false
+void RAVE::BackPropogate(Policy* policy, Node* node, Board& board, double value, bool use_rave, double c_bias) {   // :155-186
     float v = static_cast<float>(value);
     for (; node != nullptr; node = node->parent, v = -v) {
         std::size_t max_index = 0;
         double max_score = -std::numeric_limits<double>::infinity();
         for (std::size_t i = 0; i < node->children.size(); ++i) {
-            const Node* child = node->children[i].get();
-            const double score = Default::PUCB(child, policy->c_puct) + child->state_value;
+            Node* child = node->children[i].get();
+            double score = Default::PUCB(child, policy->c_puct);
+            if (use_rave) {
+                AMAFNode* rave = static_cast<AMAFNode*>(child);
+                if (board.moveState(rave->player, rave->position)) {                      // the same player's stone stands there at the end
+                    rave->amaf_visits += 1;
+                    rave->amaf_value += (-v - rave->amaf_value) / static_cast<float>(rave->amaf_visits);
+                }
+                score += WeightedValue(rave, c_bias);
+            } else {
+                score += child->state_value;
+            }
             if (score > max_score) { max_score = score; max_index = i; }
         }
         if (!node->children.empty()) node->children[0].swap(node->children[max_index]);       // best child to the front
@@ -183,9 +247,42 @@ TraditionalPolicy::TraditionalPolicy(double c_puct, double c_bias, bool use_rave
     : Policy([this](const Node* node) { return RAVE::Select(this, node); },
              [this](Node* node, Board& board, const Probs& probs) { return Default::Expand(this, node, board, probs, false); },
              [this](Board& board) { return hybridSimulate(board); },
-             [this](Node* node, Board& board, double value) { RAVE::BackPropogate(this, node, board, value); }, c_puct),
-      c_bias(c_bias), c_useRave(use_rave) {
-    if (use_rave) throw std::invalid_argument("TraditionalPolicy: use_rave is not supported (AMAF statistics are outside the hot path)");
+             [this](Node* node, Board& board, double value) { RAVE::BackPropogate(this, node, board, value, c_useRave, this->c_bias); }, c_puct),
+      c_bias(c_bias), c_useRave(use_rave) {}
+
+std::unique_ptr<Node> TraditionalPolicy::createNode(Node* parent, Position pose, Player player, float value, float prob) {
+    if (c_useRave) return std::unique_ptr<Node>(new RAVE::AMAFNode(parent, pose, player, value, prob));
+    return Policy::createNode(parent, pose, player, value, prob);
+}
+
+// ---- PoolRAVEPolicy (policies/PoolRAVE.h) ----------------------------------------------------------------------------
+PoolRAVEPolicy::PoolRAVEPolicy(double c_puct, double c_bias)
+    : Policy([this](const Node* node) { return RAVE::Select(this, node); },
+             [this](Node* node, Board& board, const Probs& probs) { return Default::Expand(this, node, board, probs, false); },
+             [this](Board& board) { return defaultSimulate(board); },
+             [this](Node* node, Board& board, double value) { RAVE::BackPropogate(this, node, board, value, true, this->c_bias); }, c_puct),
+      c_bias(c_bias) {}
+
+std::unique_ptr<Node> PoolRAVEPolicy::createNode(Node* parent, Position pose, Player player, float value, float prob) {   // PoolRAVE.h:23-25
+    return std::unique_ptr<Node>(new RAVE::AMAFNode(parent, pose, player, value, prob));
+}
+
+Policy::EvalResult PoolRAVEPolicy::defaultSimulate(Board& board) {                         // PoolRAVE.h:27-48
+    Probs probs = Default::UniformProbs(board);              // before the playout: the board is NOT restored afterwards
+    const Player init_player = board.m_curPlayer;
+    ensure_gpu();
+    std::uint32_t packed[16];
+    board.pack(packed);
+    std::int8_t winner = 0;
+    std::uint8_t length = 0, moves[BOARD_SIZE];
+    const std::uint64_t call = g_rollout_calls.fetch_add(1);
+    if (gk_rollout_trace_host(packed, 1, rollout_key(), static_cast<std::uint32_t>(call >> 30), static_cast<int>(call & 0x3fffffff),
+                              &winner, &length, moves) != GK_OK)
+        throw std::runtime_error(std::string("gk_rollout_trace_host: ") + gk_last_error());
+    for (int k = 0; k < length; ++k) board.applyMove(Position(moves[k]));                    // Default::RandomRollout's applyMove, victory checks on
+    if (static_cast<int>(board.m_winner) != winner || board.m_curPlayer != Player::None)
+        throw std::runtime_error("PoolRAVEPolicy: the replayed playout does not end where the kernel's did");
+    return { CalcScore(init_player, board.m_winner), probs };
 }
 
 Policy::EvalResult TraditionalPolicy::hybridSimulate(Board& board) {                       // Traditional.h:49-69
@@ -223,13 +320,13 @@ Position MCTS::getAction(Board& board) {
     return stepForward()->position;
 }
 
-Probs TempBasedProbs(const Probs& logits, float temperature) {                          // Statistical.hpp:37-42
+// Statistical.hpp:37-42, operation for operation: log and the division by the temperature in float, softmax in double
+// (exp, left-to-right sum, division), back to float, entries <= epsilon zeroed
+Probs TempBasedProbs(const Probs& logits, float temperature) {
     const float eps = std::numeric_limits<float>::epsilon();
     std::vector<double> t(logits.size());
-    double mx = -std::numeric_limits<double>::infinity();
-    for (std::size_t i = 0; i < t.size(); ++i) { t[i] = double(std::log(logits[i] + eps) / temperature); mx = std::max(mx, t[i]); }
     double sum = 0.0;
-    for (double& v : t) { v = std::exp(v - mx); sum += v; }
+    for (std::size_t i = 0; i < t.size(); ++i) { t[i] = std::exp(static_cast<double>(std::log(logits[i] + eps) / temperature)); sum += t[i]; }
     Probs out(logits.size());
     for (std::size_t i = 0; i < t.size(); ++i) { const float p = static_cast<float>(t[i] / sum); out[i] = p > eps ? p : 0.0f; }
     return out;
@@ -238,10 +335,11 @@ Probs TempBasedProbs(const Probs& logits, float temperature) {                  
 Policy::EvalResult MCTS::evalState(Board& board) {                                      // MCTS.cpp:104-117 (the debug print is dropped)
     runPlayouts(board);
     Probs visits(BOARD_SIZE, 0.0f);
-    double norm2 = 0.0;
-    for (auto& node : m_root->children) { visits[node->position] = static_cast<float>(node->node_visits); norm2 += double(node->node_visits) * node->node_visits; }
-    const float inv = norm2 > 0.0 ? static_cast<float>(1.0 / std::sqrt(norm2)) : 0.0f;
-    for (float& v : visits) { v *= inv; if (v != 0.0f) v += 1.0f; }
+    for (auto& node : m_root->children) visits[node->position] = static_cast<float>(node->node_visits);
+    float norm2 = 0.0f;                                                                 // normalized(): float, unchanged when the norm is 0
+    for (float v : visits) norm2 += v * v;
+    if (norm2 > 0.0f) { const float norm = std::sqrt(norm2); for (float& v : visits) v /= norm; }
+    for (float& v : visits) if (v != 0.0f) v += 1.0f;
     return { m_root->state_value, TempBasedProbs(visits, board.m_moveRecord.size() < 15 ? 1.0f : 1e-2f) };
 }
 

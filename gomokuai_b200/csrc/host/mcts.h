@@ -5,6 +5,7 @@
 // std::vector<float>(225) where the reference uses Eigen::VectorXf.
 #pragma once
 #include <chrono>
+#include <cstdint>
 #include <functional>
 #include <memory>
 #include <tuple>
@@ -36,6 +37,10 @@ struct Node {                                        // MCTS.h:25-66
     Node& operator=(Node&&) = default;
     Node(Node* parent, Position position, Player player, float value, float prob)
         : parent(parent), position(position), player(player), state_value(value), action_prob(prob) {}
+    // Policy::createNode may return a derived node (RAVE::AMAFNode) behind unique_ptr<Node>.  The reference deletes it
+    // through the base pointer without a virtual destructor (MonteCarlo.hpp:114-124, PoolRAVE.h:23-25); here the
+    // destructor is virtual so that the pooled allocator below sees the true size.
+    virtual ~Node() = default;
     bool isLeaf() const { return children.empty(); }
     bool isFull(const Board& board) const { return children.size() == board.moveCounts(Player::None); }
 
@@ -97,11 +102,32 @@ public:
     std::size_t c_rollouts;
 };
 
-// RAVE::Select / RAVE::BackPropogate<false> (algorithms/MonteCarlo.hpp:150-186): back-propagation keeps the
-// best-scoring child (PUCB + state value) at index 0 of every node on the path, select takes children[0].
+// RAVE (algorithms/MonteCarlo.hpp:112-186): back-propagation keeps the best-scoring child at index 0 of every node on
+// the path, select takes children[0].  UseRave: the score is PUCB + WeightedValue(state value, AMAF value) and a child
+// whose (player, position) stone stands on `board` -- the END of the playout -- gets an AMAF update; otherwise
+// PUCB + state value (what TraditionalPolicy uses).
 struct RAVE {
+    struct AMAFNode : public Node {                  // MonteCarlo.hpp:114-124
+        float amaf_value = 0.0f;
+        std::size_t amaf_visits = 0;
+        AMAFNode(Node* parent, Position pose, Player player, float Q, float P) : Node(parent, pose, player, Q, P) {}
+    };
+    static double HandSelect(const AMAFNode* node, std::size_t eqv_param = 800);
+    static double MinMSE(const AMAFNode* node, double c_bias);
+    static double WeightedValue(const AMAFNode* node, double c_bias);
     static Node* Select(Policy* policy, const Node* node);
-    static void BackPropogate(Policy* policy, Node* node, Board& board, double value);
+    static void BackPropogate(Policy* policy, Node* node, Board& board, double value, bool use_rave = false, double c_bias = 0.0);
+};
+
+// PoolRAVEPolicy (policies/PoolRAVE.h:13-52): AMAF nodes, RAVE select / update, ONE random playout per leaf whose
+// final position stays on the board until MCTS::playout reverts it (the AMAF update reads it).  The playout runs on the
+// GPU (gk_rollout_trace_host) and its moves are replayed on the host board.
+class PoolRAVEPolicy : public Policy {
+public:
+    explicit PoolRAVEPolicy(double c_puct = 1e-4, double c_bias = 1e-1);
+    std::unique_ptr<Node> createNode(Node* parent, Position pose, Player player, float value, float prob) override;
+    EvalResult defaultSimulate(Board& board);
+    double c_bias;
 };
 
 // TraditionalPolicy (policies/Traditional.h:13-73): pattern evaluator instead of random playouts.
@@ -109,9 +135,13 @@ struct RAVE {
 // Heuristic::EvaluationValue, computed by ac_eval_kernel (gk_hybrid_simulate_batch_host).  The reference keeps an
 // incremental Evaluator synchronised with the tree walk (CachedApplyMove / CachedRevertMove); the GPU evaluates
 // the leaf position from scratch, so the board itself is walked (Policy::applyMove / revertMove).
+// The 3-argument constructor exists only in the reference's Python binding (core/py_ext/src/policy_ext.hpp:39-45; the
+// library header has TraditionalPolicy(puct) alone): use_rave = true here selects AMAF nodes and RAVE's UseRave update
+// with c_bias, fed -- as the binding's argument order implies -- by the stones of the leaf position.
 class TraditionalPolicy : public Policy {
 public:
     explicit TraditionalPolicy(double c_puct = C_PUCT, double c_bias = 0.0, bool use_rave = false);
+    std::unique_ptr<Node> createNode(Node* parent, Position pose, Player player, float value, float prob) override;
     EvalResult hybridSimulate(Board& board);
     double c_bias;
     bool c_useRave;
@@ -144,6 +174,11 @@ private:
 };
 
 void ensure_gpu();   // gk_init(LOCAL_RANK or 0) on first use; throws std::runtime_error without a usable GPU
+
+// The mirror's random sources -- the Philox key of the GPU playouts behind RandomPolicy / PoolRAVEPolicy / Default::Simulate
+// and the calling thread's Dirichlet-noise engine -- are seeded from std::random_device once per process / thread, as the
+// reference seeds its engines (Game.cpp:11-12, Statistical.hpp:23-26).  set_seed makes a run reproducible.
+void set_seed(std::uint64_t seed);
 
 // Statistical helpers used by evalState (algorithms/Statistical.hpp:37-42)
 Probs TempBasedProbs(const Probs& logits, float temperature);

@@ -25,6 +25,7 @@ static const char* player_str(Player p) { return p == Player::Black ? "Player Bl
 PYBIND11_MODULE(CorePyExt, mod) {
     mod.doc() = "Gomoku AI core module (B200-native hot path)";
 
+    mod.def("seed", &set_seed, "seed"_a, "Seed the playout streams and the Dirichlet-noise engine (the reference seeds from random_device).");
     mod.def("init", [](int device) { if (gk_init(device) != GK_OK) throw std::runtime_error(gk_last_error()); },
             "device"_a = 0, "Bind this process to one GPU (called implicitly by gomokuai_b200.core).");
 
@@ -172,10 +173,18 @@ PYBIND11_MODULE(CorePyExt, mod) {
             return "RandomPolicy(c_puct: " + std::to_string(p.c_puct) + ", c_rollouts: " + std::to_string(p.c_rollouts) + ", init_acts: " + std::to_string(p.m_initActs) + ")";
         });
 
+    py::class_<PoolRAVEPolicy, Policy, std::shared_ptr<PoolRAVEPolicy>>(mod, "PoolRAVEPolicy", "PoolRAVE policy with MC-RAVE algorithm (GPU playouts)")
+        .def(py::init<double, double>(), "c_puct"_a = 2, "c_bias"_a = 0)                  // policy_ext.hpp:25-36
+        .def_readonly("c_bias", &PoolRAVEPolicy::c_bias)
+        .def("__repr__", [](const PoolRAVEPolicy& p) {
+            return "PoolRAVEPolicy(c_puct: " + std::to_string(p.c_puct) + ", c_bias: " + std::to_string(p.c_bias) + ", init_acts: " + std::to_string(p.m_initActs) + ")";
+        });
+
     py::class_<TraditionalPolicy, Policy, std::shared_ptr<TraditionalPolicy>>(mod, "TraditionalPolicy", "Traditional policy with MC + Pattern Matching algorithm (GPU pattern evaluator)")
         .def(py::init<double, double, bool>(), "c_puct"_a = C_PUCT, "c_bias"_a = 0, "use_rave"_a = false)
         .def("__repr__", [](const TraditionalPolicy& p) {
-            return "TraditionalPolicy(c_puct: " + std::to_string(p.c_puct) + ", init_acts: " + std::to_string(p.m_initActs) + ")";
+            return "TraditionalPolicy(c_puct: " + std::to_string(p.c_puct) + (p.c_useRave ? ", c_bias: " + std::to_string(p.c_bias) : std::string()) +
+                   ", init_acts: " + std::to_string(p.m_initActs) + ")";
         });
 
     // ---- new: root-parallel search -------------------------------------------------------------------------------
@@ -201,6 +210,19 @@ PYBIND11_MODULE(CorePyExt, mod) {
             std::copy(a.data(), a.data() + 3 * BOARD_SIZE, st.begin());
             return RootParallelSearch::bestMove(st);
         })
+        .def("tree_dump", [](const RootParallelSearch& s, int tree) {
+            const auto nodes = s.dumpTree(tree);
+            const py::ssize_t n = static_cast<py::ssize_t>(nodes.size());
+            py::array_t<std::int16_t> pos(n), depth(n);
+            py::array_t<std::int32_t> visits(n), n_moves(n);
+            py::array_t<float> value(n), prior(n);
+            for (py::ssize_t i = 0; i < n; ++i) {
+                pos.mutable_data()[i] = nodes[i].position; depth.mutable_data()[i] = nodes[i].depth;
+                visits.mutable_data()[i] = nodes[i].visits; n_moves.mutable_data()[i] = nodes[i].n_moves;
+                value.mutable_data()[i] = nodes[i].value; prior.mutable_data()[i] = nodes[i].prior;
+            }
+            return py::dict("pos"_a = pos, "visits"_a = visits, "value"_a = value, "prior"_a = prior, "depth"_a = depth, "n_children"_a = n_moves);
+        }, "tree"_a, "Visited nodes of one tree of the last run in pre-order (for node-for-node comparison with the reference's MCTS).")
         .def_readonly("seconds_total", &RootParallelSearch::seconds_total)
         .def_readonly("seconds_gpu", &RootParallelSearch::seconds_gpu)
         .def_property_readonly("driver_seconds", [](const RootParallelSearch& s) { return py::make_tuple(s.driver_seconds[0], s.driver_seconds[1], s.driver_seconds[2]); })

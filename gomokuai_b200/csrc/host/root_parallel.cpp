@@ -337,6 +337,29 @@ static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg
     t.board.revertMove(t.board.m_moveRecord.size() - root_depth);
 }
 
+std::vector<RootParallelSearch::DumpNode> RootParallelSearch::dumpTree(int tree) const {
+    std::vector<DumpNode> out;
+    if (tree < 0 || tree >= static_cast<int>(m->trees.size())) return out;
+    const Tree& t = m->trees[tree];
+    if (t.nodes.empty()) return out;
+    std::vector<std::pair<std::int32_t, int>> stack{ { 0, 0 } };
+    std::vector<std::int32_t> kids;
+    while (!stack.empty()) {
+        const auto [n, depth] = stack.back();
+        stack.pop_back();
+        const ANode& nd = t.nodes[n];
+        const bool in_block = t.in_root_block(n);
+        out.push_back({ nd.position, t.visits_of(n), in_block ? t.rvalue[n - t.rfirst] : nd.value, in_block ? t.rprior[n - t.rfirst] : nd.prior,
+                        static_cast<std::int16_t>(depth), nd.n_moves });
+        kids.clear();
+        if (nd.eager) for (std::int32_t c = nd.first_child; c < nd.first_child + nd.n_children; ++c) kids.push_back(c);
+        else for (std::int32_t c = nd.first_child; c >= 0; c = t.nodes[c].next_sibling) kids.push_back(c);
+        for (auto it = kids.rbegin(); it != kids.rend(); ++it)
+            if (t.visits_of(*it) > 0) stack.push_back({ *it, depth + 1 });
+    }
+    return out;
+}
+
 void RootParallelSearch::run(const Board& root, int playouts_per_tree, std::uint64_t seed) {
     m_cfg.seed = seed;
     run(root, playouts_per_tree);
@@ -418,8 +441,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
             done[g].fetch_add(hi - lo, std::memory_order_acq_rel);
         }
     };
-    const char* helps_env = std::getenv("GK_RP_DRIVER_HELPS");       // tuning knob (measured: +29 % at 4 threads, +2 % at 16)
-    const bool driver_helps = helps_env ? std::atoi(helps_env) != 0 : true;
+    constexpr bool driver_helps = true;                              // measured: +29 % at 4 threads, +2 % at 16
     auto driver = [&]() {
         auto arrive = [&](long long v) {                             // results of visit v's previous batch
             if (v >= visits_total || v / groups == 0 || failed.load()) return;

@@ -38,6 +38,11 @@ public:
     void run(const Board& root, int playouts_per_tree, std::uint64_t seed);   // same, with a new Philox key / noise seed (the object and its arenas are reused)
 
     const Stats& stats() const { return m_stats; }
+    // Tree `tree` of the last run in pre-order, visited nodes only (children in increasing cell order, as the reference
+    // expands them): the move into the node, its visits, value, prior, depth and number of legal moves once expanded.
+    // For tests that compare a tree node for node with the reference's MCTS under the same playout stream.
+    struct DumpNode { std::int16_t position; std::int32_t visits; float value, prior; std::int16_t depth; std::int32_t n_moves; };
+    std::vector<DumpNode> dumpTree(int tree) const;
     static Position bestMove(const Stats& stats);             // most visited root child, ties -> lowest cell (MCTS.cpp:129-134)
 
     double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / of it, time the first worker waited for GPU results

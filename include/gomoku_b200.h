@@ -58,7 +58,8 @@ enum { GK_WIDTH = 15, GK_HEIGHT = 15, GK_CELLS = 225, GK_BOARD_WORDS = 16,
 typedef struct gk_table gk_table;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
-gk_status gk_init(int device);                      /* binds the process to one GPU (one process per GPU) */
+gk_status gk_init(int device);                      /* binds the process to one GPU (one process per GPU); every later
+                                                        gk_* call rebinds its calling THREAD to that device */
 gk_status gk_shutdown(void);
 const char* gk_last_error(void);
 gk_status gk_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor);
@@ -169,6 +170,13 @@ gk_status gk_rollout_batch(const uint32_t* d_boards, int n, int rollouts_per_pos
                            int32_t* d_wdb, int8_t* d_winners, uint8_t* d_lengths, void* stream);
 gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_per_pos,
                                 uint64_t philox_key, uint32_t ctr_hi, int pos_base, int32_t* h_wdb);
+/* One position, `rollouts` (<= 256) playouts WITH their move lists, one fused launch -- what
+ * PoolRAVEPolicy::defaultSimulate needs: it leaves the board at the END of its playout (include/policies/PoolRAVE.h:
+ * 27-48) because RAVE::BackPropogate reads the final stones (include/algorithms/MonteCarlo.hpp:155-184).  Same Philox
+ * stream as gk_rollout_batch for position index `pos`.  h_winners int8[rollouts] (+1 black, -1 white, 0 draw),
+ * h_lengths uint8[rollouts], h_moves uint8[rollouts][225]: the cells in playing order (first h_lengths[r] valid). */
+gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t philox_key, uint32_t ctr_hi, int pos,
+                                int8_t* h_winners, uint8_t* h_lengths, uint8_t* h_moves);
 /* Asynchronous form of gk_rollout_batch_host for callers that keep several small batches in flight (the
  * root-parallel search: while one group of leaves is simulated, the host descends the trees of the next one).
  * `slot` in [0, 8) names an independent stream with its own device buffers.  submit enqueues copy-in, rollouts and

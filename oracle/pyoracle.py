@@ -419,6 +419,114 @@ class RefOracle(Oracle):
         self.lib.ref_rollout_free(_p(mv), len(mv), n_rollouts, _p(wdb), _p(total))
         return wdb, int(total[0])
 
+    # ---- everything above the evaluator: the reference's Heuristic.hpp / policies / MCTS.cpp, compiled unmodified
+    # ---- (oracle/ref_harness_search.cpp) --------------------------------------------------------------------------
+    def heads(self, moves, want_dw=False):
+        """Heuristic::EvaluationProbs / EvaluationValue (Heuristic.hpp:16-36) for the side to move.
+        -> (probs f32[225], value f32[, DensityWeight f32[2,225] = side to move, opponent]); None for terminal positions"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        probs = np.zeros(225, np.float32)
+        value = ctypes.c_float()
+        dw = np.zeros((2, 225), np.float32) if want_dw else None
+        rc = self.lib.ref_heads(_p(mv), len(mv), _p(probs), ctypes.byref(value), _p(dw))
+        if rc == 2:
+            return None
+        assert rc == 0, "the reference evaluator's self-check threw"
+        return (probs, np.float32(value.value), dw) if want_dw else (probs, np.float32(value.value))
+
+    def decisive_filter(self, moves, probs):
+        """Heuristic::DecisiveFilter (Heuristic.hpp:93-161) on a copy of `probs`"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        out = np.array(probs, np.float32)
+        rc = self.lib.ref_decisive_filter(_p(mv), len(mv), _p(out))
+        assert rc == 0, rc
+        return out
+
+    def hybrid_simulate(self, moves):
+        """TraditionalPolicy::prepare + simulate (Traditional.h:27-31,49-69) -> (value, probs); None for terminal positions"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        probs = np.zeros(225, np.float32)
+        value = ctypes.c_float()
+        rc = self.lib.ref_hybrid_simulate(_p(mv), len(mv), _p(probs), ctypes.byref(value))
+        if rc == 2:
+            return None
+        assert rc == 0, rc
+        return np.float32(value.value), probs
+
+    def guided_rollout_max(self, moves):
+        """Heuristic::MaxEvaluatedRollout (Heuristic.hpp:61-85) -> (winner, moves played)"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        played = np.zeros(226, np.int16)
+        n = ctypes.c_int()
+        w = self.lib.ref_guided_rollout_max(_p(mv), len(mv), _p(played), 226, ctypes.byref(n))
+        assert w != -3, "the reference evaluator threw"
+        return int(w), played[:n.value].tolist()
+
+    def sampled_first_move(self, moves, n_draws):
+        """Board::getRandomMove(EvaluationProbs) (Game.cpp:75-78) drawn n_draws times -> counts i32[225]"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        counts = np.zeros(225, np.int32)
+        rc = self.lib.ref_sampled_first_move(_p(mv), len(mv), int(n_draws), _p(counts))
+        assert rc == 0, rc
+        return counts
+
+    def guided_rollout_sampled(self, moves, n_games):
+        """n_games x Heuristic::RandomEvaluatedRollout -> (wdb i64[3] = white, draw, black; total moves)"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        wdb = np.zeros(3, np.int64)
+        total = np.zeros(1, np.int64)
+        rc = self.lib.ref_guided_rollout_sampled(_p(mv), len(mv), int(n_games), _p(wdb), _p(total))
+        assert rc == 0, rc
+        return wdb, int(total[0])
+
+    def rollout_philox(self, moves, rollouts, key, ctr_hi=0, position=0):
+        """the reference Board under the rollout kernel's Philox stream -> (wdb i32[3], total moves)"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        wdb = np.zeros(3, np.int32)
+        total = np.zeros(1, np.int64)
+        self.lib.ref_rollout_philox(_p(mv), len(mv), int(rollouts), ctypes.c_uint64(key), ctypes.c_uint32(ctr_hi),
+                                    ctypes.c_uint32(position), _p(wdb), _p(total))
+        return wdb, int(total[0])
+
+    def mcts_injected(self, moves, iterations, n_searches=0, sim_kind=0, key=1, tree=0, c_rollouts=5, c_puct=5.0,
+                      noise_seed=1, cap=1 << 20):
+        """The reference's MCTS (MCTS.cpp) with a deterministic injected `simulate` slot; see ref_harness_search.cpp.
+        -> dict(actions, pos, visits, value, prior, depth, n_children): the visited nodes of the last tree in pre-order"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        actions = np.zeros(max(n_searches, 1), np.int16)
+        pos, depth = np.zeros(cap, np.int16), np.zeros(cap, np.int16)
+        visits, nch = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        value, prior = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        self.lib.ref_mcts_injected.restype = ctypes.c_long
+        n = self.lib.ref_mcts_injected(_p(mv), len(mv), int(iterations), int(n_searches), int(sim_kind), ctypes.c_uint64(key),
+                                       ctypes.c_uint32(tree), int(c_rollouts), ctypes.c_double(c_puct), ctypes.c_uint32(noise_seed),
+                                       _p(actions), _p(pos), _p(visits), _p(value), _p(prior), _p(depth), _p(nch), ctypes.c_long(cap))
+        assert 0 <= n <= cap, n
+        return {"actions": actions[:n_searches].tolist(), "pos": pos[:n], "visits": visits[:n], "value": value[:n],
+                "prior": prior[:n], "depth": depth[:n], "n_children": nch[:n]}
+
+    def mcts_get_action(self, moves, iterations, policy="random", c_puct=5.0, c_rollouts=5, c_bias=0.0):
+        """The reference's own search with its own policies and RNG -> dict(action, seconds, size, root_visits)"""
+        mv = np.ascontiguousarray(moves, np.int16)
+        kind = {"random": 0, "traditional": 1, "poolrave": 2}[policy]
+        sec, size = ctypes.c_double(), ctypes.c_int64()
+        rv = np.zeros(225, np.int32)
+        a = self.lib.ref_mcts_get_action(_p(mv), len(mv), int(iterations), kind, ctypes.c_double(c_puct), int(c_rollouts),
+                                         ctypes.c_double(c_bias), ctypes.byref(sec), ctypes.byref(size), _p(rv))
+        return {"action": int(a), "seconds": sec.value, "size": int(size.value), "root_visits": rv}
+
+    def temp_based_probs(self, child_visits, n_moves_played):
+        v = np.ascontiguousarray(child_visits, np.float32)
+        out = np.zeros(225, np.float32)
+        self.lib.ref_temp_based_probs(_p(v), int(n_moves_played), _p(out))
+        return out
+
+    def add_noise(self, priors, seed):
+        v = np.ascontiguousarray(priors, np.float32)
+        out = np.zeros(225, np.float32)
+        self.lib.ref_add_noise(_p(v), ctypes.c_uint32(seed), _p(out))
+        return out
+
 
 _port = None
 _ref = None

@@ -17,6 +17,7 @@
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm may
 // load this library.
+#include <Eigen/Dense>   // the shim, before the access hack below reaches its standard headers
 #include <string>
 #include <cstdint>
 #include <cstring>

@@ -1,13 +1,19 @@
 """Row f1: the evaluator's policy heads -- Heuristic::DensityWeight / EvaluationProbs /
-EvaluationValue (include/algorithms/Heuristic.hpp:16-45) fused into ac_eval_kernel.
+EvaluationValue (include/algorithms/Heuristic.hpp:16-45), Heuristic::DecisiveFilter (:93-161) and
+TraditionalPolicy::hybridSimulate (include/policies/Traditional.h:49-69) fused into ac_eval_kernel.
 
-Floating point.  The reference computes these with Eigen float vectors; the kernel sums in a
-different order (lane-strided, then warp shuffles).  Tolerances, stated once:
-    probs: |gpu - oracle| <= 2e-6 + 2e-5 * |oracle|   (unit-norm vectors, entries <= 1)
-    value: |gpu - oracle| <= 2e-5                      (tanh output in [-1, 1])
-No reference test pins these functions and Heuristic.hpp itself needs real Eigen, which
-is absent here: the formulas are restated in oracle/pyoracle.py::policy_heads and evaluated on the
-density / score arrays of the COMPILED reference evaluator (oracle/_ref) for the golden fixture."""
+The checker is the REFERENCE ITSELF: Heuristic.hpp / Traditional.h compiled unmodified into oracle/_ref
+(oracle/ref_harness_search.cpp; `ref.heads`, `ref.decisive_filter`, `ref.hybrid_simulate`), plus the committed
+outputs of that build (tests/golden/reference_heads.json, made by tests/golden/make_golden_heads.py).  The numpy
+restatement in oracle/pyoracle.py is itself pinned against the compiled reference here and only stands in where
+oracle/_ref has not been built.
+
+Floating point.  The reference computes these with Eigen float vectors; Eigen, the shim the oracle is built
+against, and the kernel sum the same products in three different orders (SIMD packets / left to right /
+lane-strided then warp shuffles), so equality is up to rounding.  Tolerances in units of float32 ulp(1) = 2^-23:
+    probs: |gpu - ref| <= 16 ulp(1) + 168 ulp(1) * |ref|   (1.9e-6 + 2.0e-5 |ref|; unit-norm vectors, entries <= 1)
+    value: |gpu - ref| <= 168 ulp(1)                        (2.0e-5; tanh output in [-1, 1], its argument is a
+                                                             difference of two ~1e3-sized float dot products)"""
 import json
 import os
 
@@ -17,7 +23,17 @@ import pytest
 from conftest import GOLDEN, random_positions
 from oracle import pyoracle
 
-PROBS_ATOL, PROBS_RTOL, VALUE_ATOL = 2e-6, 2e-5, 2e-5
+ULP = 2.0 ** -23
+PROBS_ATOL, PROBS_RTOL, VALUE_ATOL = 16 * ULP, 168 * ULP, 168 * ULP
+
+
+def _checker():
+    """the compiled reference when it was built, else the numpy restatement over the C port"""
+    r = pyoracle.ref()
+    if r is not None:
+        return "reference", r.heads, r.hybrid_simulate
+    port = pyoracle.port()
+    return "restatement", (lambda m: pyoracle.policy_heads(port, m)), (lambda m: pyoracle.hybrid_simulate(port, m))
 
 
 def _positions(seed, n):
@@ -36,21 +52,52 @@ def golden():
 
 
 def test_heads_restatement_on_reference_fixture(port, golden):
-    """numpy restatement over the C oracle's evaluator state == committed values computed over the compiled reference"""
+    """numpy restatement over the C oracle's evaluator state vs the committed outputs of the COMPILED reference
+    (Heuristic.hpp itself): same formulas, different summation order"""
     for item in golden["positions"]:
         probs, value = pyoracle.policy_heads(port, item["moves"])
-        assert abs(float(value) - item["value"]) <= 1e-6
-        assert np.allclose(probs[item["top_cells"]], np.array(item["top_probs"], np.float32), rtol=1e-6, atol=1e-7)
+        assert abs(float(value) - item["value"]) <= VALUE_ATOL
+        want = np.array(item["top_probs"], np.float32)
+        assert np.all(np.abs(probs[item["top_cells"]] - want) <= 4 * ULP + 8 * ULP * np.abs(want))
         assert abs(float(np.abs(probs).sum()) - item["l1"]) <= 1e-4
+        hv, hp = pyoracle.hybrid_simulate(port, item["moves"])
+        want = np.zeros(225, np.float32)
+        want[item["hybrid_cells"]] = item["hybrid_probs"]
+        assert abs(float(hv) - item["hybrid_value"]) <= VALUE_ATOL
+        assert np.all(np.abs(hp - want) <= 4 * ULP + 8 * ULP * np.abs(want)), item["moves"]
 
 
-def test_heads_port_equals_reference(port, ref):
-    for m in _positions(3, 120):
-        if port.eval_moves(m)["winner"] != 0:
+def test_compiled_reference_reproduces_its_fixture(ref, golden):
+    for item in golden["positions"]:
+        probs, value = ref.heads(item["moves"])
+        assert float(value) == item["value"] and probs[item["top_cells"]].tolist() == item["top_probs"]
+        hv, hp = ref.hybrid_simulate(item["moves"])
+        assert float(hv) == item["hybrid_value"] and np.flatnonzero(hp).tolist() == item["hybrid_cells"]
+    for g in golden["guided_max"]:
+        assert ref.guided_rollout_max(g["moves"]) == (g["winner"], g["played"])
+
+
+def test_restatement_equals_compiled_heuristic_hpp(port, ref):
+    """oracle/pyoracle.py::policy_heads / decisive_filter / hybrid_simulate against Heuristic::EvaluationProbs /
+    EvaluationValue / DensityWeight / DecisiveFilter and TraditionalPolicy::hybridSimulate of the compiled reference"""
+    fired = 0
+    for m in _positions(3, 160):
+        h = ref.heads(m, want_dw=True)
+        if h is None:
+            assert port.eval_moves(m)["winner"] != 0 or len(m) == 225
             continue
-        pp, pv = pyoracle.policy_heads(port, m)
-        rp, rv = pyoracle.policy_heads(ref, m)
-        assert np.array_equal(pp, rp) and pv == rv          # identical inputs (scores, density) => identical floats
+        for orc in (port, ref):                             # the restatement over either evaluator state
+            pp, pv = pyoracle.policy_heads(orc, m)
+            assert np.all(np.abs(pp - h[0]) <= 4 * ULP + 8 * ULP * np.abs(h[0])) and abs(float(pv) - float(h[1])) <= VALUE_ATOL
+        assert np.all(h[2] >= 0) and all(abs(float(np.sqrt((d.astype(np.float64) ** 2).sum())) - 1.0) < 1e-5 for d in h[2] if d.any())
+        filtered = ref.decisive_filter(m, h[0])
+        mine, cand = pyoracle.decisive_filter(port, m, h[0])
+        assert np.array_equal(filtered != 0, mine != 0), m  # the same cells survive
+        assert np.all(np.abs(filtered - mine) <= 4 * ULP + 8 * ULP * np.abs(filtered))
+        fired += bool(cand)
+        hv, hp = ref.hybrid_simulate(m)
+        assert hv == h[1] and np.array_equal(hp, filtered)  # hybridSimulate = EvaluationValue + filtered EvaluationProbs
+    assert fired > 30
 
 
 def test_heads_properties(port):
@@ -65,16 +112,17 @@ def test_heads_properties(port):
 
 
 def _check_gpu(gk, lists, out):
-    port = pyoracle.port()
+    kind, heads, _ = _checker()
     probs, value = out["probs"].cpu().numpy(), out["value"].cpu().numpy()
     worst_p = worst_v = 0.0
     for i, m in enumerate(lists):
-        rp, rv = pyoracle.policy_heads(port, m)
+        rp, rv = heads(m)
         err = np.abs(probs[i] - rp) - (PROBS_ATOL + PROBS_RTOL * np.abs(rp))
         assert err.max() <= 0, (i, m, float(err.max()))
         assert abs(float(value[i]) - float(rv)) <= VALUE_ATOL, (i, m, float(value[i]), float(rv))
         worst_p = max(worst_p, float(np.abs(probs[i] - rp).max()))
         worst_v = max(worst_v, abs(float(value[i]) - float(rv)))
+    print(f"policy heads vs {kind}: worst |dprobs| = {worst_p / ULP:.1f} ulp(1), worst |dvalue| = {worst_v / ULP:.1f} ulp(1) over {len(lists)} positions")
     return worst_p, worst_v
 
 
@@ -109,10 +157,16 @@ def test_gpu_policy_heads_golden(gpu, golden):
     mv, st = pyoracle.pack_moves(lists)
     out = gpu.eval_policy_batch(gpu.pack_moves(mv, st))
     probs, value = out["probs"].cpu().numpy(), out["value"].cpu().numpy()
+    hyb = gpu.hybrid_simulate_batch(gpu.pack_moves(mv, st))
+    hprobs, hvalue = hyb["probs"].cpu().numpy(), hyb["value"].cpu().numpy()
     for i, it in enumerate(golden["positions"]):
         want = np.array(it["top_probs"], np.float32)
         assert np.all(np.abs(probs[i][it["top_cells"]] - want) <= PROBS_ATOL + PROBS_RTOL * np.abs(want))
         assert abs(float(value[i]) - it["value"]) <= VALUE_ATOL
+        want = np.zeros(225, np.float32)
+        want[it["hybrid_cells"]] = it["hybrid_probs"]
+        assert np.all(np.abs(hprobs[i] - want) <= PROBS_ATOL + PROBS_RTOL * np.abs(want)), it["moves"]
+        assert abs(float(hvalue[i]) - it["hybrid_value"]) <= VALUE_ATOL
 
 
 # ---- DecisiveFilter / hybridSimulate ------------------------------------------------------------------------
@@ -153,7 +207,7 @@ def test_hybrid_simulate_port_equals_reference(port, ref):
             continue
         pv, pp = pyoracle.hybrid_simulate(port, m)
         rv, rp = pyoracle.hybrid_simulate(ref, m)
-        assert pv == rv and np.array_equal(pp, rp)
+        assert pv == rv and np.array_equal(pp, rp)          # identical inputs (scores, density, flags) => identical floats
 
 
 @pytest.mark.gpu
@@ -166,6 +220,7 @@ def test_gpu_hybrid_simulate_vs_oracle(gpu):
     and can read 0 while contributions remain -- it depends on the move ORDER, which a from-scratch evaluation of
     the position cannot know.  Hence: kernel bits are a superset of the oracle's, on at most 2 % of the positions."""
     port = pyoracle.port()
+    kind, _, hybrid = _checker()
     lists = [m for m in _positions(41, 900) if port.eval_moves(m)["winner"] == 0]
     mv, st = pyoracle.pack_moves(lists)
     out = gpu.hybrid_simulate_batch(gpu.pack_moves(mv, st), want_flags=True)
@@ -173,7 +228,8 @@ def test_gpu_hybrid_simulate_vs_oracle(gpu):
     dflags = out["dflags"].cpu().numpy().view(np.uint32)
     flag_mismatch = prob_mismatch = 0
     for i, m in enumerate(lists):
-        rv, rp = pyoracle.hybrid_simulate(port, m)                              # leaves the evaluator at position m
+        rv, rp = hybrid(m)                                                      # TraditionalPolicy::hybridSimulate of the compiled reference
+        port.eval_moves(m)                                                      # leaves the port's evaluator at position m
         pf, cf, _ = port.eval_flags()
         want = np.array([_dflag_bits(pf[c], cf[c]) for c in range(225)], np.uint32)
         same_flags = np.array_equal(dflags[i], want)
@@ -186,4 +242,4 @@ def test_gpu_hybrid_simulate_vs_oracle(gpu):
         assert abs(float(value[i]) - float(rv)) <= VALUE_ATOL
     assert flag_mismatch <= len(lists) // 50, (flag_mismatch, len(lists))
     assert prob_mismatch <= len(lists) // 100, (prob_mismatch, len(lists))
-    print("hybridSimulate: flag-word mismatches", flag_mismatch, "prob mismatches", prob_mismatch, "of", len(lists))
+    print("hybridSimulate vs", kind, ": flag-word mismatches", flag_mismatch, "prob mismatches", prob_mismatch, "of", len(lists))
