@@ -177,13 +177,14 @@ def run_reference_arm(args, rank):
             ro.append(b)
     arm.close()
     value, rvalue = statistics.mean(ev), statistics.mean(ro)
-    sample = f"{n_eval} positions/step replayed through Evaluator::applyMove; {n_roll_pos}x{n_roll} rollouts/step"
+    sample = (f"each step replays the first {n_eval} positions of the set through Evaluator::applyMove on {arm.cores} host cores "
+              f"(one process per core); rollouts: {n_roll_pos}x{n_roll} per step")
+    config1 = reference_config1(max(1, min(args.steps, 3)))
     line = {
         "impl": "reference", "metric": "board evals/sec (15x15)", "value": value, "unit": "boards/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_eval / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": EVAL_WORKLOAD, "positions_per_gpu": N_EVAL_PER_GPU, "outputs": EVAL_OUTPUTS,
-                   "sample": f"each step replays the first {n_eval} positions of that set on the host cores"},
+        "config": bench_config(),
         "cpu_baseline": {"value": value, "unit": "boards/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": "boards/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -191,8 +192,32 @@ def run_reference_arm(args, rank):
                      "cpu_baseline": {"value": rvalue, "unit": "rollouts/s", "cores": arm.cores, "kind": arm.kind,
                                       "sample": f"{n_roll_pos} positions x {n_roll} rollouts per step"},
                      "e2e": {"value": rvalue, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "config1": config1,
     }
     _emit(line)
+
+
+def bench_config():
+    """the `config` object: the SAME dict in both arms (what differs between the arms lives in other keys)"""
+    return {"workload": EVAL_WORKLOAD, "positions_per_gpu": N_EVAL_PER_GPU, "outputs": EVAL_OUTPUTS}
+
+
+CONFIG1_WORKLOAD = ("configs[0]: 15x15 pure-MCTS random-rollout policy, MCTS(c_iterations=10000, RandomPolicy(5.0, 5))"
+                    ".get_action(Board()) from the empty board, single game")
+
+
+def reference_config1(repeats):
+    """configs[0] on the reference itself: MCTS.cpp + policies/Random.h compiled unmodified (oracle/_ref), one core --
+    the reference's search is single-threaded.  None when oracle/_ref was not built."""
+    from oracle import pyoracle
+    ref = pyoracle.ref()
+    if ref is None or not hasattr(ref.lib, "ref_mcts_get_action"):
+        return None
+    runs = [ref.mcts_get_action([], 10000, policy="random", c_puct=5.0, c_rollouts=5) for _ in range(repeats)]
+    best = min(r["seconds"] for r in runs)
+    return {"workload": CONFIG1_WORKLOAD, "value": 10000 / best, "unit": "playouts/s", "rollouts_per_sec": 50000 / best,
+            "seconds": best, "cores": 1, "kind": "reference", "tree_nodes": runs[0]["size"],
+            "sample": f"best of {repeats} runs of the whole call on one host core (Board, MCTS and RandomPolicy are the reference's own object code)"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -208,16 +233,32 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+KERNEL_SOURCES = {"ac_eval_kernel": "gk_eval.cu", "rollout_kernel": "gk_rollout.cu"}
+
+
+def git_blob_sha(path):
+    """the git blob id of a file's current content (sha1 of 'blob <len>\\0' + bytes), without calling git"""
+    import hashlib
+    data = open(path, "rb").read()
+    return hashlib.sha1(b"blob %d\0" % len(data) + data).hexdigest()
+
+
 def ncu_summary(kernel):
-    """Per-launch figures of the committed `ncu --set full` capture of the bench-size launch
-    (profiles/ncu_summary.json: dram bytes, warp instructions, issue-slot utilisation)."""
+    """Per-launch figures of the committed `ncu --set full` capture of the bench-size launch (profiles/ncu_summary.json:
+    dram bytes, warp instructions, issue-slot utilisation).  The capture is stamped with the git blob ids of the kernel
+    sources it was taken from (scripts/ncu_summary.py); when the source has changed since, the figures describe another
+    kernel and {} is returned, so that `traffic` and `roofline_issue` read null instead of a stale number."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get(kernel, {})
-        except Exception:
+    if not os.path.exists(path):
+        return {}
+    try:
+        doc = json.load(open(path))
+        src = KERNEL_SOURCES.get(kernel)
+        if src and doc.get("_sources", {}).get(src) != git_blob_sha(os.path.join(ROOT, "gomokuai_b200", "csrc", src)):
             return {}
-    return {}
+        return doc.get(kernel, {})
+    except Exception:
+        return {}
 
 
 _ISSUE_PEAKS = {}
@@ -246,6 +287,99 @@ def issue_roofline(kernel, launch_ms, sm_mhz, sm_count=148):
             "peak_nominal": nominal, "peaks_measured": dict(_ISSUE_PEAKS),
             "alu_pipe_pct_ncu": summ.get("alu_pipe_pct"), "active_lanes_per_inst": summ.get("threads_per_inst"),
             "source": "warp instructions per launch from profiles/ncu_summary.json, time and peak measured live"}
+
+
+def gpu_config1(gk):
+    """configs[0] through the drop-in: one tree, one leaf per playout, every simulate a 5-rollout GPU call (one fused launch
+    + one synchronisation).  Launch-latency bound by construction; a single game does not shard, so rank 0 alone runs it."""
+    from gomokuai_b200 import core
+    core.seed(1)
+    best, move, size = None, None, None
+    for _ in range(2):
+        b = core.Board()
+        m = core.MCTS(c_iterations=10000, policy=core.RandomPolicy(5.0, 5))
+        t0 = time.perf_counter()
+        move = int(m.get_action(b))
+        dt = time.perf_counter() - t0
+        best, size = (dt if best is None else min(best, dt)), int(m.size)
+    return {"workload": CONFIG1_WORKLOAD + ", through gomokuai_b200.core (CorePyExt mirror, simulate slot on the GPU)",
+            "value": 10000 / best, "unit": "playouts/s", "rollouts_per_sec": 50000 / best, "seconds": best, "gpu_launches": 10000,
+            "tree_nodes": size, "move": move, "replicas": "a single game does not shard: rank 0 only"}
+
+
+RP_TREES_TOTAL, RP_PLAYOUTS = 1024, 1_000_000
+
+
+def gpu_root_parallel(gk, torch, dist, dev, rank, world, barrier, moves=4):
+    """configs[3]: root-parallel MCTS, 1M playouts per move over ALL the GPUs of the job (strong scaling): RP_TREES_TOTAL
+    independent trees, cut evenly over the ranks, every tree does 1M / RP_TREES_TOTAL playouts from the same root with its own
+    Philox stream, leaves simulated by the rollout kernel in one batch per round, then ONE allreduce(sum) of the int64[3][225]
+    root statistics (gk_root_allreduce on the library's NCCL communicator) -- inside the timed region."""
+    import math
+    from gomokuai_b200 import core, root_parallel as rp
+    trees = RP_TREES_TOTAL // world
+    per_tree = math.ceil(RP_PLAYOUTS / RP_TREES_TOTAL)
+    cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    share = cores[rank * len(cores) // world:(rank + 1) * len(cores) // world] or cores
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        os.sched_setaffinity(0, share)                                   # the ranks' worker threads get disjoint cores
+    threads = max(2, len(share))
+    s = core.RootParallelSearch(trees=trees, c_rollouts=5, seed=1, replica_base=rank * trees, threads=threads)
+    if world > 1:
+        rp._ensure_gk_comm()
+    h_stats = torch.zeros((3, 225), dtype=torch.int64).pin_memory()
+    d_stats = torch.zeros((3, 225), dtype=torch.int64, device=dev)
+    b = core.Board()
+    for c in (112, 113, 97, 98):
+        b.apply_move(c)
+    rows, equal = [], True
+    for mv in range(1 + moves):                                          # the first move warms up (arenas, streams, communicator)
+        seed = 1000 + mv
+        barrier()
+        t0 = time.perf_counter()
+        local = s.run(b, per_tree, seed)
+        t1 = time.perf_counter()
+        h_stats.copy_(torch.from_numpy(local))
+        d_stats.copy_(h_stats, non_blocking=True)
+        if world > 1:
+            gk.root_allreduce(d_stats)
+        h_stats.copy_(d_stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        t2 = time.perf_counter()
+        merged = h_stats.numpy().copy()
+        t = torch.tensor([t2 - t0, t2 - t1, s.seconds_gpu, s.seconds_total], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        move = rp.best_move(merged)
+        if rank == 0:
+            # the same search on ONE rank with all the trees (tree streams are numbered globally, counts are integers)
+            alone = core.RootParallelSearch(trees=RP_TREES_TOTAL, c_rollouts=5, seed=1, replica_base=0, threads=2 if world == 1 else threads)
+            equal = equal and bool(np.array_equal(alone.run(b, per_tree, seed), merged))
+            del alone
+        if mv > 0:
+            rows.append({"seconds": float(t[0]), "exchange_us": float(t[1]) * 1e6, "worker_wait_for_gpu_s": float(t[2]),
+                         "search_s": float(t[3]), "move": int(move), "playouts": int(merged[0].sum()) + RP_TREES_TOTAL})
+        b.apply_move(move)
+        barrier()
+    if rank != 0:
+        return None
+    total_s = sum(r["seconds"] for r in rows)
+    playouts = sum(r["playouts"] for r in rows)
+    search_s = statistics.mean(r["search_s"] for r in rows)
+    return {"workload": "configs[3]: root-parallel MCTS, 1M playouts/move across the GPUs of the job with visit-count allreduce",
+            "metric": "root-parallel MCTS playouts/sec", "value": playouts / total_s, "unit": "playouts/s", "scaling": "strong",
+            "rollouts_per_sec": 5 * playouts / total_s, "seconds_per_move": total_s / len(rows),
+            "trees_total": RP_TREES_TOTAL, "trees_per_gpu": trees, "playouts_per_tree": per_tree, "c_rollouts": 5,
+            "host_threads_per_rank": threads, "cores_per_rank": len(share), "moves_timed": len(rows),
+            "exchange_us_median": statistics.median(r["exchange_us"] for r in rows),
+            "exchange": "5.4 KB H2D + gk_root_allreduce (ncclAllReduce int64[675], sum) + 5.4 KB D2H, inside the timed region" if world > 1
+                        else "5.4 KB H2D + D2H (one rank: no collective)",
+            "merged_equals_single_rank_search": equal,
+            "limiter": {"host_us_per_playout_per_worker_thread": search_s * (threads - 1) / (trees * per_tree) * 1e6,
+                        "worker_wait_for_gpu_frac": statistics.mean(r["worker_wait_for_gpu_s"] for r in rows) / max(search_s, 1e-9),
+                        "note": "the tree stays on the host (north_star): a move costs trees_per_gpu x playouts_per_tree host playouts / worker "
+                                "threads; the ranks of one box share its cores, so more GPUs add no host throughput"},
+            "gpu_launches_per_move": 2 * per_tree * min(4, max(1, trees // 64)), "moves": rows}
 
 
 def run_gpu_arm(args, rank, world, local_rank):
@@ -347,6 +481,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     if rank == 0:                                                       # the e2e result is the same data as the device path
         assert torch.equal(h_out["scores"][:4096], out["scores"][:4096].cpu())
         assert torch.equal(h_wdb, wdb.cpu())
+    # The ceiling of that copy when several GPUs deliver into ONE host memory system: every rank streams memsets with its
+    # share of the host cores at the same moment; the sum over ranks is what the box's DRAM takes.
+    host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    bw_threads = max(1, host_cores // world)
+    barrier()
+    host_bw = torch.tensor([gk.measure_host_write_bw(bw_threads, 128 << 20, 3)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(host_bw, op=dist.ReduceOp.SUM)
+    host_bw = float(host_bw.item())
 
     # ---- the other configurations of BASELINE.json, briefly (same timing rules; extra objects of the JSON line) -----
     extras = {}
@@ -362,7 +505,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                               "e2e": {"value": world * n_eval / pol_e2e_s, "unit": "boards/s", "h2d_bytes_per_step": n_eval * 64,
                                       "d2h_bytes_per_step": n_eval * 905, "ms_per_step": pol_e2e_s * 1e3}}
     del pol, h_pol
-    n_games = 8192                                                      # configs[4]: concurrent guided self-play games per GPU
+    n_games = 8192 // world                                             # configs[4]: 8192 concurrent guided self-play games across the GPUs of the job
     d_empty = torch.zeros((n_games, 16), dtype=torch.int32, device=dev)
     sp = {}
 
@@ -370,7 +513,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         sp["r"] = gk.guided_rollout_batch(d_empty, mode="sample", key=gk.SYNTH_KEY, game_base=rank * n_games, want_moves=True)
     sp_ms, _ = timed(selfplay_step, max(3, args.steps // 4), 2)
     sp_moves = float(sp["r"]["length"].float().sum().item())
-    extras["selfplay"] = {"metric": "pattern-guided self-play games/sec (configs[4], 8192 concurrent games per GPU, sampled moves)",
+    extras["selfplay"] = {"metric": "pattern-guided self-play games/sec (configs[4]: 8192 concurrent games in total, sampled moves)",
+                          "games_per_gpu": n_games, "scaling": "strong",
                           "value": world * n_games / (sp_ms * 1e-3), "unit": "games/s", "ms_per_step": sp_ms,
                           "evaluated_moves_per_sec": world * sp_moves / (sp_ms * 1e-3), "mean_game_length": sp_moves / n_games}
     n_enc = 1 << 18
@@ -382,6 +526,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                         "roofline": {"bound": "hbm", "achieved": enc_gbs, "unit": "GB/s", "kernel": "encode_states_kernel"}}
 
     clocks = sampler.summary()
+    extras["config1"] = gpu_config1(gk) if rank == 0 else None
+    extras["root_parallel"] = gpu_root_parallel(gk, torch, dist, dev, rank, world, barrier)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload --------------------------------------
     cpu_eval = cpu_roll = None
@@ -400,6 +546,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                     "sample": f"first {n_p} positions x 32768 rollouts, {w:.1f} s wall"}
         arm.close()
 
+    if arm is not None and extras["config1"] is not None:
+        extras["config1"]["cpu_baseline"] = reference_config1(2)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -413,13 +562,22 @@ def run_gpu_arm(args, rank, world, local_rank):
         "metric": "board evals/sec (15x15)", "value": eval_value, "unit": "boards/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": eval_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": EVAL_WORKLOAD, "positions_per_gpu": n_eval, "outputs": EVAL_OUTPUTS,
-                   "l2": "256 MB write between timed iterations; each step also streams 3.9 GB, > L2",
-                   "line_scans_per_sec": eval_value * 72},
+        "config": bench_config(),
+        "timing": {"l2": "256 MB write between timed iterations; each step also streams 3.9 GB, > L2",
+                   "clock": "CUDA events on the launching stream per step, max over ranks of the sum"},
+        "line_scans_per_sec": eval_value * 72,
         "clocks": clocks,
         "e2e": {"value": world * n_eval / e2e_eval_s, "unit": "boards/s", "h2d_bytes_per_step": n_eval * 64,
                 "d2h_bytes_per_step": n_eval * (3600 + 32 + 12 + 1), "ms_per_step": e2e_eval_s * 1e3,
-                "note": "gk_eval_batch_host: pinned host buffers, 3 chunks in flight; the 3.8 GB result copy is PCIe-bound"},
+                "host": {"achieved_write_gbs": world * n_eval * 3645 / e2e_eval_s / 1e9, "per_gpu_gbs": n_eval * 3645 / e2e_eval_s / 1e9,
+                         "cpu_stream_write_gbs": host_bw, "cpu_stream_threads": bw_threads * world,
+                         "frac_of_cpu_stream": world * n_eval * 3645 / e2e_eval_s / 1e9 / host_bw,
+                         "note": "results land in ONE host memory system (one NUMA node on this pool's boxes): one GPU is bound by its "
+                                 "PCIe link (~56 GB/s), several by the box's DRAM write bandwidth, measured here by all ranks' CPU threads "
+                                 "streaming memsets at the same moment"},
+                "compact": {"what": "gk_eval_policy_batch_host: probs f32[225] + value + winner = 905 B per board instead of 3645",
+                            "value": world * n_eval / pol_e2e_s, "unit": "boards/s"},
+                "note": "gk_eval_batch_host: pinned host buffers, 3 chunks in flight"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": eval_gbs, "peak": peak, "unit": "GB/s", "frac": eval_gbs / peak,
                      "traffic": ncu_summary("ac_eval_kernel").get("dram_bytes_per_launch"), "kernel": "ac_eval_kernel", "peak_source": peak_src,

@@ -422,6 +422,13 @@ def rollout_batch_host(boards, rollouts_per_pos, key=SYNTH_KEY, ctr_hi=0, pos_ba
     return wdb
 
 
+def measure_host_write_bw(threads, bytes_per_thread=256 << 20, repeats=3):
+    """GB/s of `threads` CPU threads streaming memsets into host memory (gk_measure_host_write_bw); needs no GPU."""
+    out = ctypes.c_double()
+    _check(lib().gk_measure_host_write_bw(int(threads), ctypes.c_size_t(bytes_per_thread), int(repeats), ctypes.byref(out)))
+    return out.value
+
+
 def rollout_trace_host(board, rollouts, key=SYNTH_KEY, ctr_hi=0, pos=0):
     """gk_rollout_trace_host: `rollouts` (<= 256) playouts of ONE position with their move lists.
     Returns dict(winners i8[R], lengths u8[R], moves u8[R,225])."""

@@ -4,6 +4,9 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -825,6 +828,40 @@ gk_status gk_host_free(void* ptr) {
 }
 
 // ---- host utilities ------------------------------------------------------------------------------------
+gk_status gk_measure_host_write_bw(int threads, size_t bytes_per_thread, int repeats, double* gb_per_s) {
+    if (threads <= 0 || threads > 256 || bytes_per_thread < (size_t(1) << 20) || repeats <= 0 || !gb_per_s)
+        return fail(GK_ERR_INVALID, "bad arguments");
+    std::vector<unsigned char*> bufs(threads, nullptr);
+    for (auto& b : bufs) {
+        b = static_cast<unsigned char*>(std::malloc(bytes_per_thread));
+        if (!b) { for (auto* q : bufs) std::free(q); return fail(GK_ERR_INVALID, "out of host memory"); }
+    }
+    std::vector<double> secs(threads, 0.0);
+    std::atomic<int> ready{ 0 };
+    std::atomic<bool> go{ false };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; ++w)
+        pool.emplace_back([&, w]() {
+            std::memset(bufs[w], 1, bytes_per_thread);                   // first touch: the pages exist before the clock starts
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int r = 0; r < repeats; ++r) {
+                std::memset(bufs[w], r + 2, bytes_per_thread);           // large memset: glibc streams with non-temporal stores
+                asm volatile("" :: "r"(bufs[w]) : "memory");
+            }
+            secs[w] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+    while (ready.load() < threads) std::this_thread::yield();
+    go.store(true, std::memory_order_release);
+    for (auto& th : pool) th.join();
+    double slowest = 0;
+    for (double v : secs) slowest = std::max(slowest, v);
+    for (auto* q : bufs) std::free(q);
+    *gb_per_s = double(threads) * double(bytes_per_thread) * repeats / slowest / 1e9;
+    return GK_OK;
+}
+
 gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards) {
     if (!moves || !starts || !h_boards || n < 0) return fail(GK_ERR_INVALID, "bad arguments");
     for (int p = 0; p < n; ++p) {

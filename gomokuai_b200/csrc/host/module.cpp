@@ -194,7 +194,7 @@ PYBIND11_MODULE(CorePyExt, mod) {
                  cfg.trees = trees; cfg.c_rollouts = c_rollouts; cfg.c_puct = c_puct; cfg.seed = seed;
                  cfg.replica_base = replica_base; cfg.threads = threads; cfg.noise = noise; cfg.eager = eager;
                  return new RootParallelSearch(cfg);
-             }), "trees"_a = 256, "c_rollouts"_a = 5, "c_puct"_a = C_PUCT, "seed"_a = 1, "replica_base"_a = 0, "threads"_a = 0, "noise"_a = true,
+             }), "trees"_a = 256, "c_rollouts"_a = 5, "c_puct"_a = C_PUCT, "seed"_a = 1, "replica_base"_a = 0, "threads"_a = 0, "noise"_a = false,
              "eager"_a = false)
         .def("run", [](RootParallelSearch& s, const Board& b, int playouts_per_tree, py::object seed) {
             const bool reseed = !seed.is_none();

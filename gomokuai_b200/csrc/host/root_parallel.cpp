@@ -307,7 +307,7 @@ static void select_leaf(Tree& t, double c_puct, std::uint32_t* packed) {
 static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg, std::size_t root_depth) {
     const float black_value = static_cast<float>(r[2] - r[0]) / static_cast<float>(cfg.c_rollouts);
     if (!t.terminal) {
-        expand(t, t.leaf, t.board, cfg.eager || (t.leaf == 0 && cfg.noise));
+        expand(t, t.leaf, t.board, cfg.eager || t.leaf == 0);          // the root always gets its block: its scan vectorises
         if (t.leaf == 0 && cfg.noise) {                              // Default::AddNoise on the root's fresh children
             const ANode& rt = t.nodes[0];
             std::gamma_distribution<float> gamma(0.05f, 1.0f);

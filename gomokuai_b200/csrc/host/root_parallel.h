@@ -22,7 +22,10 @@ struct RootParallelConfig {
     std::uint64_t seed = 1;     // Philox key
     int replica_base = 0;       // first global tree index of this rank (keeps streams disjoint across ranks)
     int threads = 0;            // host threads: one drives the GPU, the rest do tree work (0 = hardware concurrency; at least 2)
-    bool noise = true;          // Dirichlet noise on root priors (Default::AddNoise, MonteCarlo.hpp:97-108)
+    // Dirichlet noise on the priors of the root's fresh children.  An EXTENSION, off by default: the reference's
+    // Default::AddNoise runs before the playouts and only touches children that already exist (MonteCarlo.hpp:97-108,
+    // MCTS.cpp:182), so a search from a fresh tree -- which is what every root-parallel move is -- draws none.
+    bool noise = false;
     bool eager = false;         // materialise every child at expansion like the reference (slow; kept to test the lazy tree against)
 };
 

@@ -56,9 +56,10 @@ def best_move(stats):
 _searchers = {}
 
 
-def search(board, playouts_total, trees_per_rank=256, c_rollouts=5, c_puct=5.0, seed=1, noise=True, threads=0, group=None):
+def search(board, playouts_total, trees_per_rank=256, c_rollouts=5, c_puct=5.0, seed=1, noise=False, threads=0, group=None):
     """One move of root-parallel search. Returns (best cell, merged stats int64[3,225], local RootParallelSearch).
-    The searcher (worker threads, tree arenas, page-locked buffers) is kept between moves."""
+    The searcher (worker threads, tree arenas, page-locked buffers) is kept between moves; the number of moves already
+    on the board is mixed into the seed, so consecutive moves of one game draw different playout streams."""
     import torch.distributed as dist
     from .core import RootParallelSearch
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if (dist.is_available() and dist.is_initialized()) else (0, 1)
@@ -69,6 +70,6 @@ def search(board, playouts_total, trees_per_rank=256, c_rollouts=5, c_puct=5.0, 
         _searchers.clear()
         s = _searchers[key] = RootParallelSearch(trees=trees_per_rank, c_rollouts=c_rollouts, c_puct=c_puct, seed=seed,
                                                  replica_base=rank * trees_per_rank, threads=threads, noise=noise)
-    local = s.run(board, per_tree, seed)
+    local = s.run(board, per_tree, (int(seed) * 1000003 + len(board.move_record)) & 0xffffffffffffffff)
     merged = allreduce_root_stats(local, group)
     return best_move(merged), merged, s

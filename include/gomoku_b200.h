@@ -236,6 +236,10 @@ gk_status gk_host_alloc(void** out, size_t bytes);
 gk_status gk_host_free(void* ptr);
 
 /* ---- host utilities (no GPU needed) ------------------------------------------------- */
+/* Write bandwidth of the host's memory as `threads` CPU threads see it (each streams `repeats` large memsets over its own
+ * buffer; the slowest thread sets the clock): the ceiling of every *_host result copy when several GPUs of one box
+ * deliver into the same DRAM (bench.py prints it next to the achieved end-to-end rate). */
+gk_status gk_measure_host_write_bw(int threads, size_t bytes_per_thread, int repeats, double* gb_per_s);
 /* move lists (black first, alternating; position i = moves[starts[i]..starts[i+1])) -> packed boards */
 gk_status gk_pack_moves(const int16_t* moves, const int64_t* starts, int n, uint32_t* h_boards);
 /* The synthetic "random mid-game" set of BASELINE.json / SURVEY.md section 8(d): position

@@ -19,13 +19,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(_HERE, "libgomoku_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libgomoku_ref.so")
 REFERENCE_ROOT = "/root/reference/core/lib"
+PYREF_DIR = os.path.join(_HERE, "_ref", "pyref")     # the reference's agents/ + config.py as sourceless byte code (make pyref)
 
 
 def build(want_ref=True):
     """Compile the C restatement, and oracle/_ref when /root/reference is present."""
     subprocess.run(["make", "-s", "-C", _HERE, "port"], check=True)
     if want_ref and os.path.isdir(REFERENCE_ROOT):
-        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", _HERE, "ref", "pyref"], check=True)
 
 
 def _p(a):

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box pass of a round (run through gpurun):  scripts/gpu_round.sh r02a [tests|bench|profile ...]
+#   tests    python -m pytest tests -m gpu  (rebuilds the library on the box first, see tests/conftest.py)
+#   bench    the default bench command, 1 GPU
+#   profile  scripts/profile_round.sh <tag>: ncu launch list + one `--set full` capture with source pages
+set -u
+tag=${1:-rXX}; shift
+what=${*:-tests bench profile}
+out=gpurun_out
+mkdir -p $out
+rc=0
+for w in $what; do
+  case $w in
+    tests)   python -m pytest tests -m gpu -x -q -s > $out/pytest_$tag.log 2>&1; r=$?; tail -5 $out/pytest_$tag.log; [ $r -ne 0 ] && rc=$r ;;
+    bench)   python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err; r=$?; head -c 600 $out/bench_$tag.json; echo; [ $r -ne 0 ] && { tail -5 $out/bench_$tag.err; rc=$r; } ;;
+    refarm)  python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err || rc=$? ;;
+    profile) bash scripts/profile_round.sh $tag || rc=$? ;;
+    *)       echo "unknown step $w" ;;
+  esac
+done
+exit $rc

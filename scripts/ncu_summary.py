@@ -46,7 +46,14 @@ for r in rows[2:]:
         "stalls_per_issue": {x.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): num(r, x)
                              for x in h if "issue_stalled" in x and "per_issue_active" in x and (num(r, x) or 0) > 0.1},
     }
-dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_summary.json")
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, root)
+from bench import git_blob_sha  # noqa: E402
+# stamp: the kernel sources this capture was taken from (bench.py drops the figures once a source has changed)
+out["_sources"] = {f: git_blob_sha(os.path.join(root, "gomokuai_b200", "csrc", f)) for f in ("gk_eval.cu", "gk_rollout.cu")}
+dst = os.path.join(root, "profiles", "ncu_summary.json")
 json.dump(out, open(dst, "w"), indent=1)
 for k, v in out.items():
+    if k.startswith("_"):
+        continue
     print(k, v["ncu_duration"], "warp-inst", v["warp_inst_per_launch"], "issue%", v["issue_active_pct"], "dram bytes", v["dram_bytes_per_launch"])

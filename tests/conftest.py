@@ -64,10 +64,22 @@ def ref():
 
 @pytest.fixture(scope="session")
 def gk():
-    """The product package; the shared library must already be built in-tree."""
+    """The product package.  On a GPU box the library and CorePyExt are REBUILT from the sources of the snapshot once per
+    session, before anything loads them (nvcc is in the image), so the kernels under test are the ones in the tree and
+    not a stale prebuilt file; GK_NO_REBUILD=1 skips that.  Without a GPU the in-tree build is used (built if missing)."""
     import gomokuai_b200
-    if not os.path.exists(gomokuai_b200.LIB_PATH):
-        from gomokuai_b200 import build
+    from gomokuai_b200 import build
+    on_gpu_box = False
+    try:
+        import torch
+        on_gpu_box = torch.cuda.is_available()
+    except Exception:
+        pass
+    if on_gpu_box and not os.environ.get("GK_NO_REBUILD"):
+        assert gomokuai_b200._lib is None and "gomokuai_b200.CorePyExt" not in sys.modules, "rebuild must precede the first load"
+        build.build(force=True)
+        build.build_pyext(force=True)
+    elif not os.path.exists(gomokuai_b200.LIB_PATH):
         build.build()
     gomokuai_b200.lib()
     return gomokuai_b200

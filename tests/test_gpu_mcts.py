@@ -141,7 +141,7 @@ def test_root_allreduce_through_the_c_abi(gpu):
         gpu.nccl_shutdown()
 
 
-def test_root_parallel_pipeline_is_invisible_in_the_statistics(core, monkeypatch):
+def test_root_parallel_pipeline_is_invisible_in_the_statistics(core):
     """Four tree groups in flight, chunked work distribution, a helping driver thread: none of it may show in the
     result -- a tree's Philox stream is (round, global tree index), its noise stream is seeded per tree."""
     b = core.Board()
@@ -151,9 +151,6 @@ def test_root_parallel_pipeline_is_invisible_in_the_statistics(core, monkeypatch
     assert ref[0].sum() == 300 * 59
     for threads in (3, 7):
         assert np.array_equal(core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=threads).run(b, 60), ref)
-    monkeypatch.setenv("GK_RP_DRIVER_HELPS", "0")
-    assert np.array_equal(core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=4).run(b, 60), ref)
-    monkeypatch.delenv("GK_RP_DRIVER_HELPS")
     s = core.RootParallelSearch(trees=300, c_rollouts=5, seed=5, threads=4)
     first = s.run(b, 30)
     assert np.array_equal(s.run(b, 60, 21), ref)                    # the searcher is reusable and reseedable
