@@ -513,10 +513,15 @@ def run_gpu_arm(args, rank, world, local_rank):
         sp["r"] = gk.guided_rollout_batch(d_empty, mode="sample", key=gk.SYNTH_KEY, game_base=rank * n_games, want_moves=True)
     sp_ms, _ = timed(selfplay_step, max(3, args.steps // 4), 2)
     sp_moves = float(sp["r"]["length"].float().sum().item())
+    sp_full_ms, _ = timed(lambda: gk.guided_rollout_batch(d_empty, mode="sample", key=gk.SYNTH_KEY, game_base=rank * n_games,
+                                                          want_moves=True, full_rescan=True), 3, 1)
     extras["selfplay"] = {"metric": "pattern-guided self-play games/sec (configs[4]: 8192 concurrent games in total, sampled moves)",
                           "games_per_gpu": n_games, "scaling": "strong",
                           "value": world * n_games / (sp_ms * 1e-3), "unit": "games/s", "ms_per_step": sp_ms,
-                          "evaluated_moves_per_sec": world * sp_moves / (sp_ms * 1e-3), "mean_game_length": sp_moves / n_games}
+                          "evaluated_moves_per_sec": world * sp_moves / (sp_ms * 1e-3), "mean_game_length": sp_moves / n_games,
+                          "kernel": "guided_kernel: per move only the four lines through the new stone are re-scanned (before / after)",
+                          "full_rescan": {"value": world * n_games / (sp_full_ms * 1e-3), "unit": "games/s", "ms_per_step": sp_full_ms,
+                                          "kernel": "ac_eval_kernel<true, true>: the whole board after every move (identical games)"}}
     n_enc = 1 << 18
     d_last = torch.full((n_enc, 2), -1, dtype=torch.int16, device=dev)
     enc_ms, _ = timed(lambda: gk.encode_states_batch(d_boards[:n_enc], d_last, augment=True), max(3, args.steps // 4), 2)

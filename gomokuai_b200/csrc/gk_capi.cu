@@ -104,7 +104,7 @@ gk::EvalArgs eval_args(const gk_table* t, const uint32_t* boards, long long n, i
     a.next16 = t->d_next16; a.erec = t->d_erec; a.n_states = t->host.n_states; a.n_clones = t->host.n_clones;
     a.patrec = t->d_patrec; a.n_patterns = (int)t->host.patrec.size();
     a.tape_src = t->d_tape_src; a.tape_info = t->d_tape_info; a.tape_steps = t->host.tape_steps;
-    a.root_off = t->host.root_off; a.start_off = t->host.start_off; a.list_cap = t->host.list_cap;
+    a.root_off = t->host.root_off; a.start_off = t->host.start_off; a.list_cap = t->host.list_cap; a.trail_pad = t->host.trail_pad;
     a.boards = boards; a.n = n;
     a.scores = scores; a.pat_totals = pat; a.cmp_totals = cmp; a.winner = winner;
     return a;
@@ -519,11 +519,13 @@ gk_status gk_guided_rollout_batch(const gk_table* t, const uint32_t* d_boards, i
                                   uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner, int16_t* d_length,
                                   int16_t* d_moves, uint32_t* d_final_boards, void* stream) {
     if (gk_status s = require_device()) return s;
+    const int full_rescan = (mode & GK_GUIDED_FULL_RESCAN) ? 1 : 0;
+    mode &= ~GK_GUIDED_FULL_RESCAN;
     if (!t || n < 0 || (n > 0 && !d_boards) || (mode != 1 && mode != 2) || max_moves < 0 || max_moves > GK_CELLS)
         return fail(GK_ERR_INVALID, "bad arguments");
     if (gk_status s = ensure_uploaded(t)) return s;
     gk::EvalArgs a = eval_args(t, d_boards, n, nullptr, nullptr, nullptr, nullptr);
-    a.g_mode = mode; a.g_key_lo = uint32_t(philox_key); a.g_key_hi = uint32_t(philox_key >> 32); a.g_ctr_hi = ctr_hi;
+    a.g_mode = mode; a.g_full_rescan = full_rescan; a.g_key_lo = uint32_t(philox_key); a.g_key_hi = uint32_t(philox_key >> 32); a.g_ctr_hi = ctr_hi;
     a.g_game_base = game_base; a.g_max_moves = max_moves;
     a.g_winner = d_winner; a.g_length = d_length; a.g_moves = d_moves; a.g_final = d_final_boards;
     GK_CUDA(gk::launch_eval(a, g_sm_count, static_cast<cudaStream_t>(stream)));

@@ -93,12 +93,13 @@ __device__ __forceinline__ uint32_t squeeze_even(uint32_t x) {
 // which (compound type, favour, perspective) compound flags are set in ANY direction -- what
 // Heuristic::DecisiveFilter reads through Record::get(favour, perspective) (Heuristic.hpp:147-151):
 //   bit (type - 4) * 4 + Group(favour, perspective), bit 16 + compound type * 4 + Group(favour, perspective)
+// delta = -1 (incremental guided playouts only) takes the emission back: Updater::updatePatterns with delta = -1.
 __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflags, const PatRec rec, int vend, uint32_t dir,
-                                                   int stride) {
+                                                   int stride, int delta = 1) {
     const uint32_t type = pr_type(rec.w0), black = pr_black(rec.w0);
     if (type == kTypeFive) return black ? 1u : 2u;                              // :140-145
-    atomicAdd(&ws.totals[black * 8 + type], 1u);                                // :147
-    const int score = dir >= 2 ? int(rec.w1 >> 16) : int(rec.w1 & 0xffffu);     // :151-152
+    atomicAdd(&ws.totals[black * 8 + type], uint32_t(delta));                   // :147
+    const int score = delta * (dir >= 2 ? int(rec.w1 >> 16) : int(rec.w1 & 0xffffu));   // :151-152
     int* self = ws.scores + black * 3 * kCells;                                 // Group(f, f)
     int* rival = ws.scores + (black + 1) * kCells;                              // Group(f, -f)
     const uint32_t ncells = pr_ncells(rec.w0);
@@ -120,7 +121,7 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
                 atomicAdd(&self[cell], score);
                 if (lo) {
                     uint32_t* word = &ws.flags[cell * 2 + black];
-                    atomicAdd(word, lo);                                        // 2-bit BINARY count per (class, direction); it never exceeds 2 (theorem T2)
+                    atomicAdd(word, delta > 0 ? lo : 0u - lo);                  // 2-bit BINARY count per (class, direction); it never exceeds 2 (theorem T2)
                 }
             }
         }
@@ -136,7 +137,7 @@ __device__ __forceinline__ uint32_t apply_emission(WarpSmem& ws, uint32_t* dflag
 template <bool kRawBoard>
 __device__ __forceinline__ void anti_cells(const uint32_t* board, uint32_t* dflags, uint32_t anti_bit, uint32_t next_addr,
                                            uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
-                                           int cell, uint32_t dir, uint32_t cclass, int* rival) {
+                                           int cell, uint32_t dir, uint32_t cclass, int* rival, int amount = 600) {
     const int cx = cell % kWidth, cy = cell / kWidth;
     const int stride = dir_stride(dir);
     // steps i in [lo, hi] of the window are on the board, the rest reads as '?'
@@ -179,7 +180,7 @@ __device__ __forceinline__ void anti_cells(const uint32_t* board, uint32_t* dfla
             for (uint32_t n = pr_ncells(rec.w0); n != 0; --n, cells >>= 4) {
                 const int j = int(cells & 7u);
                 if (j != off) {
-                    atomicAdd(&rival[cell + (off - j) * stride], 600);          // updatePose(current, component, -favour), :536
+                    atomicAdd(&rival[cell + (off - j) * stride], amount);       // updatePose(current, component, -favour), :536
                     if (dflags) atomicOr(&dflags[cell + (off - j) * stride], anti_bit);
                 }
             }
@@ -194,7 +195,7 @@ __device__ __forceinline__ void anti_cells(const uint32_t* board, uint32_t* dfla
 // `scores` / `totals32` are the warp's shared accumulators, or (deferred form) the board's stored score block and
 // the 32-bit word holding its first compound total in global memory (`totals_stride_bits` = 16 there: uint16 fields).
 __device__ __forceinline__ void compound_at(int* scores, uint32_t* totals32, int totals_field_bits, uint32_t* dflags,
-                                            uint32_t f, uint32_t idx, uint32_t& t0, uint32_t& t1) {
+                                            uint32_t f, uint32_t idx, uint32_t& t0, uint32_t& t1, int amount = 600) {
     const int cell = idx >> 1;
     const uint32_t black = idx & 1u;
     // states: S0 0, L2 1, LD3 2, To33 3, To43 4, To44 5
@@ -227,8 +228,8 @@ __device__ __forceinline__ void compound_at(int* scores, uint32_t* totals32, int
     t0 = t1 = 0;
     const int type = state - 3;
     if (type < 0) return;   // needs an L3 plus two lower-class patterns on one cell of one line: excluded by exhaustive line enumeration (tests)
-    atomicAdd(&scores[black * 3 * kCells + cell], 600 * ncomp);                 // updateCritical, :515-518
-    atomicAdd(&scores[(black + 1) * kCells + cell], 600 * ncomp);
+    atomicAdd(&scores[black * 3 * kCells + cell], amount * ncomp);              // updateCritical, :515-518
+    atomicAdd(&scores[(black + 1) * kCells + cell], amount * ncomp);
     if (totals32) {                                                             // one compound, :505-508
         const uint32_t field = black * 3 + uint32_t(type);
         if (totals_field_bits == 32) atomicAdd(&totals32[field], 1u);
@@ -461,6 +462,355 @@ __device__ GK_HEADS_INLINE int select_move(const float* prob, int lane, int mode
         }
     }
     return __reduce_min_sync(0xffffffffu, chosen);
+}
+
+// ======================= incremental guided playouts (BASELINE config 5) ===================================
+// A playout adds ONE stone per evaluation, and a stone only changes the four lines through it (exhaustive theorem T5,
+// an emission that does not cover the changed cell is unchanged).  guided_kernel therefore evaluates a
+// game's START position from scratch (all 72 lines, as ac_eval_kernel) and afterwards, per move, rescans only those four
+// lines twice -- as they were (emissions taken back, Updater::updatePatterns with delta = -1) and as they are (+1) --
+// which is the reference's own incremental scheme (Updater::updateMove, Pattern.cpp:274-302) at line granularity.
+// Between moves the warp's shared block keeps the PATTERN state only: scores, per-cell compound-class counts, totals.
+// The two derived parts are added per evaluation: compounds (a function of the counts: +600s applied before the heads
+// read the maps and taken back after the move is chosen) and the block score (+160 where a player's density weight is
+// positive, folded into the heads from the density accumulators the guided variant keeps anyway).
+// Every float the heads compute is produced by the same operations in the same order as ac_eval_kernel<true, true>,
+// so both variants play IDENTICAL games (tests/test_guided.py).
+
+// the line through cell m in direction dir, restricted to the board (Mapping.cpp:11-25): first cell, cell stride, length
+__device__ __forceinline__ void line_through(int m, uint32_t dir, int& cell0, int& stride, int& len) {
+    const int my = m / kWidth, mx = m - my * kWidth;
+    if (dir == 0) { cell0 = my * kWidth; stride = 1; len = kWidth; }
+    else if (dir == 1) { cell0 = mx; stride = kWidth; len = kHeight; }
+    else if (dir == 2) { const int k = mx - my; cell0 = k > 0 ? k : -k * kWidth; stride = kWidth + 1; len = kWidth - (k > 0 ? k : -k); }
+    else {
+        const int t = mx + my, x0 = t < kWidth ? t : kWidth - 1;
+        cell0 = (t - x0) * kWidth + x0; stride = kWidth - 1; len = (t < kWidth ? t : 2 * (kWidth - 1) - t) + 1;
+    }
+}
+
+// Compounds of the current counts, added (amount = +600) or taken back (-600): the flag scan, Compound::Test, locate and
+// the updateAntis rescans of ac_eval_kernel's phase 4, in place.  `clist`: scratch for up to 450 candidates.
+__device__ __forceinline__ void compounds_pass(WarpSmem& ws, unsigned short* clist, int lane, uint32_t lt, uint32_t next_addr,
+                                               uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
+                                               int amount) {
+    int cn = 0;
+    const uint2* f2 = reinterpret_cast<const uint2*>(ws.flags);
+#pragma unroll 2
+    for (int r = 0; r < (kCells + 31) / 32; ++r) {
+        const int cell = r * 32 + lane;
+        const uint2 f = f2[cell < kCells ? cell : kCells];
+        const bool maybe = (((f.x & (f.x - 1)) | (f.y & (f.y - 1))) | ((f.x | f.y) & 0xaaaaaau)) != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, maybe);
+        if (m) {
+            uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu, bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
+            bw0 |= (bw0 >> 1) & 0x55u;
+            bw1 |= (bw1 >> 1) & 0x55u;
+            const bool h0 = (bw0 & (bw0 - 1)) != 0, h1 = (bw1 & (bw1 - 1)) != 0;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+            if (h0) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
+            cn += __popc(m0);
+            if (h1) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
+            cn += __popc(m1);
+        }
+    }
+    __syncwarp();
+    for (int base = 0; base < cn; base += 32) {
+        uint32_t t0 = 0, t1 = 0;
+        if (base + lane < cn) {
+            const uint32_t idx = clist[base + lane];
+            compound_at(ws.scores, nullptr, 32, nullptr, ws.flags[idx], idx, t0, t1, amount);
+        }
+        const uint32_t owners = __ballot_sync(0xffffffffu, t0 != 0);
+        const int ntask = 2 * __popc(owners);
+        for (int s0 = 0; s0 < ntask; s0 += 32) {
+            const int s = s0 + lane;
+            const int owner = s < ntask ? int(__fns(owners, 0, (s >> 1) + 1)) : 0;
+            const uint32_t ta = __shfl_sync(0xffffffffu, t0, owner), tb = __shfl_sync(0xffffffffu, t1, owner);
+            const uint32_t task = (s & 1) ? tb : ta;
+            if (s < ntask) {
+                const uint32_t black = (task >> 8) & 1u;
+                anti_cells<false>(ws.board, nullptr, 0u, next_addr, root_off, emit_thr, s_erec, s_patrec, int(task & 0xffu),
+                                  (task >> 9) & 3u, (task >> 11) & 3u, ws.scores + (black + 1) * kCells, amount);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// The heads of policy_heads() for the incremental variant: the density accumulators are always valid, the DensityWeight
+// values are recomputed from them where policy_heads() parks them in ws.flags (the counts must survive here), and the
+// block score the maps do not hold is added as the maps are read: +160 on S(P, P) where P's weight is positive
+// (Pattern.cpp:244,268).  Same float operations in the same order as policy_heads().
+__device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint32_t mine, int lane, const uint16_t* dacc,
+                                                 int& n_stones, int& to_move) {
+    const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
+    const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
+    const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
+    const int p = n_black == n_white ? 1 : 0;
+    const int dc = lane >= 15, dx = lane - 15 * dc;
+    const uint32_t occ = mine | __shfl_sync(0xffffffffu, mine, lane < 15 ? lane + 15 : lane - 15);
+    const bool live = lane < 30;
+    const uint32_t xbit = live ? 1u << dx : 0u;
+    const uint16_t* acc_p = dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30));
+    const int step = live ? kWidth : 0;
+    float n2 = 0.f;
+#pragma unroll 1
+    for (int y = 0; y < kHeight; ++y) {
+        const uint32_t full = live ? uint32_t(*acc_p) : 0u;
+        acc_p += step;
+        const uint32_t orow = __shfl_sync(0xffffffffu, occ, y);
+        float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
+        v = (orow & xbit) ? 0.f : v;
+        n2 += v * v;
+    }
+    float n2w = lane < 15 ? n2 : 0.f, n2b = lane >= 15 ? n2 : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        n2w += __shfl_xor_sync(0xffffffffu, n2w, d);
+        n2b += __shfl_xor_sync(0xffffffffu, n2b, d);
+    }
+    const float nrm_w = n2w > 0.f ? sqrtf(n2w) : 1.f, nrm_b = n2b > 0.f ? sqrtf(n2b) : 1.f;
+    const int* s_self = ws.scores + 3 * p * kCells;
+    const int* s_anti = ws.scores + (2 * (1 - p) + p) * kCells;
+    const int* s_rival = ws.scores + 3 * (1 - p) * kCells;
+    float a2 = 0.f, sdot = 0.f, rdot = 0.f;
+#pragma unroll 1
+    for (int c = lane; c < kCells; c += 32) {
+        const bool empty = cell_value(ws.board, c) == 0u;
+        const uint32_t fw = dacc[c], fb = dacc[kCells + c];
+        float vw = (3.f * float(fw >> 8)) / (1.f + 2.f * float(fw & 0xffu)), vb = (3.f * float(fb >> 8)) / (1.f + 2.f * float(fb & 0xffu));
+        vw = empty ? vw : 0.f;
+        vb = empty ? vb : 0.f;
+        const float w0 = vw / nrm_w, w1 = vb / nrm_b;
+        const float wp = p ? w1 : w0, wr = p ? w0 : w1;
+        const float vp = p ? vb : vw, vr = p ? vw : vb;                     // un-normalised weights: > 0 <=> the block score applies
+        const int self_i = s_self[c] + (vp > 0.f ? 160 : 0), rival_i = s_rival[c] + (vr > 0.f ? 160 : 0);
+        const float self_worthy = float(self_i) * wp, rival_anti = float(s_anti[c]) * wr;
+        const float av = 0.6f * self_worthy + 0.4f * rival_anti;
+        prob[c] = av;
+        a2 += av * av;
+        sdot += float(self_i) * wp;
+        rdot += float(rival_i) * wr;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, d);
+        rdot += __shfl_xor_sync(0xffffffffu, rdot, d);
+    }
+    const bool empty_board = n_black + n_white == 0;
+    const float an = a2 > 0.f ? sqrtf(a2) : 1.f;
+    n_stones = n_black + n_white;
+    to_move = p;
+#pragma unroll 1
+    for (int c = lane; c < kCells; c += 32)
+        prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : prob[c] / an;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
+guided_kernel(EvalArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n_rows = a.n_clones + a.n_states;
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* s_erec = reinterpret_cast<uint32_t*>(smem_raw + align16(size_t(n_rows) * 8));
+    PatRec* s_patrec = reinterpret_cast<PatRec*>(reinterpret_cast<unsigned char*>(s_erec) + align16(size_t(a.n_clones) * 4));
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_patrec) + align16(size_t(a.n_patterns) * sizeof(PatRec)));
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64));
+    unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_lut) + 4 * 128 * sizeof(uint16_t);
+
+    for (int i = threadIdx.x; i < n_rows * 4; i += blockDim.x) s_next[i] = a.next16[i];
+    for (int i = threadIdx.x; i < a.n_clones; i += blockDim.x) s_erec[i] = a.erec[i];
+    for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
+    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) s_src[i] = a.tape_src[i];
+    {
+        const int wts[4][7] = { { 1, 3, 4, 0, 4, 3, 1 }, { 0, 3, 5, 4, 5, 3, 0 }, { 0, 4, 3, 3, 3, 4, 0 }, { 2, 0, 0, 1, 0, 0, 2 } };
+        for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) {
+            int n = 0, w = 0;
+            for (int bit = 0; bit < 7; ++bit)
+                if ((i >> bit) & 1) { w += wts[i >> 7][bit]; n += wts[i >> 7][bit] > 0; }
+            s_lut[i] = uint16_t(n | w << 8);
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cap = a.list_cap;
+    WarpSmem& ws = *reinterpret_cast<WarpSmem*>(s_warps + size_t(warp) * warp_bytes(cap, true));
+    uint16_t* lists = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(&ws) + sizeof(WarpSmem));
+    uint16_t* dacc = reinterpret_cast<uint16_t*>(lists + 32 * cap);        // density accumulators, uint16 [2][225] (+ 2 idle-lane slots)
+    float* prob = reinterpret_cast<float*>(lists);                          // 225 floats over the emission lists (dead while the heads run)
+    const uint32_t lt = lanemask_lt();
+    const uint32_t emit_thr = uint32_t(a.n_clones) * 8u;
+    uint32_t next_addr = smem_addr(s_next), src_addr = smem_addr(s_src + lane);
+    uint32_t list_addr = smem_addr(lists + lane * cap);
+    asm volatile("" : "+r"(next_addr), "+r"(src_addr), "+r"(list_addr));
+
+    const int warps = blockDim.x >> 5;
+    for (long long b = (long long)blockIdx.x * warps + warp; b < a.n; b += (long long)gridDim.x * warps) {
+        // ---- the start position, from scratch: phases 0, 2, 3 of ac_eval_kernel (no block score, no compounds) -------
+        uint32_t bw = 0xffffffffu;
+        if (lane < kBoardWords) {
+            bw = __ldg(a.boards + b * kBoardWords + lane);
+            bw &= ~((bw >> 1) & 0x55555555u);
+        }
+        if (lane == 14) bw |= 0xfffffffcu;
+        if (lane == 15) bw = 0xffffffffu;
+        if (lane < kBoardSmem) ws.board[lane] = bw;
+        {
+            int4* z = reinterpret_cast<int4*>(ws.scores);
+            for (int i = lane; i < (kScoreWords + kFlagWords) / 4; i += 32) z[i] = make_int4(0, 0, 0, 0);
+            if (lane < kTotalWords) ws.totals[lane] = 0;
+        }
+        __syncwarp();
+        uint32_t mine = 0;                                                   // lanes 0..14 white rows, 15..29 black rows
+        if (lane < 30) {
+            const int y = lane - 15 * (lane >= 15), off = 30 * y;
+            const uint32_t lo = ws.board[off >> 5], hi = ws.board[(off >> 5) + 1];
+            const uint32_t v = __funnelshift_r(lo, hi, off & 31) & 0x3fffffffu;
+            mine = lane >= 15 ? squeeze_even(v) : squeeze_even(v >> 1);
+        }
+        {   // density accumulators of the start position: policy_heads()' column walk, accumulators only
+            const int dc = lane >= 15, dx = lane - 15 * dc;
+            const bool live = lane < 30;
+            uint16_t* acc_p = dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30));
+            const int step = live ? kWidth : 0, src0 = 15 * dc;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+#pragma unroll 1
+            for (int y = 0; y < kHeight + 3; ++y) {
+                uint32_t row = __shfl_sync(0xffffffffu, mine, src0 + y);
+                row = (y < kHeight && live) ? row : 0u;
+                const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;
+                const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
+                const uint32_t full = w0 + t3;
+                w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
+                if (y >= 3) { *acc_p = uint16_t(full); acc_p += step; }
+            }
+        }
+        uint32_t win = 0;
+        {
+            uint32_t nx = a.start_off, lp = list_addr, src = src_addr;
+            for (int t = 0; t < a.tape_steps; t += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u, src += 64) {
+                    const uint32_t e = lds_u16(src);
+                    const uint32_t w = __shfl_sync(0xffffffffu, bw, e);
+                    const uint32_t v2 = __funnelshift_r(w, w, e >> 8) & 6u;
+                    nx = lds_u16(next_addr + nx + v2);
+                    if (nx < emit_thr) {
+                        sts_u16(lp, nx * 8u + uint32_t(t + u));
+                        lp += 2;
+                    }
+                }
+            }
+            uint32_t incl = (lp - list_addr) >> 1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const int total = int(__shfl_sync(0xffffffffu, incl, 31));
+            const int excl = int(incl) - int((lp - list_addr) >> 1);
+            __syncwarp();
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const int i = i0 + lane;
+                int j = __shfl_sync(0xffffffffu, excl, 16) <= i ? 16 : 0;
+                if (__shfl_sync(0xffffffffu, excl, j + 8) <= i) j += 8;
+                if (__shfl_sync(0xffffffffu, excl, j + 4) <= i) j += 4;
+                if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
+                if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
+                const int first = __shfl_sync(0xffffffffu, excl, j);
+                if (i >= total) continue;
+                const uint32_t ent = lists[j * cap + (i - first)];
+                const uint32_t er = s_erec[ent >> 6];
+                const uint32_t inf = __ldg(a.tape_info + (ent & 63u) * 32u + uint32_t(j));
+                const uint32_t dir = (inf >> 9) & 3u;
+                const int vcell = inf & 0x1ff, stride = int(inf >> 11);
+                win |= apply_emission(ws, nullptr, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir, stride);
+                const uint32_t p1 = er_pid(er, 1);
+                if (p1 != kDevNoPid) win |= apply_emission(ws, nullptr, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir, stride);
+            }
+        }
+        __syncwarp();
+
+        // ---- the game: Heuristic::EvaluatedRollout (Heuristic.hpp:61-72) ------------------------------------------------
+        int played = 0, result = 0;
+        for (;;) {
+            const uint32_t won = __reduce_or_sync(0xffffffffu, win);
+            if (won) { result = (won & 1u) ? 1 : -1; break; }               // a Five emission ended the game, Pattern.cpp:140-145
+            compounds_pass(ws, lists, lane, lt, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
+            int n_stones, to_move;
+            policy_heads_inc(ws, prob, mine, lane, dacc, n_stones, to_move);
+            int cell = -1;
+            if (n_stones < kCells && played < a.g_max_moves) {               // Evaluator::checkGameEnd, Pattern.cpp:343-353
+                uint32_t rnd = 0;
+                if (a.g_mode == 2)
+                    rnd = philox_word(uint32_t(played) >> 2, 0u, uint32_t(a.g_game_base) + uint32_t(b), a.g_ctr_hi, a.g_key_lo,
+                                      a.g_key_hi, uint32_t(played) & 3u);
+                cell = select_move(prob, lane, a.g_mode, rnd);
+            }
+            if (cell < 0) break;
+            __syncwarp();
+            compounds_pass(ws, lists, lane, lt, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, -600);   // the same counts: the same compounds
+            // ---- place the stone ----------------------------------------------------------------------------------------
+            if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
+            const int my = cell / kWidth, mx = cell - my * kWidth;
+            if (lane == (cell >> 4)) { bw |= (to_move ? 1u : 2u) << ((cell & 15) * 2); ws.board[lane] = bw; }
+            if (lane == (to_move ? 15 : 0) + my) mine |= 1u << mx;
+            {
+                const int dc = lane >= 15, dx = lane - 15 * dc, j = mx - dx + 3;
+                if (lane < 30 && dc == to_move && j >= 0 && j < 7) {
+#pragma unroll 1
+                    for (int d = -3; d <= 3; ++d) {
+                        const int y = my + d;
+                        if (y >= 0 && y < kHeight) dacc[dc * kCells + y * kWidth + dx] += s_lut[(d < 0 ? -d : d) * 128 + (1 << j)];
+                    }
+                }
+            }
+            ++played;
+            __syncwarp();
+            // ---- the four lines through the stone: lane & 3 = direction, lanes 0..3 as they are now (+1), 4..7 as they were (-1)
+            int cell0, stride, len;
+            line_through(cell, uint32_t(lane) & 3u, cell0, stride, len);
+            const int steps = (lane < 8 && len >= 5) ? len + a.trail_pad : 0;   // shorter diagonals hold no pattern (they are not on the tape either)
+            uint32_t nx = a.start_off, lp = list_addr;
+            const int most = kWidth + a.trail_pad;
+#pragma unroll 1
+            for (int i = 0; i < most; ++i) {                                  // warp-uniform: every lane shuffles
+                const int c = cell0 + i * stride;
+                const bool on = i < len;
+                const uint32_t w = __shfl_sync(0xffffffffu, bw, on ? (c >> 4) : 15);
+                uint32_t v2 = on ? ((w >> ((c & 15) * 2)) & 3u) * 2u : 6u;
+                if (lane >= 4 && c == cell) v2 = 0u;                         // before the move this cell was empty
+                if (i < steps) {
+                    nx = lds_u16(next_addr + nx + v2);
+                    if (nx < emit_thr) {
+                        sts_u16(lp, nx * 8u + uint32_t(i));
+                        lp += 2;
+                    }
+                }
+            }
+            __syncwarp();
+            win = 0;
+            const int cnt = int((lp - list_addr) >> 1);
+            const int delta = lane < 4 ? 1 : -1;
+            for (int k = 0; k < cnt; ++k) {                                   // a handful of emissions on at most 8 lanes
+                const uint32_t ent = lists[lane * cap + k];
+                const uint32_t er = s_erec[ent >> 6];
+                const int vcell = cell0 + int(ent & 63u) * stride;
+                uint32_t w = apply_emission(ws, nullptr, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, uint32_t(lane) & 3u, stride, delta);
+                const uint32_t p1 = er_pid(er, 1);
+                if (p1 != kDevNoPid) w |= apply_emission(ws, nullptr, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, uint32_t(lane) & 3u, stride, delta);
+                if (delta > 0) win |= w;
+            }
+            __syncwarp();
+        }
+        if (a.g_winner && lane == 0) a.g_winner[b] = (int8_t)result;
+        if (a.g_length && lane == 0) a.g_length[b] = (int16_t)played;
+        if (a.g_final && lane < kBoardWords) a.g_final[b * kBoardWords + lane] = lane == 14 ? (bw & 3u) : lane == 15 ? 0u : bw;
+        __syncwarp();
+    }
 }
 
 template <bool kHeads, bool kGuided>
@@ -842,7 +1192,9 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
         kernel<<<grid, warps * 32, smem, stream>>>(a);
         return cudaGetLastError();
     };
-    if (a.g_mode != 0) return launch(ac_eval_kernel<true, true>);
+    // guided playouts: the incremental kernel, unless the caller asks for the full rescan or a custom table's lines could
+    // overflow a lane's emission list (one line of 15 + trail_pad steps per lane there)
+    if (a.g_mode != 0) return (a.g_full_rescan || kWidth + a.trail_pad > a.list_cap) ? launch(ac_eval_kernel<true, true>) : launch(guided_kernel);
     return wants_heads(a) ? launch(ac_eval_kernel<true, false>) : launch(ac_eval_kernel<false, false>);
 }
 

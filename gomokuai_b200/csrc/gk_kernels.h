@@ -13,7 +13,7 @@ struct EvalArgs {
     const uint16_t* next16; const uint32_t* erec; int n_states, n_clones;   // device copies of the compiled table (gk_format.h)
     const PatRec* patrec; int n_patterns;
     const uint16_t* tape_src; const uint16_t* tape_info; int tape_steps;
-    int root_off, start_off, list_cap;
+    int root_off, start_off, list_cap, trail_pad;
     const uint32_t* boards; long long n;
     int32_t* scores; uint16_t* pat_totals; uint16_t* cmp_totals; int8_t* winner;   // any may be null
     float* probs; float* value;                 // policy heads for the side to move (null = not wanted)
@@ -21,6 +21,7 @@ struct EvalArgs {
     uint32_t* dflags;                           // [n][225] per-cell decisive flag bits (gk_eval.cu), for inspection; may be null
     // guided playouts (g_mode != 0): every warp plays its board to the end inside the kernel
     int g_mode;                                 // 0 off, 1 most probable move, 2 move drawn from the probabilities
+    int g_full_rescan;                          // re-evaluate the whole board after every move (the first implementation; kept to test the incremental kernel against)
     uint32_t g_key_lo, g_key_hi, g_ctr_hi; int g_game_base, g_max_moves;
     int8_t* g_winner; int16_t* g_length; int16_t* g_moves; uint32_t* g_final;   // per game; any may be null
 };

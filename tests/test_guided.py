@@ -132,6 +132,26 @@ def test_gpu_sampled_games_win_rate_vs_reference(gpu, ref):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["max", "sample"])
+def test_gpu_incremental_guided_kernel_plays_the_games_of_the_full_rescan(gpu, mode):
+    """guided_kernel (per move: only the four lines through the new stone, before and after) against
+    ac_eval_kernel<true, true> (whole board after every move): same winners, lengths, moves and final boards, game for
+    game -- from the empty board, from the synthetic mid-game set, from clustered / nearly full / decided positions."""
+    import torch
+    lists = _starts(55, 300) + random_positions(56, 200, lo=60, hi=200)
+    mv, st = pyoracle.pack_moves(lists)
+    boards = np.concatenate([np.zeros((40, 16), np.uint32), gpu.synth_positions(7, 1500, want_moves=False)[0], gpu.pack_moves(mv, st)])
+    for max_moves in (225, 7):
+        inc = gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves)
+        full = gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves, full_rescan=True)
+        torch.cuda.synchronize()
+        for k in ("winner", "length", "moves", "final_boards"):
+            a, b = inc[k].cpu().numpy(), full[k].cpu().numpy()
+            assert np.array_equal(a, b), (mode, max_moves, k, int(np.flatnonzero((a != b).reshape(len(boards), -1).any(axis=1))[0]))
+    assert int(inc["length"].sum()) > 0
+
+
+@pytest.mark.gpu
 def test_gpu_guided_max_moves_and_determinism(gpu):
     boards, _, _ = gpu.synth_positions(0, 64)
     a = gpu.guided_rollout_batch(boards, mode="sample", key=KEY, max_moves=3)
