@@ -73,6 +73,17 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" :: "r"(addr), "r"(v) : "memory");
 }
 
+// ---- bulk asynchronous copy shared -> global (the TMA engine's 1-D form, sm_90+): one elected lane hands a whole 3 600-byte
+// score block to the copy engine and the warp goes on with its next board; the block may not be overwritten before
+// bulk_wait_read(), and is in global memory (visible to every thread) after bulk_wait_all().
+__device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                 :: "l"(dst_global), "r"(src_shared), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cell_value(const uint32_t* board, uint32_t cell) {
     return (board[cell >> 4] >> ((cell & 15u) * 2u)) & 3u;
 }
@@ -862,9 +873,14 @@ ac_eval_kernel(EvalArgs a) {
     // longer fit, all parked candidates run together -- Compound::locate, then their rescans spread over the lanes --
     // reading the boards from global memory and adding to the ALREADY STORED score blocks / totals with global atomics.
     const bool defer = !kHeads && a.scores != nullptr && (reinterpret_cast<uintptr_t>(a.cmp_totals) & 3u) == 0;
+    // The plain evaluator hands its score blocks to the bulk-copy engine (phase 5) and scans the NEXT board while the block
+    // leaves: the scan only touches the board registers and the emission lists, so the accumulators are cleared after it.
+    constexpr bool kBulk = !kHeads;
+    const uint32_t scores_addr = smem_addr(ws.scores);
     uint32_t pend_idx = 0xffffffffu, pend_flags = 0;
     long long pend_board = 0;
     auto flush_pending = [&]() {
+        if (kBulk && lane == 0) bulk_wait_all();                            // the parked boards' score blocks have landed in global memory
         __threadfence();                                                    // the parked boards' stores precede the atomics
         __syncwarp();
         __threadfence();
@@ -904,6 +920,32 @@ ac_eval_kernel(EvalArgs a) {
         if (lane == 15) bw = 0xffffffffu;
         int played = 0, result = 0;                                         // guided mode: moves played so far / final winner
       next_move:                                                            // guided mode re-enters here after every move
+        uint32_t nx = a.start_off;
+        uint32_t lp = list_addr;                                            // shared address of the lane's next free list slot
+        auto scan = [&]() {
+            // ---- phase 2: scan ---------------------------------------------------------------------
+            // per step: tape entry -> board word (shuffle) -> cell value * 2 -> next row offset.  The only
+            // state-dependent chain is  IADD (offset + value * 2), LDS.U16.
+            uint32_t src = src_addr;
+            for (int t = 0; t < a.tape_steps; t += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u, src += 64) {
+                    const uint32_t e = lds_u16(src);
+                    const uint32_t w = __shfl_sync(0xffffffffu, bw, e);     // source lane = e & 31 = board word index
+                    const uint32_t v2 = __funnelshift_r(w, w, e >> 8) & 6u; // cell value * 2
+                    nx = lds_u16(next_addr + nx + v2);
+                    if (nx < emit_thr) {
+                        sts_u16(lp, nx * 8u + uint32_t(t + u));             // clone id << 6 | step
+                        lp += 2;
+                    }
+                }
+            }
+        };
+        if (kBulk) {
+            scan();                                                         // the previous board's block is still leaving
+            if (lane == 0) bulk_wait_read();                                // ... now the copy engine has read it
+            __syncwarp();
+        }
         if (lane < kBoardSmem) ws.board[lane] = bw;
         {
             int4* z = reinterpret_cast<int4*>(ws.scores);
@@ -945,25 +987,7 @@ ac_eval_kernel(EvalArgs a) {
         }
         __syncwarp();
 
-        // ---- phase 2: scan -------------------------------------------------------------------------
-        // per step: tape entry -> board word (shuffle) -> cell value * 2 -> next row offset.  The only
-        // state-dependent chain is  IADD (offset + value * 2), LDS.U16.
-        uint32_t nx = a.start_off;
-        uint32_t lp = list_addr;                                            // shared address of the lane's next free list slot
-        uint32_t src = src_addr;
-        for (int t = 0; t < a.tape_steps; t += 2) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u, src += 64) {
-                const uint32_t e = lds_u16(src);
-                const uint32_t w = __shfl_sync(0xffffffffu, bw, e);         // source lane = e & 31 = board word index
-                const uint32_t v2 = __funnelshift_r(w, w, e >> 8) & 6u;     // cell value * 2
-                nx = lds_u16(next_addr + nx + v2);
-                if (nx < emit_thr) {
-                    sts_u16(lp, nx * 8u + uint32_t(t + u));                 // clone id << 6 | step
-                    lp += 2;
-                }
-            }
-        }
+        if (!kBulk) scan();
         // ---- phase 3: balanced scatter ----------------------------------------------------------------
         uint32_t win = 0;
         {
@@ -1107,9 +1131,15 @@ ac_eval_kernel(EvalArgs a) {
         }
         // ---- phase 5: output --------------------------------------------------------------------------
         if (a.scores) {
-            const int4* s4 = reinterpret_cast<const int4*>(ws.scores);
-            int4* dst = reinterpret_cast<int4*>(a.scores + b * kScoreWords);
-            for (int i = lane; i < kScoreWords / 4; i += 32) dst[i] = s4[i];
+            if (kBulk) {
+                fence_async_shared();                                       // the lanes' shared-memory updates, made visible to the copy engine
+                __syncwarp();
+                if (lane == 0) bulk_store(a.scores + b * kScoreWords, scores_addr, kScoreWords * 4);
+            } else {
+                const int4* s4 = reinterpret_cast<const int4*>(ws.scores);
+                int4* dst = reinterpret_cast<int4*>(a.scores + b * kScoreWords);
+                for (int i = lane; i < kScoreWords / 4; i += 32) dst[i] = s4[i];
+            }
         }
         if (a.pat_totals && lane < 16) a.pat_totals[b * 16 + lane] = (uint16_t)ws.totals[lane];
         if (a.cmp_totals && lane < 6) a.cmp_totals[b * 6 + lane] = (uint16_t)ws.totals[16 + lane];
@@ -1118,6 +1148,7 @@ ac_eval_kernel(EvalArgs a) {
         __syncwarp();
     }
     if (defer && __ballot_sync(0xffffffffu, pend_idx != 0xffffffffu)) flush_pending();
+    if (kBulk && lane == 0) bulk_wait_read();                               // shared memory must outlive the copies that read it
 }
 
 // PatternSearch::matches for arbitrary symbol strings, one thread per string (test / tooling path).
