@@ -201,6 +201,40 @@ def test_decisive_filter_restatement_properties(port):
     assert fired > 30
 
 
+def test_reference_compound_flags_depend_on_the_move_order(ref):
+    """Why the compound-flag bits of a from-scratch evaluation can only be compared one way (see the GPU test below): the
+    REFERENCE's own per-cell compound flags are not a function of the position.  Replaying the same stones in another
+    order (black stones permuted among the black moves, white among the white) leaves m_scores and every pattern-flag
+    presence bit unchanged, but changes compound-flag bits -- Record::set's 2-bit saturating counters (Pattern.cpp:395-400)
+    forget contributions that are removed after a third was added, and which ones depends on the history."""
+    rng = np.random.default_rng(0)
+
+    def state(m):
+        r = ref.eval_moves(m)
+        if r["bad"] or r["winner"] != 0:
+            return None
+        pf, cf, _ = ref.eval_flags()
+        return r["scores"].copy(), np.array([_dflag_bits(pf[c], cf[c]) for c in range(225)], np.uint32)
+
+    tried = differ = 0
+    for m in _positions(41, 260):
+        a = state(m) if len(m) >= 6 else None
+        if a is None:
+            continue
+        for _ in range(3):
+            mm = [0] * len(m)
+            mm[0::2] = [int(c) for c in rng.permutation(m[0::2])]
+            mm[1::2] = [int(c) for c in rng.permutation(m[1::2])]
+            b = state(mm)                                    # a permuted order can complete a five early: skipped
+            if b is None:
+                continue
+            tried += 1
+            assert np.array_equal(a[0], b[0])                # scores: order-independent (SURVEY Appendix B)
+            assert np.array_equal(a[1] & 0xffff, b[1] & 0xffff)   # pattern-flag presence bits: order-independent
+            differ += not np.array_equal(a[1] >> 16, b[1] >> 16)
+    assert tried > 400 and differ >= 3, (tried, differ)     # compound-flag bits: the reference disagrees with itself
+
+
 def test_hybrid_simulate_port_equals_reference(port, ref):
     for m in _positions(14, 80):
         if port.eval_moves(m)["winner"] != 0:
