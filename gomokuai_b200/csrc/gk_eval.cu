@@ -481,10 +481,11 @@ __device__ GK_HEADS_INLINE int select_move(const float* prob, int lane, int mode
 // game's START position from scratch (all 72 lines, as ac_eval_kernel) and afterwards, per move, rescans only those four
 // lines twice -- as they were (emissions taken back, Updater::updatePatterns with delta = -1) and as they are (+1) --
 // which is the reference's own incremental scheme (Updater::updateMove, Pattern.cpp:274-302) at line granularity.
-// Between moves the warp's shared block keeps the PATTERN state only: scores, per-cell compound-class counts, totals.
-// The two derived parts are added per evaluation: compounds (a function of the counts: +600s applied before the heads
-// read the maps and taken back after the move is chosen) and the block score (+160 where a player's density weight is
-// positive, folded into the heads from the density accumulators the guided variant keeps anyway).
+// Compounds follow the same scheme: they are a function of a cell's counts and of its own four 13-symbol windows, so a move
+// can only change the compounds of the cells within 6 steps of it on its four lines; those are taken back before the
+// lines change and added again afterwards (Updater::updateCompound, Pattern.cpp:169-197, does the same).
+// The block score (+160 where a player's density weight is positive) is not stored: the heads add it as they read the
+// maps, from the density accumulators the guided variant keeps anyway.
 // Every float the heads compute is produced by the same operations in the same order as ac_eval_kernel<true, true>,
 // so both variants play IDENTICAL games (tests/test_guided.py).
 
@@ -500,32 +501,66 @@ __device__ __forceinline__ void line_through(int m, uint32_t dir, int& cell0, in
     }
 }
 
-// Compounds of the current counts, added (amount = +600) or taken back (-600): the flag scan, Compound::Test, locate and
-// the updateAntis rescans of ac_eval_kernel's phase 4, in place.  `clist`: scratch for up to 450 candidates.
-__device__ __forceinline__ void compounds_pass(WarpSmem& ws, unsigned short* clist, int lane, uint32_t lt, uint32_t next_addr,
-                                               uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
-                                               int amount) {
+// Compound::Test (Pattern.cpp:424-433) on the two count words of a cell: per direction the classes' counts are OR-ed and
+// a binary 10 is widened to 11 before the "at least two bits" test; bit 0 = white passes, bit 1 = black passes
+__device__ __forceinline__ uint32_t compound_test(uint2 f) {
+    const bool maybe = (((f.x & (f.x - 1)) | (f.y & (f.y - 1))) | ((f.x | f.y) & 0xaaaaaau)) != 0;   // two fields set, or a count of 2
+    if (!maybe) return 0u;
+    uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu, bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
+    bw0 |= (bw0 >> 1) & 0x55u;
+    bw1 |= (bw1 >> 1) & 0x55u;
+    return ((bw0 & (bw0 - 1)) != 0 ? 1u : 0u) | ((bw1 & (bw1 - 1)) != 0 ? 2u : 0u);
+}
+
+// every (cell, player) of the board that passes Compound::Test -> clist (cell * 2 + player), returns their number
+__device__ __forceinline__ int compound_candidates_all(const WarpSmem& ws, unsigned short* clist, int lane, uint32_t lt) {
     int cn = 0;
     const uint2* f2 = reinterpret_cast<const uint2*>(ws.flags);
 #pragma unroll 2
     for (int r = 0; r < (kCells + 31) / 32; ++r) {
         const int cell = r * 32 + lane;
-        const uint2 f = f2[cell < kCells ? cell : kCells];
-        const bool maybe = (((f.x & (f.x - 1)) | (f.y & (f.y - 1))) | ((f.x | f.y) & 0xaaaaaau)) != 0;
-        const uint32_t m = __ballot_sync(0xffffffffu, maybe);
-        if (m) {
-            uint32_t bw0 = (f.x | (f.x >> 8) | (f.x >> 16)) & 0xffu, bw1 = (f.y | (f.y >> 8) | (f.y >> 16)) & 0xffu;
-            bw0 |= (bw0 >> 1) & 0x55u;
-            bw1 |= (bw1 >> 1) & 0x55u;
-            const bool h0 = (bw0 & (bw0 - 1)) != 0, h1 = (bw1 & (bw1 - 1)) != 0;
-            const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-            if (h0) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
-            cn += __popc(m0);
-            if (h1) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
-            cn += __popc(m1);
-        }
+        const uint32_t pass = compound_test(f2[cell < kCells ? cell : kCells]);      // flags[450..451] stay zero
+        const uint32_t m0 = __ballot_sync(0xffffffffu, pass & 1u), m1 = __ballot_sync(0xffffffffu, pass & 2u);
+        if (pass & 1u) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
+        cn += __popc(m0);
+        if (pass & 2u) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
+        cn += __popc(m1);
     }
     __syncwarp();
+    return cn;
+}
+
+// The same over the cells whose compounds a move at m can change: the (up to 12) neighbours of m within 6 steps on each
+// of its four lines -- a compound's counts and its updateAntis windows only see its own four 13-symbol windows
+// (Updater::updateCompound walks exactly these cells, Pattern.cpp:169-197) -- and, with_centre, m itself.
+__device__ __forceinline__ int compound_candidates_window(const WarpSmem& ws, unsigned short* clist, int m, bool with_centre,
+                                                          int lane, uint32_t lt) {
+    const int my = m / kWidth, mx = m - my * kWidth;
+    const uint2* f2 = reinterpret_cast<const uint2*>(ws.flags);
+    int cn = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int slot = r * 32 + lane;                            // slot = direction * 13 + (k + 6), 52 slots
+        const int dir = slot / 13, k = slot - dir * 13 - 6;
+        const int x = mx + k * (dir == 1 ? 0 : dir == 3 ? -1 : 1), y = my + k * (dir == 0 ? 0 : 1);
+        const bool on = slot < 52 && (k != 0 || (with_centre && dir == 0)) && x >= 0 && x < kWidth && y >= 0 && y < kHeight;
+        const int cell = y * kWidth + x;
+        const uint32_t pass = compound_test(f2[on ? cell : kCells]);
+        const uint32_t m0 = __ballot_sync(0xffffffffu, pass & 1u), m1 = __ballot_sync(0xffffffffu, pass & 2u);
+        if (pass & 1u) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
+        cn += __popc(m0);
+        if (pass & 2u) clist[cn + __popc(m1 & lt)] = (unsigned short)(cell * 2 + 1);
+        cn += __popc(m1);
+    }
+    __syncwarp();
+    return cn;
+}
+
+// Compound::locate / update / updateAntis for the candidates in clist, added (amount = +600) or taken back (-600):
+// ac_eval_kernel's phase 4, in place.
+__device__ __forceinline__ void compounds_apply(WarpSmem& ws, const unsigned short* clist, int cn, int lane, uint32_t next_addr,
+                                                uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
+                                                int amount) {
     for (int base = 0; base < cn; base += 32) {
         uint32_t t0 = 0, t1 = 0;
         if (base + lane < cn) {
@@ -553,8 +588,11 @@ __device__ __forceinline__ void compounds_pass(WarpSmem& ws, unsigned short* cli
 // values are recomputed from them where policy_heads() parks them in ws.flags (the counts must survive here), and the
 // block score the maps do not hold is added as the maps are read: +160 on S(P, P) where P's weight is positive
 // (Pattern.cpp:244,268).  Same float operations in the same order as policy_heads().
+// s_vlut[N * 101 + W] = (3 W) / (1 + 2 N) for every possible accumulator (N <= 24 weighted cells, W <= 100 = the sum of
+// Evaluator::BlockWeights): the IEEE quotients, computed once per CTA, instead of four divisions per cell and move.
+constexpr int kVlutW = 101, kVlutN = 25;
 __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint32_t mine, int lane, const uint16_t* dacc,
-                                                 int& n_stones, int& to_move) {
+                                                 const float* s_vlut, int& n_stones, int& to_move) {
     const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
     const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
     const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
@@ -571,7 +609,7 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
         const uint32_t full = live ? uint32_t(*acc_p) : 0u;
         acc_p += step;
         const uint32_t orow = __shfl_sync(0xffffffffu, occ, y);
-        float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
+        float v = s_vlut[(full & 0xffu) * kVlutW + (full >> 8)];
         v = (orow & xbit) ? 0.f : v;
         n2 += v * v;
     }
@@ -590,7 +628,7 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     for (int c = lane; c < kCells; c += 32) {
         const bool empty = cell_value(ws.board, c) == 0u;
         const uint32_t fw = dacc[c], fb = dacc[kCells + c];
-        float vw = (3.f * float(fw >> 8)) / (1.f + 2.f * float(fw & 0xffu)), vb = (3.f * float(fb >> 8)) / (1.f + 2.f * float(fb & 0xffu));
+        float vw = s_vlut[(fw & 0xffu) * kVlutW + (fw >> 8)], vb = s_vlut[(fb & 0xffu) * kVlutW + (fb >> 8)];
         vw = empty ? vw : 0.f;
         vb = empty ? vb : 0.f;
         const float w0 = vw / nrm_w, w1 = vb / nrm_b;
@@ -629,8 +667,11 @@ guided_kernel(EvalArgs a) {
     PatRec* s_patrec = reinterpret_cast<PatRec*>(reinterpret_cast<unsigned char*>(s_erec) + align16(size_t(a.n_clones) * 4));
     uint16_t* s_src = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_patrec) + align16(size_t(a.n_patterns) * sizeof(PatRec)));
     uint16_t* s_lut = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64));
-    unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_lut) + 4 * 128 * sizeof(uint16_t);
+    float* s_vlut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_lut) + 4 * 128 * sizeof(uint16_t));
+    unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_vlut) + align16(size_t(kVlutN) * kVlutW * sizeof(float));
 
+    for (int i = threadIdx.x; i < kVlutN * kVlutW; i += blockDim.x)
+        s_vlut[i] = (3.f * float(i % kVlutW)) / (1.f + 2.f * float(i / kVlutW));     // the expression of policy_heads(), Heuristic.hpp:39-45
     for (int i = threadIdx.x; i < n_rows * 4; i += blockDim.x) s_next[i] = a.next16[i];
     for (int i = threadIdx.x; i < a.n_clones; i += blockDim.x) s_erec[i] = a.erec[i];
     for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
@@ -744,15 +785,18 @@ guided_kernel(EvalArgs a) {
             }
         }
         __syncwarp();
+        {   // the start position's compounds, from all its counts
+            const int cn = compound_candidates_all(ws, lists, lane, lt);
+            compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
+        }
 
         // ---- the game: Heuristic::EvaluatedRollout (Heuristic.hpp:61-72) ------------------------------------------------
         int played = 0, result = 0;
         for (;;) {
             const uint32_t won = __reduce_or_sync(0xffffffffu, win);
             if (won) { result = (won & 1u) ? 1 : -1; break; }               // a Five emission ended the game, Pattern.cpp:140-145
-            compounds_pass(ws, lists, lane, lt, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
             int n_stones, to_move;
-            policy_heads_inc(ws, prob, mine, lane, dacc, n_stones, to_move);
+            policy_heads_inc(ws, prob, mine, lane, dacc, s_vlut, n_stones, to_move);
             int cell = -1;
             if (n_stones < kCells && played < a.g_max_moves) {               // Evaluator::checkGameEnd, Pattern.cpp:343-353
                 uint32_t rnd = 0;
@@ -763,7 +807,10 @@ guided_kernel(EvalArgs a) {
             }
             if (cell < 0) break;
             __syncwarp();
-            compounds_pass(ws, lists, lane, lt, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, -600);   // the same counts: the same compounds
+            {   // the compounds this move can change are taken back while the lines still are as they were
+                const int cn = compound_candidates_window(ws, lists, cell, true, lane, lt);
+                compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, -600);
+            }
             // ---- place the stone ----------------------------------------------------------------------------------------
             if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
             const int my = cell / kWidth, mx = cell - my * kWidth;
@@ -802,20 +849,39 @@ guided_kernel(EvalArgs a) {
                     }
                 }
             }
-            __syncwarp();
             win = 0;
-            const int cnt = int((lp - list_addr) >> 1);
-            const int delta = lane < 4 ? 1 : -1;
-            for (int k = 0; k < cnt; ++k) {                                   // a handful of emissions on at most 8 lanes
-                const uint32_t ent = lists[lane * cap + k];
-                const uint32_t er = s_erec[ent >> 6];
-                const int vcell = cell0 + int(ent & 63u) * stride;
-                uint32_t w = apply_emission(ws, nullptr, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, uint32_t(lane) & 3u, stride, delta);
-                const uint32_t p1 = er_pid(er, 1);
-                if (p1 != kDevNoPid) w |= apply_emission(ws, nullptr, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, uint32_t(lane) & 3u, stride, delta);
-                if (delta > 0) win |= w;
+            {   // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names line and sign)
+                uint32_t incl = (lp - list_addr) >> 1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const int total = int(__shfl_sync(0xffffffffu, incl, 31));
+                const int excl = int(incl) - int((lp - list_addr) >> 1);
+                __syncwarp();
+                for (int i0 = 0; i0 < total; i0 += 32) {
+                    const int i = i0 + lane;
+                    int j = __shfl_sync(0xffffffffu, excl, 4) <= i ? 4 : 0;   // only lanes 0..7 hold entries
+                    if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
+                    if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
+                    const int first = __shfl_sync(0xffffffffu, excl, j);
+                    const int jc0 = __shfl_sync(0xffffffffu, cell0, j), jstride = __shfl_sync(0xffffffffu, stride, j);
+                    if (i >= total) continue;
+                    const uint32_t ent = lists[j * cap + (i - first)];
+                    const uint32_t er = s_erec[ent >> 6];
+                    const int vcell = jc0 + int(ent & 63u) * jstride, delta = j < 4 ? 1 : -1;
+                    uint32_t w = apply_emission(ws, nullptr, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * jstride, uint32_t(j) & 3u, jstride, delta);
+                    const uint32_t p1 = er_pid(er, 1);
+                    if (p1 != kDevNoPid) w |= apply_emission(ws, nullptr, s_patrec[p1], vcell - int(er_prev(er, 1)) * jstride, uint32_t(j) & 3u, jstride, delta);
+                    if (delta > 0) win |= w;
+                }
             }
             __syncwarp();
+            {   // ... and added again from the new counts and the new board
+                const int cn = compound_candidates_window(ws, lists, cell, false, lane, lt);
+                compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
+            }
         }
         if (a.g_winner && lane == 0) a.g_winner[b] = (int8_t)result;
         if (a.g_length && lane == 0) a.g_length[b] = (int16_t)played;
@@ -1190,8 +1256,14 @@ static bool wants_heads(const EvalArgs& a) {
     return a.probs != nullptr || a.value != nullptr || a.g_mode != 0 || a.dflags != nullptr;
 }
 
+// shared tables beside the automaton: the density LUT of the head variants, the quotient LUT of the incremental guided kernel
+static bool incremental_guided(const EvalArgs& a) { return a.g_mode != 0 && !a.g_full_rescan && kWidth + a.trail_pad <= a.list_cap; }
+static size_t extra_table_bytes(const EvalArgs& a) {
+    return (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) + (incremental_guided(a) ? align16(size_t(kVlutN) * kVlutW * sizeof(float)) : 0);
+}
+
 static int eval_warps(const EvalArgs& a) {
-    const size_t tables = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0),
+    const size_t tables = table_smem_bytes(a) + extra_table_bytes(a),
                  per_warp = warp_bytes(a.list_cap, wants_heads(a));
     if (tables + per_warp > kSmemLimit) return 0;
     const size_t fit = (kSmemLimit - tables) / per_warp;
@@ -1199,8 +1271,7 @@ static int eval_warps(const EvalArgs& a) {
 }
 
 size_t eval_smem_bytes(const EvalArgs& a) {
-    return table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) +
-           size_t(eval_warps(a)) * warp_bytes(a.list_cap, wants_heads(a));
+    return table_smem_bytes(a) + extra_table_bytes(a) + size_t(eval_warps(a)) * warp_bytes(a.list_cap, wants_heads(a));
 }
 
 cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
@@ -1213,8 +1284,7 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     // 0.88 ms, 256: 0.93 -> 0.80 ms; no difference from 4 096 games up).
     const long long per_sm = (a.n + sm_count - 1) / sm_count;
     if (a.n >= sm_count && per_sm < warps) warps = (int)(per_sm > 4 ? per_sm : (warps < 4 ? warps : 4));   // (a handful of boards: one full CTA loads the tables fastest)
-    const size_t smem = table_smem_bytes(a) + (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) +
-                        size_t(warps) * warp_bytes(a.list_cap, wants_heads(a));
+    const size_t smem = table_smem_bytes(a) + extra_table_bytes(a) + size_t(warps) * warp_bytes(a.list_cap, wants_heads(a));
     const long long want = (a.n + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? want : sm_count);               // persistent: one CTA per SM
     auto launch = [&](auto kernel) -> cudaError_t {
@@ -1225,7 +1295,7 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     };
     // guided playouts: the incremental kernel, unless the caller asks for the full rescan or a custom table's lines could
     // overflow a lane's emission list (one line of 15 + trail_pad steps per lane there)
-    if (a.g_mode != 0) return (a.g_full_rescan || kWidth + a.trail_pad > a.list_cap) ? launch(ac_eval_kernel<true, true>) : launch(guided_kernel);
+    if (a.g_mode != 0) return incremental_guided(a) ? launch(guided_kernel) : launch(ac_eval_kernel<true, true>);
     return wants_heads(a) ? launch(ac_eval_kernel<true, false>) : launch(ac_eval_kernel<false, false>);
 }
 

@@ -380,7 +380,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
             for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < n_trees;) {
                 Tree& t = m->trees[i];
                 t.clear(reserve);
-                t.add(-1, -1, 1.0f, static_cast<int>(root_last));
+                t.add(-1, root.m_moveRecord.empty() ? -1 : static_cast<int>(root.m_moveRecord.back()), 1.0f, static_cast<int>(root_last));   // MCTS.h:138-151
                 t.board = root;
                 t.black_wins.fill(0);
                 t.white_wins.fill(0);

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(_HERE, "libgomoku_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libgomoku_ref.so")
 REFERENCE_ROOT = "/root/reference/core/lib"
-PYREF_DIR = os.path.join(_HERE, "_ref", "pyref")     # the reference's agents/ + config.py as sourceless byte code (make pyref)
+PYREF_ZIP = os.path.join(_HERE, "_ref", "pyref.zip")     # the reference's agents/ + config.py as sourceless byte code (make pyref)
 
 
 def build(want_ref=True):

@@ -1,0 +1,31 @@
+"""Pattern-guided playouts (configs[4]): games/s of the incremental kernel and of the full-rescan variant at several batch
+sizes, kernel alone (CUDA events, best of 5 after 2 warm-ups).    python scripts/bench_guided.py [1024 8192 ...]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gomokuai_b200 as gk
+
+gk.init(0)
+sizes = [int(x) for x in sys.argv[1:]] or [256, 1024, 8192, 65536]
+rows = []
+for n in sizes:
+    boards = torch.zeros((n, 16), dtype=torch.int32, device="cuda")
+    row = {"games": n}
+    for name, full in (("incremental", False), ("full_rescan", True)):
+        for mode in ("sample", "max"):
+            best = None
+            for it in range(7):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                r = gk.guided_rollout_batch(boards, mode=mode, key=gk.SYNTH_KEY, game_base=0, want_moves=True, full_rescan=full)
+                b.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
+            moves = float(r["length"].float().sum().item())
+            row[f"{name}_{mode}"] = {"ms": best, "games_per_s": n / (best * 1e-3), "moves_per_s": moves / (best * 1e-3), "mean_length": moves / n}
+    row["speedup_sample"] = row["full_rescan_sample"]["ms"] / row["incremental_sample"]["ms"]
+    row["speedup_max"] = row["full_rescan_max"]["ms"] / row["incremental_max"]["ms"]
+    rows.append(row)
+    print(json.dumps(row), file=sys.stderr)
+print(json.dumps({"metric": "guided playouts: incremental kernel vs full rescan, kernel alone", "rows": rows}))

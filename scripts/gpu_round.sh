@@ -15,6 +15,8 @@ for w in $what; do
     bench)   python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err; r=$?; head -c 600 $out/bench_$tag.json; echo; [ $r -ne 0 ] && { tail -5 $out/bench_$tag.err; rc=$r; } ;;
     refarm)  python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err || rc=$? ;;
     profile) bash scripts/profile_round.sh $tag || rc=$? ;;
+    guided)  python scripts/bench_guided.py 256 1024 8192 65536 > $out/guided_$tag.json 2> $out/guided_$tag.err; r=$?; cat $out/guided_$tag.err | cut -c1-400; [ $r -ne 0 ] && rc=$r ;;
+    sweep)   python scripts/sweep_root_parallel.py > $out/rp_sweep_$tag.json 2> $out/rp_sweep_$tag.err; r=$?; tail -6 $out/rp_sweep_$tag.err | cut -c1-300; [ $r -ne 0 ] && rc=$r ;;
     *)       echo "unknown step $w" ;;
   esac
 done

@@ -75,8 +75,10 @@ def test_root_parallel_search_finds_the_winning_move(core):
     b = core.Board()
     for c in (112, 0, 113, 1, 114, 2, 115, 30):        # black completes five at 111 or 116
         b.apply_move(c)
-    # every tree needs > 217 playouts before each root move has been tried once (uniform priors, ties -> lowest cell)
-    move, stats, _ = rp.search(b, playouts_total=32 * 1500, trees_per_rank=32, c_puct=1.0)
+    # With uniform priors and no noise the reference's own search (fresh root: Default::AddNoise draws nothing) keeps
+    # exploiting the first cells it tried -- black wins most random playouts from here, so a visited child scores far
+    # above every unvisited one and the search never reaches cell 111.  The root-noise extension spreads the trees.
+    move, stats, _ = rp.search(b, playouts_total=32 * 1500, trees_per_rank=32, c_puct=1.0, noise=True)
     assert move in (111, 116)
     # white to move must block: after black's four is open on both sides every move loses, so just check legality
     b.apply_move(30 + 15)

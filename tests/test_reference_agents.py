@@ -2,9 +2,9 @@
 -- agents/mcts.py (MCTSAgent, RandomMCTSAgent, RAVEAgent, TraditionalAgent), agents/utils.py (dual_play, eval_agents),
 agents/agent.py -- runs UNMODIFIED with `core` -> `gomokuai_b200.core`.
 
-Where it comes from: /root/reference when it is there (the build container), else oracle/_ref/pyref -- the same files
-compiled to sourceless byte code by `make -C oracle pyref` (a built artefact that travels to the GPU box like
-oracle/_ref/libgomoku_ref.so; the sources are never copied).  No stand-in is written here: without either, the tests
+Where it comes from: /root/reference when it is there (the build container), else oracle/_ref/pyref.zip -- the same
+files compiled to sourceless byte code by `make -C oracle pyref` (a built artefact that travels to the GPU box like
+oracle/_ref/libgomoku_ref.so; the sources are never copied).  GK_PYREF_ONLY=1 forces the byte-code build.  No stand-in is written here: without either, the tests
 skip.  The CPU tests fill the Policy slots from Python (how agents/alphazero.py plugs a network in, core/py_ext/src/
 mcts_ext.hpp:43-61), the GPU tests use RandomPolicy / PoolRAVEPolicy / TraditionalPolicy, whose simulate slots run on
 the B200."""
@@ -18,7 +18,7 @@ import pytest
 from search_util import injected_eval_state
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CANDIDATES = ["/root/reference", os.path.join(ROOT, "oracle", "_ref", "pyref")]
+CANDIDATES = ([] if os.environ.get("GK_PYREF_ONLY") else ["/root/reference"]) + [os.path.join(ROOT, "oracle", "_ref", "pyref.zip")]
 
 
 @pytest.fixture(scope="module")
@@ -26,9 +26,9 @@ def ref_agents(gk):
     from gomokuai_b200 import build
     build.build_pyext()
     from gomokuai_b200 import core
-    base = next((p for p in CANDIDATES if os.path.isdir(os.path.join(p, "agents"))), None)
+    base = next((p for p in CANDIDATES if os.path.isdir(os.path.join(p, "agents")) or os.path.isfile(p)), None)
     if base is None:
-        pytest.skip("neither /root/reference nor oracle/_ref/pyref is present")
+        pytest.skip("neither /root/reference nor oracle/_ref/pyref.zip is present")
     saved = {k: sys.modules.get(k) for k in ("core", "agents", "config")}
     for k in list(sys.modules):
         if k == "agents" or k.startswith("agents."):
