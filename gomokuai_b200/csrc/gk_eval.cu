@@ -84,6 +84,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// x / d for d > 0, IEEE-rounded like the reference's float division.  A zero numerator (most cells: no stone nearby, or
+// occupied) skips the division: 0 / d is +0 anyway, and the correctly rounded division's special-case path -- which a
+// zero operand takes -- costs ~40 instructions for the whole warp every time ANY lane needs it.
+__device__ __forceinline__ float div_pos(float x, float d) { return x != 0.f ? x / d : 0.f; }
+
 __device__ __forceinline__ uint32_t cell_value(const uint32_t* board, uint32_t cell) {
     return (board[cell >> 4] >> ((cell & 15u) * 2u)) & 3u;
 }
@@ -304,7 +309,7 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
             const uint32_t full = live ? uint32_t(*acc_p) : 0u;
             acc_p += dst_step;
             const uint32_t orow = __shfl_sync(0xffffffffu, occ, y);
-            float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
+            float v = div_pos(3.f * float(full >> 8), 1.f + 2.f * float(full & 0xffu));
             v = (orow & xbit) ? 0.f : v;
             *dst = v;
             dst += dst_step;
@@ -321,7 +326,7 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
             w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
             if (y >= 3) {                                               // warp-uniform
                 const uint32_t orow = __shfl_sync(0xffffffffu, occ, y - 3);
-                float v = (3.f * float(full >> 8)) / (1.f + 2.f * float(full & 0xffu));
+                float v = div_pos(3.f * float(full >> 8), 1.f + 2.f * float(full & 0xffu));
                 v = (orow & xbit) ? 0.f : v;                            // occupied cells are filtered to 0 (DensityWeight's max(x, 0))
                 *dst = v;
                 dst += dst_step;
@@ -344,7 +349,7 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
     __syncwarp();
 #pragma unroll 1
     for (int c = lane; c < kCells; c += 32) {
-        const float w0 = dwv[c] / nrm_w, w1 = dwv[kCells + c] / nrm_b;    // normalized DW(white), DW(black)
+        const float w0 = div_pos(dwv[c], nrm_w), w1 = div_pos(dwv[kCells + c], nrm_b);    // normalized DW(white), DW(black)
         const float wp = p ? w1 : w0, wr = p ? w0 : w1;
         const float self_worthy = float(s_self[c]) * wp, rival_anti = float(s_anti[c]) * wr;
         const float av = 0.6f * self_worthy + 0.4f * rival_anti;
@@ -365,7 +370,7 @@ __device__ GK_HEADS_INLINE void policy_heads(WarpSmem& ws, float* prob, const ui
     to_move = p;
 #pragma unroll 1
     for (int c = lane; c < kCells; c += 32)
-        prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : prob[c] / an;
+        prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : div_pos(prob[c], an);
     if (value_out && lane == 0) *value_out = float(tanh((1.2 * double(sdot) - double(rdot)) / 500.0));
     __syncwarp();
 }
@@ -407,7 +412,7 @@ __device__ GK_HEADS_INLINE void decisive_filter(const WarpSmem& ws, const uint32
     if (n2 > 0.f) {
         const float nrm = sqrtf(n2);
 #pragma unroll 1
-        for (int c = lane; c < kCells; c += 32) prob[c] = prob[c] / nrm;
+        for (int c = lane; c < kCells; c += 32) prob[c] = div_pos(prob[c], nrm);
     }
     __syncwarp();
 }
@@ -558,7 +563,7 @@ __device__ __forceinline__ int compound_candidates_window(const WarpSmem& ws, un
 
 // Compound::locate / update / updateAntis for the candidates in clist, added (amount = +600) or taken back (-600):
 // ac_eval_kernel's phase 4, in place.
-__device__ __forceinline__ void compounds_apply(WarpSmem& ws, const unsigned short* clist, int cn, int lane, uint32_t next_addr,
+__device__ __noinline__ void compounds_apply(WarpSmem& ws, const unsigned short* clist, int cn, int lane, uint32_t next_addr,
                                                 uint32_t root_off, uint32_t emit_thr, const uint32_t* s_erec, const PatRec* s_patrec,
                                                 int amount) {
     for (int base = 0; base < cn; base += 32) {
@@ -591,7 +596,8 @@ __device__ __forceinline__ void compounds_apply(WarpSmem& ws, const unsigned sho
 // s_vlut[N * 101 + W] = (3 W) / (1 + 2 N) for every possible accumulator (N <= 24 weighted cells, W <= 100 = the sum of
 // Evaluator::BlockWeights): the IEEE quotients, computed once per CTA, instead of four divisions per cell and move.
 constexpr int kVlutW = 101, kVlutN = 25;
-__device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint32_t mine, int lane, const uint16_t* dacc,
+// occ8: bit k = cell lane + 32 k is occupied (kept by the kernel as stones are placed).
+__device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint32_t mine, uint32_t occ8, int lane, const uint16_t* dacc,
                                                  const float* s_vlut, int& n_stones, int& to_move) {
     const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
     const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
@@ -625,13 +631,13 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     const int* s_rival = ws.scores + 3 * (1 - p) * kCells;
     float a2 = 0.f, sdot = 0.f, rdot = 0.f;
 #pragma unroll 1
-    for (int c = lane; c < kCells; c += 32) {
-        const bool empty = cell_value(ws.board, c) == 0u;
+    for (int c = lane; c < kCells; c += 32, occ8 >>= 1) {
+        const bool empty = (occ8 & 1u) == 0u;
         const uint32_t fw = dacc[c], fb = dacc[kCells + c];
         float vw = s_vlut[(fw & 0xffu) * kVlutW + (fw >> 8)], vb = s_vlut[(fb & 0xffu) * kVlutW + (fb >> 8)];
         vw = empty ? vw : 0.f;
         vb = empty ? vb : 0.f;
-        const float w0 = vw / nrm_w, w1 = vb / nrm_b;
+        const float w0 = div_pos(vw, nrm_w), w1 = div_pos(vb, nrm_b);
         const float wp = p ? w1 : w0, wr = p ? w0 : w1;
         const float vp = p ? vb : vw, vr = p ? vw : vb;                     // un-normalised weights: > 0 <=> the block score applies
         const int self_i = s_self[c] + (vp > 0.f ? 160 : 0), rival_i = s_rival[c] + (vr > 0.f ? 160 : 0);
@@ -654,7 +660,7 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     to_move = p;
 #pragma unroll 1
     for (int c = lane; c < kCells; c += 32)
-        prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : prob[c] / an;
+        prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : div_pos(prob[c], an);
     __syncwarp();
 }
 
@@ -723,6 +729,10 @@ guided_kernel(EvalArgs a) {
             const uint32_t v = __funnelshift_r(lo, hi, off & 31) & 0x3fffffffu;
             mine = lane >= 15 ? squeeze_even(v) : squeeze_even(v >> 1);
         }
+        uint32_t occ8 = 0;                                                   // bit k: cell lane + 32 k holds a stone
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (lane + 32 * k < kCells && cell_value(ws.board, lane + 32 * k) != 0u) occ8 |= 1u << k;
         {   // density accumulators of the start position: policy_heads()' column walk, accumulators only
             const int dc = lane >= 15, dx = lane - 15 * dc;
             const bool live = lane < 30;
@@ -796,7 +806,7 @@ guided_kernel(EvalArgs a) {
             const uint32_t won = __reduce_or_sync(0xffffffffu, win);
             if (won) { result = (won & 1u) ? 1 : -1; break; }               // a Five emission ended the game, Pattern.cpp:140-145
             int n_stones, to_move;
-            policy_heads_inc(ws, prob, mine, lane, dacc, s_vlut, n_stones, to_move);
+            policy_heads_inc(ws, prob, mine, occ8, lane, dacc, s_vlut, n_stones, to_move);
             int cell = -1;
             if (n_stones < kCells && played < a.g_max_moves) {               // Evaluator::checkGameEnd, Pattern.cpp:343-353
                 uint32_t rnd = 0;
@@ -816,6 +826,7 @@ guided_kernel(EvalArgs a) {
             const int my = cell / kWidth, mx = cell - my * kWidth;
             if (lane == (cell >> 4)) { bw |= (to_move ? 1u : 2u) << ((cell & 15) * 2); ws.board[lane] = bw; }
             if (lane == (to_move ? 15 : 0) + my) mine |= 1u << mx;
+            if (lane == (cell & 31)) occ8 |= 1u << (cell >> 5);
             {
                 const int dc = lane >= 15, dx = lane - 15 * dc, j = mx - dx + 3;
                 if (lane < 30 && dc == to_move && j >= 0 && j < 7) {
@@ -833,22 +844,18 @@ guided_kernel(EvalArgs a) {
             line_through(cell, uint32_t(lane) & 3u, cell0, stride, len);
             const int steps = (lane < 8 && len >= 5) ? len + a.trail_pad : 0;   // shorter diagonals hold no pattern (they are not on the tape either)
             uint32_t nx = a.start_off, lp = list_addr;
-            const int most = kWidth + a.trail_pad;
 #pragma unroll 1
-            for (int i = 0; i < most; ++i) {                                  // warp-uniform: every lane shuffles
+            for (int i = 0; i < steps; ++i) {                                 // lanes 0..7 only; symbols from the warp's shared board copy
                 const int c = cell0 + i * stride;
-                const bool on = i < len;
-                const uint32_t w = __shfl_sync(0xffffffffu, bw, on ? (c >> 4) : 15);
-                uint32_t v2 = on ? ((w >> ((c & 15) * 2)) & 3u) * 2u : 6u;
+                uint32_t v2 = i < len ? cell_value(ws.board, c) * 2u : 6u;
                 if (lane >= 4 && c == cell) v2 = 0u;                         // before the move this cell was empty
-                if (i < steps) {
-                    nx = lds_u16(next_addr + nx + v2);
-                    if (nx < emit_thr) {
-                        sts_u16(lp, nx * 8u + uint32_t(i));
-                        lp += 2;
-                    }
+                nx = lds_u16(next_addr + nx + v2);
+                if (nx < emit_thr) {
+                    sts_u16(lp, nx * 8u + uint32_t(i));
+                    lp += 2;
                 }
             }
+            __syncwarp();
             win = 0;
             {   // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names line and sign)
                 uint32_t incl = (lp - list_addr) >> 1;
