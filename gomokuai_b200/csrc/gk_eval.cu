@@ -87,7 +87,15 @@ __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy
 // x / d for d > 0, IEEE-rounded like the reference's float division.  A zero numerator (most cells: no stone nearby, or
 // occupied) skips the division: 0 / d is +0 anyway, and the correctly rounded division's special-case path -- which a
 // zero operand takes -- costs ~40 instructions for the whole warp every time ANY lane needs it.
-__device__ __forceinline__ float div_pos(float x, float d) { return x != 0.f ? x / d : 0.f; }
+// (A plain `x != 0 ? x / d : 0` does not help: the compiler divides first and selects afterwards.  So the division itself
+// never sees the zero: it divides 1 instead and the quotient is dropped.)
+__device__ __forceinline__ float div_pos(float x, float d) {
+    const bool nz = x != 0.f;
+    float xs = nz ? x : 1.f;
+    asm("" : "+f"(xs));                                   // opaque: or the compiler folds the two selects back into x / d
+    const float q = xs / d;
+    return nz ? q : 0.f;
+}
 
 __device__ __forceinline__ uint32_t cell_value(const uint32_t* board, uint32_t cell) {
     return (board[cell >> 4] >> ((cell & 15u) * 2u)) & 3u;

@@ -16,6 +16,10 @@ for w in $what; do
     refarm)  python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err || rc=$? ;;
     profile) bash scripts/profile_round.sh $tag || rc=$? ;;
     guided)  python scripts/bench_guided.py 256 1024 8192 65536 > $out/guided_$tag.json 2> $out/guided_$tag.err; r=$?; cat $out/guided_$tag.err | cut -c1-400; [ $r -ne 0 ] && rc=$r ;;
+    gprofile) python scripts/profile_guided.py > $out/gplain_$tag.log 2>&1 && \
+             ncu --set full --clock-control none --import-source on -f -o /tmp/gprof_$tag python scripts/profile_guided.py > $out/gncu_$tag.log 2>&1; \
+             ncu -i /tmp/gprof_$tag.ncu-rep --page source --csv --kernel-name regex:guided_kernel --launch-count 1 > $out/src_guided1k_$tag.csv 2>/dev/null; \
+             ncu -i /tmp/gprof_$tag.ncu-rep --page raw --csv > $out/gprof_${tag}_raw.csv 2>/dev/null; tail -2 $out/gncu_$tag.log ;;
     sweep)   python scripts/sweep_root_parallel.py > $out/rp_sweep_$tag.json 2> $out/rp_sweep_$tag.err; r=$?; tail -6 $out/rp_sweep_$tag.err | cut -c1-300; [ $r -ne 0 ] && rc=$r ;;
     *)       echo "unknown step $w" ;;
   esac
