@@ -518,6 +518,13 @@ static gk_status policy_host(const gk_table* t, const uint32_t* h_boards, int n,
 gk_status gk_guided_rollout_batch(const gk_table* t, const uint32_t* d_boards, int n, int mode, uint64_t philox_key,
                                   uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner, int16_t* d_length,
                                   int16_t* d_moves, uint32_t* d_final_boards, void* stream) {
+    return gk_guided_rollout_queue(t, d_boards, n, 0, mode, philox_key, ctr_hi, game_base, max_moves, d_winner, d_length, d_moves,
+                                   d_final_boards, stream);
+}
+
+gk_status gk_guided_rollout_queue(const gk_table* t, const uint32_t* d_boards, int n, int max_in_flight, int mode, uint64_t philox_key,
+                                  uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner, int16_t* d_length,
+                                  int16_t* d_moves, uint32_t* d_final_boards, void* stream) {
     if (gk_status s = require_device()) return s;
     const int full_rescan = (mode & GK_GUIDED_FULL_RESCAN) ? 1 : 0;
     mode &= ~GK_GUIDED_FULL_RESCAN;
@@ -525,7 +532,7 @@ gk_status gk_guided_rollout_batch(const gk_table* t, const uint32_t* d_boards, i
         return fail(GK_ERR_INVALID, "bad arguments");
     if (gk_status s = ensure_uploaded(t)) return s;
     gk::EvalArgs a = eval_args(t, d_boards, n, nullptr, nullptr, nullptr, nullptr);
-    a.g_mode = mode; a.g_full_rescan = full_rescan; a.g_key_lo = uint32_t(philox_key); a.g_key_hi = uint32_t(philox_key >> 32); a.g_ctr_hi = ctr_hi;
+    a.g_mode = mode; a.g_full_rescan = full_rescan; a.g_in_flight = max_in_flight > 0 ? max_in_flight : 0; a.g_key_lo = uint32_t(philox_key); a.g_key_hi = uint32_t(philox_key >> 32); a.g_ctr_hi = ctr_hi;
     a.g_game_base = game_base; a.g_max_moves = max_moves;
     a.g_winner = d_winner; a.g_length = d_length; a.g_moves = d_moves; a.g_final = d_final_boards;
     GK_CUDA(gk::launch_eval(a, g_sm_count, static_cast<cudaStream_t>(stream)));

@@ -1297,10 +1297,15 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
     // A small batch is spread over all SMs (fewer warps per CTA, at least 4 to share the table load) instead of filling a
     // few: a warp is one serial chain, and seven of them per scheduler slow each other down (1 024 guided games: 0.99 ->
     // 0.88 ms, 256: 0.93 -> 0.80 ms; no difference from 4 096 games up).
-    const long long per_sm = (a.n + sm_count - 1) / sm_count;
-    if (a.n >= sm_count && per_sm < warps) warps = (int)(per_sm > 4 ? per_sm : (warps < 4 ? warps : 4));   // (a handful of boards: one full CTA loads the tables fastest)
+    // Guided playouts may bound the games IN FLIGHT (one warp each): the n games are then a queue that the resident warps
+    // work through (the kernels' grid-stride loop), i.e. self-play as a continuous stream with a fixed concurrency.
+    const long long units = (a.g_mode != 0 && a.g_in_flight > 0 && a.g_in_flight < a.n) ? a.g_in_flight : a.n;
+    const long long per_sm = (units + sm_count - 1) / sm_count;
+    if (units >= sm_count && per_sm < warps) warps = (int)(per_sm > 4 ? per_sm : (warps < 4 ? warps : 4));   // (a handful of boards: one full CTA loads the tables fastest)
     const size_t smem = table_smem_bytes(a) + extra_table_bytes(a) + size_t(warps) * warp_bytes(a.list_cap, wants_heads(a));
-    const long long want = (a.n + warps - 1) / warps;
+    if (units < warps) warps = (int)(units > 0 ? units : 1);
+    const bool bounded = units < a.n;                                        // a bound on the games in flight is not to be exceeded
+    const long long want = bounded ? (units / warps > 0 ? units / warps : 1) : (units + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? want : sm_count);               // persistent: one CTA per SM
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -157,6 +157,14 @@ gk_status gk_guided_rollout_batch(const gk_table* table, const uint32_t* d_board
                                   uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner, int16_t* d_length,
                                   int16_t* d_moves, uint32_t* d_final_boards, void* stream);
 
+/* The same with at most `max_in_flight` games being played at any moment (one warp each; <= 0: as many as the GPU holds):
+ * the n games form a queue that the resident warps work through.  This is self-play as a continuous stream with a fixed
+ * number of concurrent games (BASELINE config 5) -- one batch of that size lasts as long as its LONGEST game, a stream
+ * runs at the rate of the mean.  Results are the same as gk_guided_rollout_batch's. */
+gk_status gk_guided_rollout_queue(const gk_table* table, const uint32_t* d_boards, int n, int max_in_flight, int mode,
+                                  uint64_t philox_key, uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner,
+                                  int16_t* d_length, int16_t* d_moves, uint32_t* d_final_boards, void* stream);
+
 /* ---- random rollouts ----------------------------------------------------------------
  * Replaces Default::RandomRollout / Default::Simulate (include/algorithms/MonteCarlo.hpp:
  * 37-47,83-88) and RandomPolicy::averagedSimulate (include/policies/Random.h:22-35) for

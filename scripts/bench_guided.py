@@ -24,6 +24,19 @@ for n in sizes:
                     best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
             moves = float(r["length"].float().sum().item())
             row[f"{name}_{mode}"] = {"ms": best, "games_per_s": n / (best * 1e-3), "moves_per_s": moves / (best * 1e-3), "mean_length": moves / n}
+    # the same concurrency as a STREAM: 16 batches' worth of games, at most n in flight
+    big = torch.zeros((16 * n, 16), dtype=torch.int32, device="cuda")
+    for name, full in (("incremental", False), ("full_rescan", True)):
+        best = None
+        for it in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = gk.guided_rollout_batch(big, mode="sample", key=gk.SYNTH_KEY, game_base=0, want_moves=True, full_rescan=full, max_in_flight=n)
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 1:
+                best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
+        row[f"{name}_sample_stream"] = {"ms": best, "games": 16 * n, "in_flight": n, "games_per_s": 16 * n / (best * 1e-3)}
     row["speedup_sample"] = row["full_rescan_sample"]["ms"] / row["incremental_sample"]["ms"]
     row["speedup_max"] = row["full_rescan_max"]["ms"] / row["incremental_max"]["ms"]
     rows.append(row)

@@ -157,6 +157,8 @@ def test_gpu_guided_max_moves_and_determinism(gpu):
     a = gpu.guided_rollout_batch(boards, mode="sample", key=KEY, max_moves=3)
     assert int(a["length"].max()) <= 3
     b = gpu.guided_rollout_batch(boards, mode="sample", key=KEY)
+    q = gpu.guided_rollout_batch(boards, mode="sample", key=KEY, max_in_flight=8)     # a queue worked through by 8 warps
+    assert all(np.array_equal(b[k].cpu().numpy(), q[k].cpu().numpy()) for k in ("winner", "length", "moves", "final_boards"))
     c = gpu.guided_rollout_batch(boards[32:], mode="sample", key=KEY, game_base=32)
     assert np.array_equal(b["moves"].cpu().numpy()[32:], c["moves"].cpu().numpy())   # independent of batch split
     assert np.array_equal(b["winner"].cpu().numpy()[32:], c["winner"].cpu().numpy())
