@@ -491,9 +491,10 @@ __device__ GK_HEADS_INLINE int select_move(const float* prob, int lane, int mode
 // ======================= incremental guided playouts (BASELINE config 5) ===================================
 // A playout adds ONE stone per evaluation, and a stone only changes the four lines through it (exhaustive theorem T5,
 // an emission that does not cover the changed cell is unchanged).  guided_kernel therefore evaluates a
-// game's START position from scratch (all 72 lines, as ac_eval_kernel) and afterwards, per move, rescans only those four
-// lines twice -- as they were (emissions taken back, Updater::updatePatterns with delta = -1) and as they are (+1) --
-// which is the reference's own incremental scheme (Updater::updateMove, Pattern.cpp:274-302) at line granularity.
+// game's START position from scratch (all 72 lines, as ac_eval_kernel) and afterwards, per move, rescans only the four
+// 13-symbol windows around the stone twice -- as they were (emissions that cover the stone taken back,
+// Updater::updatePatterns with delta = -1) and as they are (+1) -- which is the reference's own incremental scheme
+// (Updater::updateMove, Pattern.cpp:274-302; theorem T4: the covering emissions of a window are the whole line's).
 // Compounds follow the same scheme: they are a function of a cell's counts and of its own four 13-symbol windows, so a move
 // can only change the compounds of the cells within 6 steps of it on its four lines; those are taken back before the
 // lines change and added again afterwards (Updater::updateCompound, Pattern.cpp:169-197, does the same).
@@ -501,18 +502,6 @@ __device__ GK_HEADS_INLINE int select_move(const float* prob, int lane, int mode
 // maps, from the density accumulators the guided variant keeps anyway.
 // Every float the heads compute is produced by the same operations in the same order as ac_eval_kernel<true, true>,
 // so both variants play IDENTICAL games (tests/test_guided.py).
-
-// the line through cell m in direction dir, restricted to the board (Mapping.cpp:11-25): first cell, cell stride, length
-__device__ __forceinline__ void line_through(int m, uint32_t dir, int& cell0, int& stride, int& len) {
-    const int my = m / kWidth, mx = m - my * kWidth;
-    if (dir == 0) { cell0 = my * kWidth; stride = 1; len = kWidth; }
-    else if (dir == 1) { cell0 = mx; stride = kWidth; len = kHeight; }
-    else if (dir == 2) { const int k = mx - my; cell0 = k > 0 ? k : -k * kWidth; stride = kWidth + 1; len = kWidth - (k > 0 ? k : -k); }
-    else {
-        const int t = mx + my, x0 = t < kWidth ? t : kWidth - 1;
-        cell0 = (t - x0) * kWidth + x0; stride = kWidth - 1; len = (t < kWidth ? t : 2 * (kWidth - 1) - t) + 1;
-    }
-}
 
 // Compound::Test (Pattern.cpp:424-433) on the two count words of a cell: per direction the classes' counts are OR-ed and
 // a binary 10 is widened to 11 before the "at least two bits" test; bit 0 = white passes, bit 1 = black passes
@@ -543,21 +532,31 @@ __device__ __forceinline__ int compound_candidates_all(const WarpSmem& ws, unsig
     return cn;
 }
 
-// The same over the cells whose compounds a move at m can change: the (up to 12) neighbours of m within 6 steps on each
-// of its four lines -- a compound's counts and its updateAntis windows only see its own four 13-symbol windows
-// (Updater::updateCompound walks exactly these cells, Pattern.cpp:169-197) -- and, with_centre, m itself.
-__device__ __forceinline__ int compound_candidates_window(const WarpSmem& ws, unsigned short* clist, int m, bool with_centre,
-                                                          int lane, uint32_t lt) {
+// The cells a move at m can touch: its four 13-cell windows (Mapping.cpp:31-34), slot = direction * 13 + (k + 6) for the
+// cell k steps from m; a lane holds slots lane and lane + 32 (52 slots).  wc[r] = the cell of slot r * 32 + lane, -1 off the board.
+__device__ __forceinline__ void window_slots(int m, int lane, int wc[2]) {
     const int my = m / kWidth, mx = m - my * kWidth;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int slot = r * 32 + lane;
+        const int dir = slot / 13, k = slot - dir * 13 - 6;
+        const int x = mx + k * (dir == 1 ? 0 : dir == 3 ? -1 : 1), y = my + k * (dir == 0 ? 0 : 1);
+        wc[r] = (slot < 52 && x >= 0 && x < kWidth && y >= 0 && y < kHeight) ? y * kWidth + x : -1;
+    }
+}
+__device__ __forceinline__ bool slot_is_centre(int slot) { return slot == 6 || slot == 19 || slot == 32 || slot == 45; }
+
+// compound_candidates_all over the cells whose compounds a move at m can change: the (up to 12) neighbours of m within 6
+// steps on each of its four lines -- a compound's counts and its updateAntis windows only see its own four 13-symbol
+// windows (Updater::updateCompound walks exactly these cells, Pattern.cpp:169-197) -- and, with_centre, m itself.
+__device__ __forceinline__ int compound_candidates_window(const WarpSmem& ws, unsigned short* clist, const int wc[2], bool with_centre,
+                                                          int lane, uint32_t lt) {
     const uint2* f2 = reinterpret_cast<const uint2*>(ws.flags);
     int cn = 0;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int slot = r * 32 + lane;                            // slot = direction * 13 + (k + 6), 52 slots
-        const int dir = slot / 13, k = slot - dir * 13 - 6;
-        const int x = mx + k * (dir == 1 ? 0 : dir == 3 ? -1 : 1), y = my + k * (dir == 0 ? 0 : 1);
-        const bool on = slot < 52 && (k != 0 || (with_centre && dir == 0)) && x >= 0 && x < kWidth && y >= 0 && y < kHeight;
-        const int cell = y * kWidth + x;
+        const int slot = r * 32 + lane, cell = wc[r];
+        const bool on = cell >= 0 && (!slot_is_centre(slot) || (with_centre && slot == 6));
         const uint32_t pass = compound_test(f2[on ? cell : kCells]);
         const uint32_t m0 = __ballot_sync(0xffffffffu, pass & 1u), m1 = __ballot_sync(0xffffffffu, pass & 2u);
         if (pass & 1u) clist[cn + __popc(m0 & lt)] = (unsigned short)(cell * 2);
@@ -825,8 +824,10 @@ guided_kernel(EvalArgs a) {
             }
             if (cell < 0) break;
             __syncwarp();
+            int wc[2];
+            window_slots(cell, lane, wc);
             {   // the compounds this move can change are taken back while the lines still are as they were
-                const int cn = compound_candidates_window(ws, lists, cell, true, lane, lt);
+                const int cn = compound_candidates_window(ws, lists, wc, true, lane, lt);
                 compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, -600);
             }
             // ---- place the stone ----------------------------------------------------------------------------------------
@@ -847,25 +848,35 @@ guided_kernel(EvalArgs a) {
             }
             ++played;
             __syncwarp();
-            // ---- the four lines through the stone: lane & 3 = direction, lanes 0..3 as they are now (+1), 4..7 as they were (-1)
-            int cell0, stride, len;
-            line_through(cell, uint32_t(lane) & 3u, cell0, stride, len);
-            const int steps = (lane < 8 && len >= 5) ? len + a.trail_pad : 0;   // shorter diagonals hold no pattern (they are not on the tape either)
-            uint32_t nx = a.start_off, lp = list_addr;
+            // ---- the four 13-symbol windows around the stone (Updater::matchPatterns, Pattern.cpp:128-136): lane & 3 = direction,
+            // lanes 0..3 scan them as they are now (emissions added), lanes 4..7 as they were (taken back).  Only emissions that
+            // cover the stone count (HasCovered, Pattern.cpp:22-25); by theorem T4 those are the whole line's, by T5 no other changes.
+            uint32_t p0, p1;                                                   // the lane's window, one bit plane per symbol bit
+            {
+                uint32_t v[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) v[r] = wc[r] >= 0 ? cell_value(ws.board, uint32_t(wc[r])) : 3u;   // off the board: '?'
+                const uint32_t a0 = __ballot_sync(0xffffffffu, v[0] & 1u), b0 = __ballot_sync(0xffffffffu, v[1] & 1u);
+                const uint32_t a1 = __ballot_sync(0xffffffffu, v[0] & 2u), b1 = __ballot_sync(0xffffffffu, v[1] & 2u);
+                const uint32_t sh = 13u * (uint32_t(lane) & 3u);               // direction d owns slots 13 d .. 13 d + 12
+                p0 = (sh < 32u ? __funnelshift_r(a0, b0, sh) : b0 >> (sh - 32u)) & 0x1fffu;
+                p1 = (sh < 32u ? __funnelshift_r(a1, b1, sh) : b1 >> (sh - 32u)) & 0x1fffu;
+                if (lane >= 4) { p0 &= ~0x40u; p1 &= ~0x40u; }                // before the move the centre was empty
+            }
+            uint32_t nx = uint32_t(a.root_off), lp = list_addr;
+            if (lane < 8) {
 #pragma unroll 1
-            for (int i = 0; i < steps; ++i) {                                 // lanes 0..7 only; symbols from the warp's shared board copy
-                const int c = cell0 + i * stride;
-                uint32_t v2 = i < len ? cell_value(ws.board, c) * 2u : 6u;
-                if (lane >= 4 && c == cell) v2 = 0u;                         // before the move this cell was empty
-                nx = lds_u16(next_addr + nx + v2);
-                if (nx < emit_thr) {
-                    sts_u16(lp, nx * 8u + uint32_t(i));
-                    lp += 2;
+                for (int i = 0; i < 13; ++i, p0 >>= 1, p1 >>= 1) {
+                    nx = lds_u16(next_addr + nx + ((p0 & 1u) * 2u + (p1 & 1u) * 4u));
+                    if (nx < emit_thr) {
+                        sts_u16(lp, nx * 8u + uint32_t(i));
+                        lp += 2;
+                    }
                 }
             }
             __syncwarp();
             win = 0;
-            {   // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names line and sign)
+            {   // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names direction and sign)
                 uint32_t incl = (lp - list_addr) >> 1;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -881,20 +892,26 @@ guided_kernel(EvalArgs a) {
                     if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
                     if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
                     const int first = __shfl_sync(0xffffffffu, excl, j);
-                    const int jc0 = __shfl_sync(0xffffffffu, cell0, j), jstride = __shfl_sync(0xffffffffu, stride, j);
                     if (i >= total) continue;
                     const uint32_t ent = lists[j * cap + (i - first)];
                     const uint32_t er = s_erec[ent >> 6];
-                    const int vcell = jc0 + int(ent & 63u) * jstride, delta = j < 4 ? 1 : -1;
-                    uint32_t w = apply_emission(ws, nullptr, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * jstride, uint32_t(j) & 3u, jstride, delta);
-                    const uint32_t p1 = er_pid(er, 1);
-                    if (p1 != kDevNoPid) w |= apply_emission(ws, nullptr, s_patrec[p1], vcell - int(er_prev(er, 1)) * jstride, uint32_t(j) & 3u, jstride, delta);
-                    if (delta > 0) win |= w;
+                    const uint32_t dir = uint32_t(j) & 3u;
+                    const int stride = dir_stride(int(dir)), delta = j < 4 ? 1 : -1;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t pid = er_pid(er, k);
+                        if (pid == kDevNoPid) break;
+                        const PatRec rec = s_patrec[pid];
+                        const int off = int(ent & 63u) - int(er_prev(er, k));  // window index of the pattern's last symbol; the stone sits at 6
+                        if (off < 6 || off - int(pr_len(rec.w0)) + 1 > 6) continue;
+                        const uint32_t w = apply_emission(ws, nullptr, rec, cell + (off - 6) * stride, dir, stride, delta);
+                        if (delta > 0) win |= w;
+                    }
                 }
             }
             __syncwarp();
             {   // ... and added again from the new counts and the new board
-                const int cn = compound_candidates_window(ws, lists, cell, false, lane, lt);
+                const int cn = compound_candidates_window(ws, lists, wc, false, lane, lt);
                 compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
             }
         }
@@ -1272,7 +1289,7 @@ static bool wants_heads(const EvalArgs& a) {
 }
 
 // shared tables beside the automaton: the density LUT of the head variants, the quotient LUT of the incremental guided kernel
-static bool incremental_guided(const EvalArgs& a) { return a.g_mode != 0 && !a.g_full_rescan && kWidth + a.trail_pad <= a.list_cap; }
+static bool incremental_guided(const EvalArgs& a) { return a.g_mode != 0 && !a.g_full_rescan && a.list_cap >= 13; }   // a lane's list holds one 13-symbol window
 static size_t extra_table_bytes(const EvalArgs& a) {
     return (wants_heads(a) ? 4 * 128 * sizeof(uint16_t) : 0) + (incremental_guided(a) ? align16(size_t(kVlutN) * kVlutW * sizeof(float)) : 0);
 }
@@ -1313,8 +1330,7 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
         kernel<<<grid, warps * 32, smem, stream>>>(a);
         return cudaGetLastError();
     };
-    // guided playouts: the incremental kernel, unless the caller asks for the full rescan or a custom table's lines could
-    // overflow a lane's emission list (one line of 15 + trail_pad steps per lane there)
+    // guided playouts: the incremental kernel, unless the caller asks for the full rescan
     if (a.g_mode != 0) return incremental_guided(a) ? launch(guided_kernel) : launch(ac_eval_kernel<true, true>);
     return wants_heads(a) ? launch(ac_eval_kernel<true, false>) : launch(ac_eval_kernel<false, false>);
 }
