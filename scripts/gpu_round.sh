@@ -20,6 +20,8 @@ for w in $what; do
              ncu --set full --clock-control none --import-source on -f -o /tmp/gprof_$tag python scripts/profile_guided.py > $out/gncu_$tag.log 2>&1; \
              ncu -i /tmp/gprof_$tag.ncu-rep --page source --csv --kernel-name regex:guided_kernel --launch-count 1 > $out/src_guided1k_$tag.csv 2>/dev/null; \
              ncu -i /tmp/gprof_$tag.ncu-rep --page raw --csv > $out/gprof_${tag}_raw.csv 2>/dev/null; tail -2 $out/gncu_$tag.log ;;
+    parity)  python tests/tools/full_parity.py > $out/full_parity_$tag.json 2> $out/full_parity_$tag.err; r=$?; head -c 700 $out/full_parity_$tag.json; echo; [ $r -ne 0 ] && { tail -3 $out/full_parity_$tag.err; rc=$r; } ;;
+    benchN)  n=$(nvidia-smi -L | wc -l); python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 > $out/bench_n${n}_$tag.json 2> $out/bench_n${n}_$tag.err; r=$?; head -c 400 $out/bench_n${n}_$tag.json; echo; [ $r -ne 0 ] && { tail -8 $out/bench_n${n}_$tag.err; rc=$r; } ;;
     sweep)   python scripts/sweep_root_parallel.py > $out/rp_sweep_$tag.json 2> $out/rp_sweep_$tag.err; r=$?; tail -6 $out/rp_sweep_$tag.err | cut -c1-300; [ $r -ne 0 ] && rc=$r ;;
     *)       echo "unknown step $w" ;;
   esac
