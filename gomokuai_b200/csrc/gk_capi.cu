@@ -680,6 +680,7 @@ gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t 
 // ---- asynchronous host entry points: several small batches in flight (root-parallel search) ----------------
 namespace {
 constexpr int kAsyncSlots = 8;
+constexpr int kFusedAsyncMax = 4096;     // positions per asynchronous batch that still go through the one-launch path
 struct AsyncSlot {
     std::mutex mutex;
     cudaStream_t stream = nullptr;
@@ -710,12 +711,27 @@ gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int 
     // on a path whose cost is launch latency; pageable boards are staged through the slot's device buffer
     const uint32_t* boards = a.d_boards;
     cudaPointerAttributes attr{};
-    if (cudaPointerGetAttributes(&attr, h_boards) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+    bool boards_mapped = false;
+    if (cudaPointerGetAttributes(&attr, h_boards) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
         boards = static_cast<const uint32_t*>(attr.devicePointer);
-    else {
+        boards_mapped = true;
+    } else {
         cudaGetLastError();
-        GK_CUDA(cudaMemcpyAsync(a.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, a.stream));
     }
+    // A leaf batch of a tree search is a few hundred positions x a handful of playouts: pure latency.  With both buffers
+    // page-locked the whole round trip is ONE launch -- one CTA per position builds the slot image, plays the playouts and
+    // writes the three counts straight into the caller's memory -- instead of image kernel + rollout kernel + copy-out.
+    cudaPointerAttributes wattr{};
+    if (boards_mapped && n <= kFusedAsyncMax && rollouts_per_pos <= 256 &&
+        cudaPointerGetAttributes(&wattr, h_wdb) == cudaSuccess && wattr.type == cudaMemoryTypeHost && wattr.devicePointer) {
+        gk::RolloutArgs ra{};
+        ra.boards = boards; ra.n = n; ra.rollouts_per_pos = rollouts_per_pos;
+        ra.key_lo = uint32_t(philox_key); ra.key_hi = uint32_t(philox_key >> 32); ra.ctr_hi = ctr_hi; ra.pos_base = pos_base;
+        GK_CUDA(gk::launch_rollout_small(ra, static_cast<int32_t*>(wattr.devicePointer), a.stream));
+        return GK_OK;
+    }
+    cudaGetLastError();
+    if (!boards_mapped) GK_CUDA(cudaMemcpyAsync(a.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, a.stream));
     if (gk_status s = rollout_common(boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, a.d_wdb, nullptr,
                                      nullptr, a.stream))
         return s;
