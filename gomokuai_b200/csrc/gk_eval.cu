@@ -1007,15 +1007,16 @@ ac_eval_kernel(EvalArgs a) {
     };
 
     const int warps = blockDim.x >> 5;
-    for (long long b = (long long)blockIdx.x * warps + warp; b < a.n; b += (long long)gridDim.x * warps) {
+    const long long b0 = (long long)blockIdx.x * warps + warp, bstride = (long long)gridDim.x * warps;
+    // the warp's next board is requested one board ahead: its 64 bytes are in flight while the current board is evaluated
+    uint32_t bw_next = (b0 < a.n && lane < kBoardWords) ? __ldg(a.boards + b0 * kBoardWords + lane) : 0u;
+    for (long long b = b0; b < a.n; b += bstride) {
         // ---- phase 0 ---------------------------------------------------------------------------
         uint32_t bw = 0xffffffffu;
-        if (lane < kBoardWords) {
-            bw = __ldg(a.boards + b * kBoardWords + lane);
-            bw &= ~((bw >> 1) & 0x55555555u);                               // a cell holding the invalid value 3 reads as white
-        }
+        if (lane < kBoardWords) bw = bw_next & ~((bw_next >> 1) & 0x55555555u);   // a cell holding the invalid value 3 reads as white
         if (lane == 14) bw |= 0xfffffffcu;                                  // cells 225.. are pads
         if (lane == 15) bw = 0xffffffffu;
+        if (b + bstride < a.n && lane < kBoardWords) bw_next = __ldg(a.boards + (b + bstride) * kBoardWords + lane);
         int played = 0, result = 0;                                         // guided mode: moves played so far / final winner
       next_move:                                                            // guided mode re-enters here after every move
         uint32_t nx = a.start_off;

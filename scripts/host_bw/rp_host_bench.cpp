@@ -33,6 +33,7 @@ gk_status gk_host_alloc(void** out, size_t bytes) { *out = std::malloc(bytes); r
 gk_status gk_host_free(void* p) { std::free(p); return GK_OK; }
 gk_status gk_table_default(gk_table**) { return GK_ERR_NO_DEVICE; }
 gk_status gk_hybrid_simulate_batch_host(const gk_table*, const uint32_t*, int, float*, float*, int8_t*) { return GK_ERR_NO_DEVICE; }
+gk_status gk_rollout_trace_host(const uint32_t*, int, uint64_t, uint32_t, int, int8_t*, uint8_t*, uint8_t*) { return GK_ERR_NO_DEVICE; }
 gk_status gk_rollout_batch_host(const uint32_t* b, int n, int r, uint64_t key, uint32_t ctr, int base, int32_t* wdb) {
     spin_us(g_latency_us);
     fake(b, n, r, key, ctr, base, wdb);
