@@ -599,9 +599,7 @@ __device__ __noinline__ void compounds_apply(WarpSmem& ws, const unsigned short*
 // The heads of policy_heads() for the incremental variant: the density accumulators are always valid, the DensityWeight
 // values are recomputed from them where policy_heads() parks them in ws.flags (the counts must survive here), and the
 // block score the maps do not hold is added as the maps are read: +160 on S(P, P) where P's weight is positive
-// (Pattern.cpp:244,268).  Same float operations in the same order as policy_heads().  Unlike there the loops are partly
-// unrolled: a guided game is one warp's serial chain (often the only warp of its scheduler), so the loads of the next
-// cells must be in flight while the current ones are divided and summed.
+// (Pattern.cpp:244,268).  Same float operations in the same order as policy_heads().
 // s_vlut[N * 101 + W] = (3 W) / (1 + 2 N) for every possible accumulator (N <= 24 weighted cells, W <= 100 = the sum of
 // Evaluator::BlockWeights): the IEEE quotients, computed once per CTA, instead of four divisions per cell and move.
 constexpr int kVlutW = 101, kVlutN = 25;
@@ -619,7 +617,7 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     const uint16_t* acc_p = dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30));
     const int step = live ? kWidth : 0;
     float n2 = 0.f;
-#pragma unroll 5
+#pragma unroll 1
     for (int y = 0; y < kHeight; ++y) {
         const uint32_t full = live ? uint32_t(*acc_p) : 0u;
         acc_p += step;
@@ -639,7 +637,7 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     const int* s_anti = ws.scores + (2 * (1 - p) + p) * kCells;
     const int* s_rival = ws.scores + 3 * (1 - p) * kCells;
     float a2 = 0.f, sdot = 0.f, rdot = 0.f;
-#pragma unroll 4
+#pragma unroll 1
     for (int c = lane; c < kCells; c += 32, occ8 >>= 1) {
         const bool empty = (occ8 & 1u) == 0u;
         const uint32_t fw = dacc[c], fb = dacc[kCells + c];
@@ -667,14 +665,13 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     const float an = a2 > 0.f ? sqrtf(a2) : 1.f;
     n_stones = n_black + n_white;
     to_move = p;
-#pragma unroll 4
+#pragma unroll 1
     for (int c = lane; c < kCells; c += 32)
         prob[c] = empty_board ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : div_pos(prob[c], an);
     __syncwarp();
 }
 
-constexpr int kGuidedWarps = 24;        // 768 threads: 85 registers per thread for the unrolled heads (shared memory would hold 26 warps)
-__global__ void __launch_bounds__(kGuidedWarps * 32, 1)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
 guided_kernel(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_rows = a.n_clones + a.n_states;
@@ -1302,8 +1299,8 @@ static int eval_warps(const EvalArgs& a) {
     const size_t tables = table_smem_bytes(a) + extra_table_bytes(a),
                  per_warp = warp_bytes(a.list_cap, wants_heads(a));
     if (tables + per_warp > kSmemLimit) return 0;
-    const size_t fit = (kSmemLimit - tables) / per_warp, most = incremental_guided(a) ? size_t(kGuidedWarps) : size_t(kWarpsPerCta);
-    return int(fit < most ? fit : most);
+    const size_t fit = (kSmemLimit - tables) / per_warp;
+    return int(fit < size_t(kWarpsPerCta) ? fit : size_t(kWarpsPerCta));
 }
 
 size_t eval_smem_bytes(const EvalArgs& a) {
