@@ -12,6 +12,7 @@ rc=0
 for w in $what; do
   case $w in
     tests)   python -m pytest tests -m gpu -q -s > $out/pytest_$tag.log 2>&1; r=$?; tail -5 $out/pytest_$tag.log; [ $r -ne 0 ] && rc=$r ;;
+    gtests)  python -m pytest tests/test_guided.py tests/test_gpu_eval.py -m gpu -q -s > $out/pytest_$tag.log 2>&1; r=$?; tail -4 $out/pytest_$tag.log; [ $r -ne 0 ] && rc=$r ;;
     bench)   python bench.py --steps 10 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err; r=$?; head -c 600 $out/bench_$tag.json; echo; [ $r -ne 0 ] && { tail -5 $out/bench_$tag.err; rc=$r; } ;;
     refarm)  python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err || rc=$? ;;
     profile) bash scripts/profile_round.sh $tag || rc=$? ;;
