@@ -165,8 +165,8 @@ def run_reference_arm(args, rank):
         return
     import gomokuai_b200 as gk                                          # host-only use: the synthetic position generator
     arm = CpuArm()
-    n_eval = 384 * arm.cores                                             # ~0.25 s of evaluator replay per core and step
-    n_roll_pos, n_roll = 2 * arm.cores, 16384                            # ~0.15 s of rollouts per core and step
+    n_eval = 1536 * arm.cores                                            # ~0.5 s of evaluator replay per core and step: long enough that the
+    n_roll_pos, n_roll = 4 * arm.cores, 32768                            # pool's start-up does not weigh on the rate; ~0.5 s of rollouts
     _, moves, starts = gk.synth_positions(0, max(n_eval, n_roll_pos))
     ev, ro = [], []
     for i in range(args.warmup + args.steps):
