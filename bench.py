@@ -490,6 +490,21 @@ def run_gpu_arm(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(host_bw, op=dist.ReduceOp.SUM)
     host_bw = float(host_bw.item())
+    # ... and the platform's device-to-host DMA ceiling: every rank copies 1 GiB out of HBM into pinned memory at the same
+    # moment, nothing else running (one GPU: its PCIe link; several: whatever the box's I/O fabric and memory take together)
+    d_big = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    h_big = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    h_big.copy_(d_big)                                                  # touch the pages
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h_big.copy_(d_big, non_blocking=True)
+    torch.cuda.synchronize()
+    dma_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(dma_s, op=dist.ReduceOp.MAX)
+    dma_gbs = world * 3 * (1 << 30) / float(dma_s.item()) / 1e9
+    del d_big, h_big
 
     # ---- the other configurations of BASELINE.json, briefly (same timing rules; extra objects of the JSON line) -----
     extras = {}
@@ -575,11 +590,11 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": world * n_eval / e2e_eval_s, "unit": "boards/s", "h2d_bytes_per_step": n_eval * 64,
                 "d2h_bytes_per_step": n_eval * (3600 + 32 + 12 + 1), "ms_per_step": e2e_eval_s * 1e3,
                 "host": {"achieved_write_gbs": world * n_eval * 3645 / e2e_eval_s / 1e9, "per_gpu_gbs": n_eval * 3645 / e2e_eval_s / 1e9,
+                         "d2h_copy_ceiling_gbs": dma_gbs, "frac_of_d2h_copy_ceiling": world * n_eval * 3645 / e2e_eval_s / 1e9 / dma_gbs,
                          "cpu_stream_write_gbs": host_bw, "cpu_stream_threads": bw_threads * world,
-                         "frac_of_cpu_stream": world * n_eval * 3645 / e2e_eval_s / 1e9 / host_bw,
-                         "note": "results land in ONE host memory system (one NUMA node on this pool's boxes): one GPU is bound by its "
-                                 "PCIe link (~56 GB/s), several by the box's DRAM write bandwidth, measured here by all ranks' CPU threads "
-                                 "streaming memsets at the same moment"},
+                         "note": "two ceilings measured in the same job: d2h_copy_ceiling = every rank copying 1 GiB from HBM to pinned host "
+                                 "memory at the same moment (one GPU: its PCIe link; several: the box's I/O path into ONE host memory "
+                                 "system), cpu_stream_write = every rank's share of the host cores streaming memsets (what the DRAM itself takes)"},
                 "compact": {"what": "gk_eval_policy_batch_host: probs f32[225] + value + winner = 905 B per board instead of 3645",
                             "value": world * n_eval / pol_e2e_s, "unit": "boards/s"},
                 "note": "gk_eval_batch_host: pinned host buffers, 3 chunks in flight"},

@@ -407,7 +407,9 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     // waits for batches (publishing `ready`) and submits a visit's leaves once all of them are packed (`done`), so CUDA
     // call latency stays off the workers' critical path; while it waits for the workers it takes chunks itself.  A tree's Philox
     // stream is (round, global tree index), whatever G and the thread count are.
-    const int groups = std::max(1, std::min(kMaxGroups, n_trees / 64));
+    // (a group needs few trees to be worth a launch since a leaf batch is ONE fused launch: with 128 trees per rank -- the
+    // benchmark's 1 024 trees over 8 GPUs -- four groups of 32 keep four round trips in flight instead of two)
+    const int groups = std::max(1, std::min(kMaxGroups, n_trees / 16));
     std::array<int, kMaxGroups + 1> gs{};
     for (int g = 0; g <= groups; ++g) gs[g] = static_cast<int>(static_cast<long long>(n_trees) * g / groups);
     const long long visits_total = static_cast<long long>(playouts_per_tree + 1) * groups;
