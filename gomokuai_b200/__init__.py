@@ -355,15 +355,17 @@ def eval_policy_batch_host(boards, table=None, decisive=False, out=None):
 
 
 GUIDED_FULL_RESCAN = 0x100
+GUIDED_SINGLE_WARP = 0x200
 
 
 def guided_rollout_batch(boards, mode="max", key=SYNTH_KEY, ctr_hi=0, game_base=0, max_moves=CELLS, want_moves=True,
-                         table=None, stream=None, full_rescan=False, max_in_flight=0):
+                         table=None, stream=None, full_rescan=False, max_in_flight=0, single_warp=False):
     """Pattern-guided playouts (Heuristic::EvaluatedRollout, include/algorithms/Heuristic.hpp:61-91), one warp per game,
     whole games inside one kernel.  mode "max" = MaxEvaluatedRollout, "sample" = RandomEvaluatedRollout.
     full_rescan: re-evaluate the whole board after every move instead of the four lines through the new stone (slower;
     both play identical games).  max_in_flight > 0: at most that many games are played at the same time, the others queue
     (gk_guided_rollout_queue: a stream of games with fixed concurrency); the results do not depend on it.
+    single_warp: keep every game on one warp even when few are in flight (else two warps per game there; same games).
     Returns dict(winner[n] i8, length[n] i16, moves[n,max_moves] i16 (-1 padded), final_boards[n,16] i32)."""
     torch = _torch()
     boards = _as_board_tensor(boards)
@@ -376,7 +378,8 @@ def guided_rollout_batch(boards, mode="max", key=SYNTH_KEY, ctr_hi=0, game_base=
         "final_boards": torch.empty((n, BOARD_WORDS), dtype=torch.int32, device=dev),
     }
     _check(lib().gk_guided_rollout_queue(table.handle, _ptr(boards), n, int(max_in_flight),
-                                         {"max": 1, "sample": 2}[mode] | (GUIDED_FULL_RESCAN if full_rescan else 0), ctypes.c_uint64(key),
+                                         {"max": 1, "sample": 2}[mode] | (GUIDED_FULL_RESCAN if full_rescan else 0) | (GUIDED_SINGLE_WARP if single_warp else 0),
+                                         ctypes.c_uint64(key),
                                          ctypes.c_uint32(ctr_hi), int(game_base), int(max_moves), _ptr(out["winner"]),
                                          _ptr(out["length"]), _ptr(out["moves"]), _ptr(out["final_boards"]),
                                          _stream_ptr(stream)))

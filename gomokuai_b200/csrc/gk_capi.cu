@@ -526,13 +526,13 @@ gk_status gk_guided_rollout_queue(const gk_table* t, const uint32_t* d_boards, i
                                   uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner, int16_t* d_length,
                                   int16_t* d_moves, uint32_t* d_final_boards, void* stream) {
     if (gk_status s = require_device()) return s;
-    const int full_rescan = (mode & GK_GUIDED_FULL_RESCAN) ? 1 : 0;
-    mode &= ~GK_GUIDED_FULL_RESCAN;
+    const int full_rescan = (mode & GK_GUIDED_FULL_RESCAN) ? 1 : 0, single_warp = (mode & GK_GUIDED_SINGLE_WARP) ? 1 : 0;
+    mode &= ~(GK_GUIDED_FULL_RESCAN | GK_GUIDED_SINGLE_WARP);
     if (!t || n < 0 || (n > 0 && !d_boards) || (mode != 1 && mode != 2) || max_moves < 0 || max_moves > GK_CELLS)
         return fail(GK_ERR_INVALID, "bad arguments");
     if (gk_status s = ensure_uploaded(t)) return s;
     gk::EvalArgs a = eval_args(t, d_boards, n, nullptr, nullptr, nullptr, nullptr);
-    a.g_mode = mode; a.g_full_rescan = full_rescan; a.g_in_flight = max_in_flight > 0 ? max_in_flight : 0; a.g_key_lo = uint32_t(philox_key); a.g_key_hi = uint32_t(philox_key >> 32); a.g_ctr_hi = ctr_hi;
+    a.g_mode = mode; a.g_full_rescan = full_rescan; a.g_single_warp = single_warp; a.g_in_flight = max_in_flight > 0 ? max_in_flight : 0; a.g_key_lo = uint32_t(philox_key); a.g_key_hi = uint32_t(philox_key >> 32); a.g_ctr_hi = ctr_hi;
     a.g_game_base = game_base; a.g_max_moves = max_moves;
     a.g_winner = d_winner; a.g_length = d_length; a.g_moves = d_moves; a.g_final = d_final_boards;
     GK_CUDA(gk::launch_eval(a, g_sm_count, static_cast<cudaStream_t>(stream)));

@@ -671,6 +671,214 @@ __device__ GK_HEADS_INLINE void policy_heads_inc(WarpSmem& ws, float* prob, uint
     __syncwarp();
 }
 
+// ---- pieces shared by guided_kernel and guided_pair_kernel ----------------------------------------------------------
+// what the kernels read of the compiled table and their own shared tables
+struct GuidedTables {
+    const uint32_t* s_erec; const PatRec* s_patrec; const uint16_t* s_lut; const float* s_vlut;
+    uint32_t next_addr, src_addr, emit_thr, root_off, start_off;
+    const uint16_t* tape_info; int tape_steps, cap;
+};
+
+// the board of game b: one word per lane (lanes 14 / 15 carry the pads), cells holding the invalid value 3 read as white
+__device__ __forceinline__ uint32_t guided_load_board(const uint32_t* boards, long long b, int lane) {
+    uint32_t bw = 0xffffffffu;
+    if (lane < kBoardWords) {
+        bw = __ldg(boards + b * kBoardWords + lane);
+        bw &= ~((bw >> 1) & 0x55555555u);
+    }
+    if (lane == 14) bw |= 0xfffffffcu;
+    if (lane == 15) bw = 0xffffffffu;
+    return bw;
+}
+
+// lanes 0..14: the white stones of row `lane`, lanes 15..29: the black stones of row `lane - 15` (from the shared board copy)
+__device__ __forceinline__ uint32_t guided_rows(const uint32_t* board, int lane) {
+    uint32_t mine = 0;
+    if (lane < 30) {
+        const int y = lane - 15 * (lane >= 15), off = 30 * y;
+        const uint32_t lo = board[off >> 5], hi = board[(off >> 5) + 1];
+        const uint32_t v = __funnelshift_r(lo, hi, off & 31) & 0x3fffffffu;
+        mine = lane >= 15 ? squeeze_even(v) : squeeze_even(v >> 1);
+    }
+    return mine;
+}
+
+// bit k: cell lane + 32 k holds a stone
+__device__ __forceinline__ uint32_t guided_occ8(const uint32_t* board, int lane) {
+    uint32_t occ8 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (lane + 32 * k < kCells && cell_value(board, lane + 32 * k) != 0u) occ8 |= 1u << k;
+    return occ8;
+}
+
+// density accumulators of the start position: policy_heads()' column walk, accumulators only
+__device__ __forceinline__ void guided_density_init(uint32_t mine, int lane, const uint16_t* s_lut, uint16_t* dacc) {
+    const int dc = lane >= 15, dx = lane - 15 * dc;
+    const bool live = lane < 30;
+    uint16_t* acc_p = dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30));
+    const int step = live ? kWidth : 0, src0 = 15 * dc;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+#pragma unroll 1
+    for (int y = 0; y < kHeight + 3; ++y) {
+        uint32_t row = __shfl_sync(0xffffffffu, mine, src0 + y);
+        row = (y < kHeight && live) ? row : 0u;
+        const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;
+        const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
+        const uint32_t full = w0 + t3;
+        w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
+        if (y >= 3) { *acc_p = uint16_t(full); acc_p += step; }
+    }
+}
+
+// a new stone of colour to_move (1 black) at (mx, my): its contribution to the density accumulators of its colour
+__device__ __forceinline__ void guided_density_add(uint16_t* dacc, const uint16_t* s_lut, int lane, int mx, int my, int to_move) {
+    const int dc = lane >= 15, dx = lane - 15 * dc, j = mx - dx + 3;
+    if (lane < 30 && dc == to_move && j >= 0 && j < 7) {
+#pragma unroll 1
+        for (int d = -3; d <= 3; ++d) {
+            const int y = my + d;
+            if (y >= 0 && y < kHeight) dacc[dc * kCells + y * kWidth + dx] += s_lut[(d < 0 ? -d : d) * 128 + (1 << j)];
+        }
+    }
+}
+
+// the start position from scratch: phases 2 and 3 of ac_eval_kernel (all 72 lines; no block score, no compounds).  Returns winner bits.
+__device__ __forceinline__ uint32_t guided_start_position(WarpSmem& ws, const uint16_t* lists, uint32_t list_addr, const GuidedTables& T,
+                                                          uint32_t bw, int lane) {
+    uint32_t win = 0;
+    uint32_t nx = T.start_off, lp = list_addr, src = T.src_addr;
+    for (int t = 0; t < T.tape_steps; t += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u, src += 64) {
+            const uint32_t e = lds_u16(src);
+            const uint32_t w = __shfl_sync(0xffffffffu, bw, e);
+            const uint32_t v2 = __funnelshift_r(w, w, e >> 8) & 6u;
+            nx = lds_u16(T.next_addr + nx + v2);
+            if (nx < T.emit_thr) {
+                sts_u16(lp, nx * 8u + uint32_t(t + u));
+                lp += 2;
+            }
+        }
+    }
+    uint32_t incl = (lp - list_addr) >> 1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int total = int(__shfl_sync(0xffffffffu, incl, 31));
+    const int excl = int(incl) - int((lp - list_addr) >> 1);
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const int i = i0 + lane;
+        int j = __shfl_sync(0xffffffffu, excl, 16) <= i ? 16 : 0;
+        if (__shfl_sync(0xffffffffu, excl, j + 8) <= i) j += 8;
+        if (__shfl_sync(0xffffffffu, excl, j + 4) <= i) j += 4;
+        if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
+        if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
+        const int first = __shfl_sync(0xffffffffu, excl, j);
+        if (i >= total) continue;
+        const uint32_t ent = lists[j * T.cap + (i - first)];
+        const uint32_t er = T.s_erec[ent >> 6];
+        const uint32_t inf = __ldg(T.tape_info + (ent & 63u) * 32u + uint32_t(j));
+        const uint32_t dir = (inf >> 9) & 3u;
+        const int vcell = inf & 0x1ff, stride = int(inf >> 11);
+        win |= apply_emission(ws, nullptr, T.s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir, stride);
+        const uint32_t p1 = er_pid(er, 1);
+        if (p1 != kDevNoPid) win |= apply_emission(ws, nullptr, T.s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir, stride);
+    }
+    __syncwarp();
+    return win;
+}
+
+// A stone was placed at `cell` (ws.board already holds it): the four 13-symbol windows around it (Updater::matchPatterns,
+// Pattern.cpp:128-136) are scanned from the root state, lane & 3 = direction, lanes 0..3 as they are now (emissions added),
+// lanes 4..7 as they were (taken back).  Only emissions that cover the stone count (HasCovered, Pattern.cpp:22-25); by
+// theorem T4 those are the whole line's, by T5 nothing else changes.  wc: window_slots(cell).  Returns winner bits.
+__device__ __forceinline__ uint32_t guided_move_patterns(WarpSmem& ws, const uint16_t* lists, uint32_t list_addr, const GuidedTables& T,
+                                                         int cell, const int wc[2], int lane) {
+    uint32_t p0, p1;                                                           // the lane's window, one bit plane per symbol bit
+    {
+        uint32_t v[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) v[r] = wc[r] >= 0 ? cell_value(ws.board, uint32_t(wc[r])) : 3u;   // off the board: '?'
+        const uint32_t a0 = __ballot_sync(0xffffffffu, v[0] & 1u), b0 = __ballot_sync(0xffffffffu, v[1] & 1u);
+        const uint32_t a1 = __ballot_sync(0xffffffffu, v[0] & 2u), b1 = __ballot_sync(0xffffffffu, v[1] & 2u);
+        const uint32_t sh = 13u * (uint32_t(lane) & 3u);                       // direction d owns slots 13 d .. 13 d + 12
+        p0 = (sh < 32u ? __funnelshift_r(a0, b0, sh) : b0 >> (sh - 32u)) & 0x1fffu;
+        p1 = (sh < 32u ? __funnelshift_r(a1, b1, sh) : b1 >> (sh - 32u)) & 0x1fffu;
+        if (lane >= 4) { p0 &= ~0x40u; p1 &= ~0x40u; }                        // before the move the centre was empty
+    }
+    uint32_t nx = T.root_off, lp = list_addr;
+    if (lane < 8) {
+#pragma unroll 1
+        for (int i = 0; i < 13; ++i, p0 >>= 1, p1 >>= 1) {
+            nx = lds_u16(T.next_addr + nx + ((p0 & 1u) * 2u + (p1 & 1u) * 4u));
+            if (nx < T.emit_thr) {
+                sts_u16(lp, nx * 8u + uint32_t(i));
+                lp += 2;
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t win = 0;
+    // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names direction and sign)
+    uint32_t incl = (lp - list_addr) >> 1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int total = int(__shfl_sync(0xffffffffu, incl, 31));
+    const int excl = int(incl) - int((lp - list_addr) >> 1);
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const int i = i0 + lane;
+        int j = __shfl_sync(0xffffffffu, excl, 4) <= i ? 4 : 0;               // only lanes 0..7 hold entries
+        if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
+        if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
+        const int first = __shfl_sync(0xffffffffu, excl, j);
+        if (i >= total) continue;
+        const uint32_t ent = lists[j * T.cap + (i - first)];
+        const uint32_t er = T.s_erec[ent >> 6];
+        const uint32_t dir = uint32_t(j) & 3u;
+        const int stride = dir_stride(int(dir)), delta = j < 4 ? 1 : -1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t pid = er_pid(er, k);
+            if (pid == kDevNoPid) break;
+            const PatRec rec = T.s_patrec[pid];
+            const int off = int(ent & 63u) - int(er_prev(er, k));              // window index of the pattern's last symbol; the stone sits at 6
+            if (off < 6 || off - int(pr_len(rec.w0)) + 1 > 6) continue;
+            const uint32_t w = apply_emission(ws, nullptr, rec, cell + (off - 6) * stride, dir, stride, delta);
+            if (delta > 0) win |= w;
+        }
+    }
+    __syncwarp();
+    return win;
+}
+
+// the compiled table and the two look-up tables of the heads -> shared memory (all threads of the CTA)
+__device__ __forceinline__ void guided_load_tables(const EvalArgs& a, uint16_t* s_next, uint32_t* s_erec, PatRec* s_patrec, uint16_t* s_src,
+                                                   uint16_t* s_lut, float* s_vlut) {
+    const int n_rows = a.n_clones + a.n_states;
+    for (int i = threadIdx.x; i < kVlutN * kVlutW; i += blockDim.x)
+        s_vlut[i] = (3.f * float(i % kVlutW)) / (1.f + 2.f * float(i / kVlutW));     // the expression of policy_heads(), Heuristic.hpp:39-45
+    for (int i = threadIdx.x; i < n_rows * 4; i += blockDim.x) s_next[i] = a.next16[i];
+    for (int i = threadIdx.x; i < a.n_clones; i += blockDim.x) s_erec[i] = a.erec[i];
+    for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
+    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) s_src[i] = a.tape_src[i];
+    // density of one window row: count | weight << 8 of the stones in a 7-bit row slice, by |dy| (Evaluator::BlockWeights, Pattern.cpp:598-609)
+    const int wts[4][7] = { { 1, 3, 4, 0, 4, 3, 1 }, { 0, 3, 5, 4, 5, 3, 0 }, { 0, 4, 3, 3, 3, 4, 0 }, { 2, 0, 0, 1, 0, 0, 2 } };
+    for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) {
+        int n = 0, w = 0;
+        for (int bit = 0; bit < 7; ++bit)
+            if ((i >> bit) & 1) { w += wts[i >> 7][bit]; n += wts[i >> 7][bit] > 0; }
+        s_lut[i] = uint16_t(n | w << 8);
+    }
+}
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
 guided_kernel(EvalArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -682,22 +890,7 @@ guided_kernel(EvalArgs a) {
     uint16_t* s_lut = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64));
     float* s_vlut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_lut) + 4 * 128 * sizeof(uint16_t));
     unsigned char* s_warps = reinterpret_cast<unsigned char*>(s_vlut) + align16(size_t(kVlutN) * kVlutW * sizeof(float));
-
-    for (int i = threadIdx.x; i < kVlutN * kVlutW; i += blockDim.x)
-        s_vlut[i] = (3.f * float(i % kVlutW)) / (1.f + 2.f * float(i / kVlutW));     // the expression of policy_heads(), Heuristic.hpp:39-45
-    for (int i = threadIdx.x; i < n_rows * 4; i += blockDim.x) s_next[i] = a.next16[i];
-    for (int i = threadIdx.x; i < a.n_clones; i += blockDim.x) s_erec[i] = a.erec[i];
-    for (int i = threadIdx.x; i < a.n_patterns; i += blockDim.x) s_patrec[i] = a.patrec[i];
-    for (int i = threadIdx.x; i < a.tape_steps * 32; i += blockDim.x) s_src[i] = a.tape_src[i];
-    {
-        const int wts[4][7] = { { 1, 3, 4, 0, 4, 3, 1 }, { 0, 3, 5, 4, 5, 3, 0 }, { 0, 4, 3, 3, 3, 4, 0 }, { 2, 0, 0, 1, 0, 0, 2 } };
-        for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) {
-            int n = 0, w = 0;
-            for (int bit = 0; bit < 7; ++bit)
-                if ((i >> bit) & 1) { w += wts[i >> 7][bit]; n += wts[i >> 7][bit] > 0; }
-            s_lut[i] = uint16_t(n | w << 8);
-        }
-    }
+    guided_load_tables(a, s_next, s_erec, s_patrec, s_src, s_lut, s_vlut);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -707,21 +900,15 @@ guided_kernel(EvalArgs a) {
     uint16_t* dacc = reinterpret_cast<uint16_t*>(lists + 32 * cap);        // density accumulators, uint16 [2][225] (+ 2 idle-lane slots)
     float* prob = reinterpret_cast<float*>(lists);                          // 225 floats over the emission lists (dead while the heads run)
     const uint32_t lt = lanemask_lt();
-    const uint32_t emit_thr = uint32_t(a.n_clones) * 8u;
-    uint32_t next_addr = smem_addr(s_next), src_addr = smem_addr(s_src + lane);
+    GuidedTables T{ s_erec, s_patrec, s_lut, s_vlut, smem_addr(s_next), smem_addr(s_src + lane), uint32_t(a.n_clones) * 8u,
+                    uint32_t(a.root_off), uint32_t(a.start_off), a.tape_info, a.tape_steps, cap };
     uint32_t list_addr = smem_addr(lists + lane * cap);
-    asm volatile("" : "+r"(next_addr), "+r"(src_addr), "+r"(list_addr));
+    asm volatile("" : "+r"(T.next_addr), "+r"(T.src_addr), "+r"(list_addr));
 
     const int warps = blockDim.x >> 5;
     for (long long b = (long long)blockIdx.x * warps + warp; b < a.n; b += (long long)gridDim.x * warps) {
-        // ---- the start position, from scratch: phases 0, 2, 3 of ac_eval_kernel (no block score, no compounds) -------
-        uint32_t bw = 0xffffffffu;
-        if (lane < kBoardWords) {
-            bw = __ldg(a.boards + b * kBoardWords + lane);
-            bw &= ~((bw >> 1) & 0x55555555u);
-        }
-        if (lane == 14) bw |= 0xfffffffcu;
-        if (lane == 15) bw = 0xffffffffu;
+        // ---- the start position, from scratch -------------------------------------------------------------------------
+        uint32_t bw = guided_load_board(a.boards, b, lane);
         if (lane < kBoardSmem) ws.board[lane] = bw;
         {
             int4* z = reinterpret_cast<int4*>(ws.scores);
@@ -729,82 +916,13 @@ guided_kernel(EvalArgs a) {
             if (lane < kTotalWords) ws.totals[lane] = 0;
         }
         __syncwarp();
-        uint32_t mine = 0;                                                   // lanes 0..14 white rows, 15..29 black rows
-        if (lane < 30) {
-            const int y = lane - 15 * (lane >= 15), off = 30 * y;
-            const uint32_t lo = ws.board[off >> 5], hi = ws.board[(off >> 5) + 1];
-            const uint32_t v = __funnelshift_r(lo, hi, off & 31) & 0x3fffffffu;
-            mine = lane >= 15 ? squeeze_even(v) : squeeze_even(v >> 1);
-        }
-        uint32_t occ8 = 0;                                                   // bit k: cell lane + 32 k holds a stone
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (lane + 32 * k < kCells && cell_value(ws.board, lane + 32 * k) != 0u) occ8 |= 1u << k;
-        {   // density accumulators of the start position: policy_heads()' column walk, accumulators only
-            const int dc = lane >= 15, dx = lane - 15 * dc;
-            const bool live = lane < 30;
-            uint16_t* acc_p = dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30));
-            const int step = live ? kWidth : 0, src0 = 15 * dc;
-            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
-#pragma unroll 1
-            for (int y = 0; y < kHeight + 3; ++y) {
-                uint32_t row = __shfl_sync(0xffffffffu, mine, src0 + y);
-                row = (y < kHeight && live) ? row : 0u;
-                const uint32_t w7 = ((row << 3) >> dx) & 0x7fu;
-                const uint32_t t0 = s_lut[w7], t1 = s_lut[128 + w7], t2 = s_lut[256 + w7], t3 = s_lut[384 + w7];
-                const uint32_t full = w0 + t3;
-                w0 = w1 + t2; w1 = w2 + t1; w2 = w3 + t0; w3 = w4 + t1; w4 = w5 + t2; w5 = t3;
-                if (y >= 3) { *acc_p = uint16_t(full); acc_p += step; }
-            }
-        }
-        uint32_t win = 0;
-        {
-            uint32_t nx = a.start_off, lp = list_addr, src = src_addr;
-            for (int t = 0; t < a.tape_steps; t += 2) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u, src += 64) {
-                    const uint32_t e = lds_u16(src);
-                    const uint32_t w = __shfl_sync(0xffffffffu, bw, e);
-                    const uint32_t v2 = __funnelshift_r(w, w, e >> 8) & 6u;
-                    nx = lds_u16(next_addr + nx + v2);
-                    if (nx < emit_thr) {
-                        sts_u16(lp, nx * 8u + uint32_t(t + u));
-                        lp += 2;
-                    }
-                }
-            }
-            uint32_t incl = (lp - list_addr) >> 1;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
-            }
-            const int total = int(__shfl_sync(0xffffffffu, incl, 31));
-            const int excl = int(incl) - int((lp - list_addr) >> 1);
-            __syncwarp();
-            for (int i0 = 0; i0 < total; i0 += 32) {
-                const int i = i0 + lane;
-                int j = __shfl_sync(0xffffffffu, excl, 16) <= i ? 16 : 0;
-                if (__shfl_sync(0xffffffffu, excl, j + 8) <= i) j += 8;
-                if (__shfl_sync(0xffffffffu, excl, j + 4) <= i) j += 4;
-                if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
-                if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
-                const int first = __shfl_sync(0xffffffffu, excl, j);
-                if (i >= total) continue;
-                const uint32_t ent = lists[j * cap + (i - first)];
-                const uint32_t er = s_erec[ent >> 6];
-                const uint32_t inf = __ldg(a.tape_info + (ent & 63u) * 32u + uint32_t(j));
-                const uint32_t dir = (inf >> 9) & 3u;
-                const int vcell = inf & 0x1ff, stride = int(inf >> 11);
-                win |= apply_emission(ws, nullptr, s_patrec[er_pid(er, 0)], vcell - int(er_prev(er, 0)) * stride, dir, stride);
-                const uint32_t p1 = er_pid(er, 1);
-                if (p1 != kDevNoPid) win |= apply_emission(ws, nullptr, s_patrec[p1], vcell - int(er_prev(er, 1)) * stride, dir, stride);
-            }
-        }
-        __syncwarp();
+        uint32_t mine = guided_rows(ws.board, lane);                         // lanes 0..14 white rows, 15..29 black rows
+        uint32_t occ8 = guided_occ8(ws.board, lane);
+        guided_density_init(mine, lane, s_lut, dacc);
+        uint32_t win = guided_start_position(ws, lists, list_addr, T, bw, lane);
         {   // the start position's compounds, from all its counts
             const int cn = compound_candidates_all(ws, lists, lane, lt);
-            compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
+            compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, 600);
         }
 
         // ---- the game: Heuristic::EvaluatedRollout (Heuristic.hpp:61-72) ------------------------------------------------
@@ -828,7 +946,7 @@ guided_kernel(EvalArgs a) {
             window_slots(cell, lane, wc);
             {   // the compounds this move can change are taken back while the lines still are as they were
                 const int cn = compound_candidates_window(ws, lists, wc, true, lane, lt);
-                compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, -600);
+                compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, -600);
             }
             // ---- place the stone ----------------------------------------------------------------------------------------
             if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
@@ -836,89 +954,210 @@ guided_kernel(EvalArgs a) {
             if (lane == (cell >> 4)) { bw |= (to_move ? 1u : 2u) << ((cell & 15) * 2); ws.board[lane] = bw; }
             if (lane == (to_move ? 15 : 0) + my) mine |= 1u << mx;
             if (lane == (cell & 31)) occ8 |= 1u << (cell >> 5);
-            {
-                const int dc = lane >= 15, dx = lane - 15 * dc, j = mx - dx + 3;
-                if (lane < 30 && dc == to_move && j >= 0 && j < 7) {
-#pragma unroll 1
-                    for (int d = -3; d <= 3; ++d) {
-                        const int y = my + d;
-                        if (y >= 0 && y < kHeight) dacc[dc * kCells + y * kWidth + dx] += s_lut[(d < 0 ? -d : d) * 128 + (1 << j)];
-                    }
-                }
-            }
+            guided_density_add(dacc, s_lut, lane, mx, my, to_move);
             ++played;
             __syncwarp();
-            // ---- the four 13-symbol windows around the stone (Updater::matchPatterns, Pattern.cpp:128-136): lane & 3 = direction,
-            // lanes 0..3 scan them as they are now (emissions added), lanes 4..7 as they were (taken back).  Only emissions that
-            // cover the stone count (HasCovered, Pattern.cpp:22-25); by theorem T4 those are the whole line's, by T5 no other changes.
-            uint32_t p0, p1;                                                   // the lane's window, one bit plane per symbol bit
-            {
-                uint32_t v[2];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) v[r] = wc[r] >= 0 ? cell_value(ws.board, uint32_t(wc[r])) : 3u;   // off the board: '?'
-                const uint32_t a0 = __ballot_sync(0xffffffffu, v[0] & 1u), b0 = __ballot_sync(0xffffffffu, v[1] & 1u);
-                const uint32_t a1 = __ballot_sync(0xffffffffu, v[0] & 2u), b1 = __ballot_sync(0xffffffffu, v[1] & 2u);
-                const uint32_t sh = 13u * (uint32_t(lane) & 3u);               // direction d owns slots 13 d .. 13 d + 12
-                p0 = (sh < 32u ? __funnelshift_r(a0, b0, sh) : b0 >> (sh - 32u)) & 0x1fffu;
-                p1 = (sh < 32u ? __funnelshift_r(a1, b1, sh) : b1 >> (sh - 32u)) & 0x1fffu;
-                if (lane >= 4) { p0 &= ~0x40u; p1 &= ~0x40u; }                // before the move the centre was empty
-            }
-            uint32_t nx = uint32_t(a.root_off), lp = list_addr;
-            if (lane < 8) {
-#pragma unroll 1
-                for (int i = 0; i < 13; ++i, p0 >>= 1, p1 >>= 1) {
-                    nx = lds_u16(next_addr + nx + ((p0 & 1u) * 2u + (p1 & 1u) * 4u));
-                    if (nx < emit_thr) {
-                        sts_u16(lp, nx * 8u + uint32_t(i));
-                        lp += 2;
-                    }
-                }
-            }
-            __syncwarp();
-            win = 0;
-            {   // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names direction and sign)
-                uint32_t incl = (lp - list_addr) >> 1;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += up;
-                }
-                const int total = int(__shfl_sync(0xffffffffu, incl, 31));
-                const int excl = int(incl) - int((lp - list_addr) >> 1);
-                __syncwarp();
-                for (int i0 = 0; i0 < total; i0 += 32) {
-                    const int i = i0 + lane;
-                    int j = __shfl_sync(0xffffffffu, excl, 4) <= i ? 4 : 0;   // only lanes 0..7 hold entries
-                    if (__shfl_sync(0xffffffffu, excl, j + 2) <= i) j += 2;
-                    if (__shfl_sync(0xffffffffu, excl, j + 1) <= i) j += 1;
-                    const int first = __shfl_sync(0xffffffffu, excl, j);
-                    if (i >= total) continue;
-                    const uint32_t ent = lists[j * cap + (i - first)];
-                    const uint32_t er = s_erec[ent >> 6];
-                    const uint32_t dir = uint32_t(j) & 3u;
-                    const int stride = dir_stride(int(dir)), delta = j < 4 ? 1 : -1;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint32_t pid = er_pid(er, k);
-                        if (pid == kDevNoPid) break;
-                        const PatRec rec = s_patrec[pid];
-                        const int off = int(ent & 63u) - int(er_prev(er, k));  // window index of the pattern's last symbol; the stone sits at 6
-                        if (off < 6 || off - int(pr_len(rec.w0)) + 1 > 6) continue;
-                        const uint32_t w = apply_emission(ws, nullptr, rec, cell + (off - 6) * stride, dir, stride, delta);
-                        if (delta > 0) win |= w;
-                    }
-                }
-            }
-            __syncwarp();
+            win = guided_move_patterns(ws, lists, list_addr, T, cell, wc, lane);
             {   // ... and added again from the new counts and the new board
                 const int cn = compound_candidates_window(ws, lists, wc, false, lane, lt);
-                compounds_apply(ws, lists, cn, lane, next_addr, uint32_t(a.root_off), emit_thr, s_erec, s_patrec, 600);
+                compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, 600);
             }
         }
         if (a.g_winner && lane == 0) a.g_winner[b] = (int8_t)result;
         if (a.g_length && lane == 0) a.g_length[b] = (int16_t)played;
         if (a.g_final && lane < kBoardWords) a.g_final[b * kBoardWords + lane] = lane == 14 ? (bw & 3u) : lane == 15 ? 0u : bw;
         __syncwarp();
+    }
+}
+
+// ---- two warps per game: the latency-bound regime (at most a few games per SM) ------------------------------------------
+// With 1 024 games on 148 SMs a guided game is the only warp of its scheduler and a move is one serial chain of ~2 900
+// instructions.  Two of its parts do not depend on each other: (A) the evaluator update -- compounds taken back, the four
+// windows scanned, emissions scattered, compounds added -- and (B) the density weights -- accumulators of the new stone, the
+// two norms, one normalised weight per cell and colour.  guided_pair_kernel gives a game two warps: warp A does (A), warp B
+// does (B) at the same time, then both halves of the per-cell work of the heads (each warp takes four of a lane's eight
+// cells), warp A picks the move.  Every float is produced by the operations of policy_heads_inc() and SUMMED IN ITS ORDER
+// (the a2 sum is taken from the stored per-cell values in cell order), so the games are those of guided_kernel, bit for bit.
+// Four named barriers per move (bar.sync id, 64); the loop is the same for both warps, so they cannot miss each other.
+constexpr int kPairMax = 15;                                       // pairs per CTA: barrier ids 1..15
+constexpr int kWnWords = 2 * kCells + 2;                           // normalised density weights, float [2][225] (16-byte multiple)
+struct PairMail { int cell; uint32_t won; int pad0, pad1; };
+__host__ __device__ inline size_t pair_bytes(int list_cap) { return warp_bytes(list_cap, true) + kWnWords * sizeof(float) + sizeof(PairMail); }
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(kPairMax * 64, 1)
+guided_pair_kernel(EvalArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n_rows = a.n_clones + a.n_states;
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* s_erec = reinterpret_cast<uint32_t*>(smem_raw + align16(size_t(n_rows) * 8));
+    PatRec* s_patrec = reinterpret_cast<PatRec*>(reinterpret_cast<unsigned char*>(s_erec) + align16(size_t(a.n_clones) * 4));
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_patrec) + align16(size_t(a.n_patterns) * sizeof(PatRec)));
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_src) + align16(size_t(a.tape_steps) * 64));
+    float* s_vlut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_lut) + 4 * 128 * sizeof(uint16_t));
+    unsigned char* s_pairs = reinterpret_cast<unsigned char*>(s_vlut) + align16(size_t(kVlutN) * kVlutW * sizeof(float));
+    guided_load_tables(a, s_next, s_erec, s_patrec, s_src, s_lut, s_vlut);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, role = warp & 1, bar = 1 + pair;
+    const int cap = a.list_cap;
+    unsigned char* base = s_pairs + size_t(pair) * pair_bytes(cap);
+    WarpSmem& ws = *reinterpret_cast<WarpSmem*>(base);
+    uint16_t* lists = reinterpret_cast<uint16_t*>(base + sizeof(WarpSmem));
+    uint16_t* dacc = reinterpret_cast<uint16_t*>(lists + 32 * cap);
+    float* wn = reinterpret_cast<float*>(base + warp_bytes(cap, true));    // wn[c] white, wn[225 + c] black: v / norm
+    PairMail* mail = reinterpret_cast<PairMail*>(wn + kWnWords);
+    float* prob = reinterpret_cast<float*>(lists);
+    const uint32_t lt = lanemask_lt();
+    GuidedTables T{ s_erec, s_patrec, s_lut, s_vlut, smem_addr(s_next), smem_addr(s_src + lane), uint32_t(a.n_clones) * 8u,
+                    uint32_t(a.root_off), uint32_t(a.start_off), a.tape_info, a.tape_steps, cap };
+    uint32_t list_addr = smem_addr(lists + lane * cap);
+    asm volatile("" : "+r"(T.next_addr), "+r"(T.src_addr), "+r"(list_addr));
+
+    const int pairs = blockDim.x >> 6;
+    for (long long b = (long long)blockIdx.x * pairs + pair; b < a.n; b += (long long)gridDim.x * pairs) {
+        pair_sync(bar);                                                      // the pair's block is free (previous game finished on both warps)
+        uint32_t bw = guided_load_board(a.boards, b, lane);                  // both warps keep the board words and the row masks
+        if (role == 0) {
+            if (lane < kBoardSmem) ws.board[lane] = bw;
+            int4* z = reinterpret_cast<int4*>(ws.scores);
+            for (int i = lane; i < (kScoreWords + kFlagWords) / 4; i += 32) z[i] = make_int4(0, 0, 0, 0);
+            if (lane < kTotalWords) ws.totals[lane] = 0;
+        }
+        pair_sync(bar);                                                      // ws.board is there
+        uint32_t mine = guided_rows(ws.board, lane);
+        uint32_t occ8 = guided_occ8(ws.board, lane);
+        uint32_t win = 0;
+        if (role == 0) {
+            win = guided_start_position(ws, lists, list_addr, T, bw, lane);
+            const int cn = compound_candidates_all(ws, lists, lane, lt);
+            compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, 600);
+        } else {
+            guided_density_init(mine, lane, s_lut, dacc);
+        }
+        int played = 0, result = 0;
+        for (;;) {
+            // ---- (B) the density weights of this position, while (A) finishes the evaluator update ------------------------------
+            const uint32_t cnt = lane < 30 ? __popc(mine) : 0u;
+            const int n_white = int(__reduce_add_sync(0xffffffffu, lane < 15 ? cnt : 0u));
+            const int n_black = int(__reduce_add_sync(0xffffffffu, lane >= 15 ? cnt : 0u));
+            const int p = n_black == n_white ? 1 : 0, n_stones = n_black + n_white;
+            if (role == 1) {
+                __syncwarp();
+                const int dc = lane >= 15, dx = lane - 15 * dc;
+                const uint32_t occ = mine | __shfl_sync(0xffffffffu, mine, lane < 15 ? lane + 15 : lane - 15);
+                const bool live = lane < 30;
+                const uint32_t xbit = live ? 1u << dx : 0u;
+                const uint16_t* acc_p = dacc + (live ? dc * kCells + dx : 2 * kCells + (lane - 30));
+                const int step = live ? kWidth : 0;
+                float n2 = 0.f;
+#pragma unroll 1
+                for (int y = 0; y < kHeight; ++y) {                          // policy_heads_inc(): the column sums, row by row
+                    const uint32_t full = live ? uint32_t(*acc_p) : 0u;
+                    acc_p += step;
+                    const uint32_t orow = __shfl_sync(0xffffffffu, occ, y);
+                    float v = s_vlut[(full & 0xffu) * kVlutW + (full >> 8)];
+                    v = (orow & xbit) ? 0.f : v;
+                    n2 += v * v;
+                }
+                float n2w = lane < 15 ? n2 : 0.f, n2b = lane >= 15 ? n2 : 0.f;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    n2w += __shfl_xor_sync(0xffffffffu, n2w, d);
+                    n2b += __shfl_xor_sync(0xffffffffu, n2b, d);
+                }
+                const float nrm_w = n2w > 0.f ? sqrtf(n2w) : 1.f, nrm_b = n2b > 0.f ? sqrtf(n2b) : 1.f;
+                uint32_t o = occ8;
+#pragma unroll 1
+                for (int c = lane; c < kCells; c += 32, o >>= 1) {
+                    const bool empty = (o & 1u) == 0u;
+                    const uint32_t fw = dacc[c], fb = dacc[kCells + c];
+                    float vw = s_vlut[(fw & 0xffu) * kVlutW + (fw >> 8)], vb = s_vlut[(fb & 0xffu) * kVlutW + (fb >> 8)];
+                    vw = empty ? vw : 0.f;
+                    vb = empty ? vb : 0.f;
+                    wn[c] = div_pos(vw, nrm_w);
+                    wn[kCells + c] = div_pos(vb, nrm_b);
+                }
+            } else {
+                const uint32_t won = __reduce_or_sync(0xffffffffu, win);
+                if (lane == 0) mail->won = won;
+            }
+            pair_sync(bar);                                                  // (1) scores, counts and weights of this position are complete
+            const uint32_t won = mail->won;
+            if (won) { result = (won & 1u) ? 1 : -1; break; }               // a Five emission ended the game, Pattern.cpp:140-145
+            // ---- the heads' per-cell values: warp A takes a lane's cells k = 0..3, warp B k = 4..7 ------------------------------------
+            {
+                const int* s_self = ws.scores + 3 * p * kCells;
+                const int* s_anti = ws.scores + (2 * (1 - p) + p) * kCells;
+#pragma unroll 1
+                for (int k = 4 * role; k < 4 * role + 4; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < kCells) {
+                        const float w0 = wn[c], w1 = wn[kCells + c];
+                        const float wp = p ? w1 : w0, wr = p ? w0 : w1;
+                        const int self_i = s_self[c] + (wp > 0.f ? 160 : 0);  // a positive normalised weight <=> a positive weight: block score
+                        const float self_worthy = float(self_i) * wp, rival_anti = float(s_anti[c]) * wr;
+                        prob[c] = 0.6f * self_worthy + 0.4f * rival_anti;
+                    }
+                }
+            }
+            pair_sync(bar);                                                  // (2) all 225 values stored
+            float a2 = 0.f;                                                  // both warps: the sum in policy_heads_inc()'s order
+#pragma unroll 1
+            for (int c = lane; c < kCells; c += 32) { const float av = prob[c]; a2 += av * av; }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+            const float an = a2 > 0.f ? sqrtf(a2) : 1.f;
+            pair_sync(bar);                                                  // (3) everybody has read the raw values
+#pragma unroll 1
+            for (int k = 4 * role; k < 4 * role + 4; ++k) {
+                const int c = lane + 32 * k;
+                if (c < kCells) prob[c] = n_stones == 0 ? (c == (kHeight / 2) * kWidth + kWidth / 2 ? 1.f : 0.f) : div_pos(prob[c], an);
+            }
+            pair_sync(bar);                                                  // (4) the probabilities are complete
+            if (role == 0) {
+                int cell = -1;
+                if (n_stones < kCells && played < a.g_max_moves) {           // Evaluator::checkGameEnd, Pattern.cpp:343-353
+                    uint32_t rnd = 0;
+                    if (a.g_mode == 2)
+                        rnd = philox_word(uint32_t(played) >> 2, 0u, uint32_t(a.g_game_base) + uint32_t(b), a.g_ctr_hi, a.g_key_lo,
+                                          a.g_key_hi, uint32_t(played) & 3u);
+                    cell = select_move(prob, lane, a.g_mode, rnd);
+                }
+                if (lane == 0) mail->cell = cell;
+            }
+            pair_sync(bar);                                                  // (5) the move is known
+            const int cell = mail->cell;
+            if (cell < 0) break;
+            const int my = cell / kWidth, mx = cell - my * kWidth;
+            if (lane == (p ? 15 : 0) + my) mine |= 1u << mx;
+            if (lane == (cell & 31)) occ8 |= 1u << (cell >> 5);
+            if (role == 0) {
+                int wc[2];
+                window_slots(cell, lane, wc);
+                {   // the compounds this move can change are taken back while the lines still are as they were
+                    const int cn = compound_candidates_window(ws, lists, wc, true, lane, lt);
+                    compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, -600);
+                }
+                if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
+                if (lane == (cell >> 4)) { bw |= (p ? 1u : 2u) << ((cell & 15) * 2); ws.board[lane] = bw; }
+                __syncwarp();
+                win = guided_move_patterns(ws, lists, list_addr, T, cell, wc, lane);
+                {   // ... and added again from the new counts and the new board
+                    const int cn = compound_candidates_window(ws, lists, wc, false, lane, lt);
+                    compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, 600);
+                }
+            } else {
+                guided_density_add(dacc, s_lut, lane, mx, my, p);
+            }
+            ++played;
+        }
+        if (role == 0) {
+            if (a.g_winner && lane == 0) a.g_winner[b] = (int8_t)result;
+            if (a.g_length && lane == 0) a.g_length[b] = (int16_t)played;
+            if (a.g_final && lane < kBoardWords) a.g_final[b * kBoardWords + lane] = lane == 14 ? (bw & 3u) : lane == 15 ? 0u : bw;
+        }
     }
 }
 
@@ -1331,8 +1570,23 @@ cudaError_t launch_eval(const EvalArgs& a, int sm_count, cudaStream_t stream) {
         kernel<<<grid, warps * 32, smem, stream>>>(a);
         return cudaGetLastError();
     };
-    // guided playouts: the incremental kernel, unless the caller asks for the full rescan
-    if (a.g_mode != 0) return incremental_guided(a) ? launch(guided_kernel) : launch(ac_eval_kernel<true, true>);
+    // guided playouts: the incremental kernels, unless the caller asks for the full rescan.  Few games in flight (at most
+    // kPairMax per SM) get two warps each -- the latency-bound regime, see guided_pair_kernel -- more get one.
+    if (incremental_guided(a)) {
+        const size_t tables = table_smem_bytes(a) + extra_table_bytes(a), per_pair = pair_bytes(a.list_cap);
+        const long long fit = (long long)((kSmemLimit - tables) / per_pair) < kPairMax ? (long long)((kSmemLimit - tables) / per_pair) : kPairMax;
+        if (!a.g_single_warp && fit >= 1 && units <= (long long)sm_count * fit) {
+            const int pairs = (int)(per_sm < 1 ? 1 : per_sm > fit ? fit : per_sm);
+            const long long ctas = bounded ? (units / pairs > 0 ? units / pairs : 1) : (units + pairs - 1) / pairs;
+            const size_t psmem = tables + size_t(pairs) * per_pair;
+            cudaError_t err = cudaFuncSetAttribute(guided_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+            if (err != cudaSuccess) return err;
+            guided_pair_kernel<<<(int)(ctas < sm_count ? ctas : sm_count), pairs * 64, psmem, stream>>>(a);
+            return cudaGetLastError();
+        }
+        return launch(guided_kernel);
+    }
+    if (a.g_mode != 0) return launch(ac_eval_kernel<true, true>);
     return wants_heads(a) ? launch(ac_eval_kernel<true, false>) : launch(ac_eval_kernel<false, false>);
 }
 

@@ -22,6 +22,7 @@ struct EvalArgs {
     // guided playouts (g_mode != 0): every warp plays its board to the end inside the kernel
     int g_mode;                                 // 0 off, 1 most probable move, 2 move drawn from the probabilities
     int g_in_flight;                            // > 0: at most this many games are played at the same time (one warp each); the rest queue
+    int g_single_warp;                          // never give a game two warps (guided_pair_kernel), whatever the batch size; for tests
     int g_full_rescan;                          // re-evaluate the whole board after every move (the first implementation; kept to test the incremental kernel against)
     uint32_t g_key_lo, g_key_hi, g_ctr_hi; int g_game_base, g_max_moves;
     int8_t* g_winner; int16_t* g_length; int16_t* g_moves; uint32_t* g_final;   // per game; any may be null

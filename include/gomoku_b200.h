@@ -144,15 +144,16 @@ gk_status gk_hybrid_simulate_batch_host(const gk_table* table, const uint32_t* h
  * to its end inside ONE kernel, one warp per game: the start position is evaluated from scratch, then every move
  * re-scans only the four lines through the new stone -- before and after, emissions taken back and added, the
  * reference's own incremental scheme (Updater::updateMove, src/Pattern.cpp:274-302).  mode | GK_GUIDED_FULL_RESCAN
- * re-evaluates the whole board after every move instead (the first implementation, ~2.5x the work; both play
- * identical games, which the tests check).
+ * re-evaluates the whole board after every move instead (the first implementation; both play identical games, which
+ * the tests check).  With at most 15 games per SM in flight a game gets TWO warps (evaluator update and density weights of
+ * a move run side by side; same games again); mode | GK_GUIDED_SINGLE_WARP keeps it on one.
  * Randomness (mode 2): weights w = round(p * 2^20), cells in index order, r = mulhi32(word, sum w) with word
  * (k & 3) of Philox4x32-10(counter = {k >> 2, 0, game_base + i, ctr_hi}, key) for move k of game i; the
  * first cell whose running sum exceeds r is played.  (The reference draws from std::discrete_distribution
  * over a process-global mt19937, Game.cpp:75-78, which is implementation defined.)
  * d_winner int8[n] (+1 black, -1 white, 0 draw or max_moves reached), d_length int16[n] moves played,
  * d_moves int16[n][max_moves] (nullable) the cells played, d_final_boards uint32[n][16] (nullable). */
-enum { GK_GUIDED_FULL_RESCAN = 0x100 };
+enum { GK_GUIDED_FULL_RESCAN = 0x100, GK_GUIDED_SINGLE_WARP = 0x200 };
 gk_status gk_guided_rollout_batch(const gk_table* table, const uint32_t* d_boards, int n, int mode, uint64_t philox_key,
                                   uint32_t ctr_hi, int game_base, int max_moves, int8_t* d_winner, int16_t* d_length,
                                   int16_t* d_moves, uint32_t* d_final_boards, void* stream);

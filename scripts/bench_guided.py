@@ -11,13 +11,13 @@ rows = []
 for n in sizes:
     boards = torch.zeros((n, 16), dtype=torch.int32, device="cuda")
     row = {"games": n}
-    for name, full in (("incremental", False), ("full_rescan", True)):
+    for name, full, single in (("incremental", False, False), ("single_warp", False, True), ("full_rescan", True, False)):
         for mode in ("sample", "max"):
             best = None
             for it in range(7):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                r = gk.guided_rollout_batch(boards, mode=mode, key=gk.SYNTH_KEY, game_base=0, want_moves=True, full_rescan=full)
+                r = gk.guided_rollout_batch(boards, mode=mode, key=gk.SYNTH_KEY, game_base=0, want_moves=True, full_rescan=full, single_warp=single)
                 b.record()
                 torch.cuda.synchronize()
                 if it >= 2:
@@ -28,7 +28,7 @@ for n in sizes:
     big = torch.zeros((16 * n, 16), dtype=torch.int32, device="cuda")
     for name, full in (("incremental", False), ("full_rescan", True)):
         best = None
-        for it in range(4):
+        for it in range(3):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             r = gk.guided_rollout_batch(big, mode="sample", key=gk.SYNTH_KEY, game_base=0, want_moves=True, full_rescan=full, max_in_flight=n)

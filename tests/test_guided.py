@@ -141,14 +141,18 @@ def test_gpu_incremental_guided_kernel_plays_the_games_of_the_full_rescan(gpu, m
     lists = _starts(55, 300) + random_positions(56, 200, lo=60, hi=200)
     mv, st = pyoracle.pack_moves(lists)
     boards = np.concatenate([np.zeros((40, 16), np.uint32), gpu.synth_positions(7, 1500, want_moves=False)[0], gpu.pack_moves(mv, st)])
+    assert len(boards) <= 148 * 15                          # few enough for the two-warps-per-game kernel to be the default
     for max_moves in (225, 7):
-        inc = gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves)
         full = gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves, full_rescan=True)
+        variants = {"two warps per game": gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves),
+                    "one warp per game": gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves, single_warp=True),
+                    "two warps, 64 in flight": gpu.guided_rollout_batch(boards, mode=mode, key=KEY + 3, game_base=17, max_moves=max_moves, max_in_flight=64)}
         torch.cuda.synchronize()
-        for k in ("winner", "length", "moves", "final_boards"):
-            a, b = inc[k].cpu().numpy(), full[k].cpu().numpy()
-            assert np.array_equal(a, b), (mode, max_moves, k, int(np.flatnonzero((a != b).reshape(len(boards), -1).any(axis=1))[0]))
-    assert int(inc["length"].sum()) > 0
+        for name, inc in variants.items():
+            for k in ("winner", "length", "moves", "final_boards"):
+                a, b = inc[k].cpu().numpy(), full[k].cpu().numpy()
+                assert np.array_equal(a, b), (name, mode, max_moves, k, int(np.flatnonzero((a != b).reshape(len(boards), -1).any(axis=1))[0]))
+    assert int(full["length"].sum()) > 0
 
 
 @pytest.mark.gpu
