@@ -792,23 +792,23 @@ __device__ __forceinline__ uint32_t guided_start_position(WarpSmem& ws, const ui
     return win;
 }
 
-// A stone of value `stone` (1 black, 2 white) goes to `cell`: the four 13-symbol windows around it (Updater::matchPatterns,
-// Pattern.cpp:128-136) are scanned from the root state, lane & 3 = direction, lanes 0..3 with the stone (emissions to add),
-// lanes 4..7 with the cell still empty (emissions to take back).  The centre symbol is supplied, so ws.board may or may not
-// hold the stone yet.  wc: window_slots(cell).  Returns the lane's list end (shared address).
-__device__ __forceinline__ uint32_t guided_window_scan(const uint32_t* board, uint32_t list_addr, const GuidedTables& T, uint32_t stone,
-                                                       const int wc[2], int lane) {
+// A stone was placed at `cell` (ws.board already holds it): the four 13-symbol windows around it (Updater::matchPatterns,
+// Pattern.cpp:128-136) are scanned from the root state, lane & 3 = direction, lanes 0..3 as they are now (emissions added),
+// lanes 4..7 as they were (taken back).  Only emissions that cover the stone count (HasCovered, Pattern.cpp:22-25); by
+// theorem T4 those are the whole line's, by T5 nothing else changes.  wc: window_slots(cell).  Returns winner bits.
+__device__ __forceinline__ uint32_t guided_move_patterns(WarpSmem& ws, const uint16_t* lists, uint32_t list_addr, const GuidedTables& T,
+                                                         int cell, const int wc[2], int lane) {
     uint32_t p0, p1;                                                           // the lane's window, one bit plane per symbol bit
     {
         uint32_t v[2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) v[r] = wc[r] >= 0 ? cell_value(board, uint32_t(wc[r])) : 3u;   // off the board: '?'
+        for (int r = 0; r < 2; ++r) v[r] = wc[r] >= 0 ? cell_value(ws.board, uint32_t(wc[r])) : 3u;   // off the board: '?'
         const uint32_t a0 = __ballot_sync(0xffffffffu, v[0] & 1u), b0 = __ballot_sync(0xffffffffu, v[1] & 1u);
         const uint32_t a1 = __ballot_sync(0xffffffffu, v[0] & 2u), b1 = __ballot_sync(0xffffffffu, v[1] & 2u);
         const uint32_t sh = 13u * (uint32_t(lane) & 3u);                       // direction d owns slots 13 d .. 13 d + 12
-        p0 = (sh < 32u ? __funnelshift_r(a0, b0, sh) : b0 >> (sh - 32u)) & 0x1fffu & ~0x40u;
-        p1 = (sh < 32u ? __funnelshift_r(a1, b1, sh) : b1 >> (sh - 32u)) & 0x1fffu & ~0x40u;
-        if (lane < 4) { p0 |= (stone & 1u) << 6; p1 |= (stone >> 1) << 6; }   // the centre: the stone, or (lanes 4..7) still empty
+        p0 = (sh < 32u ? __funnelshift_r(a0, b0, sh) : b0 >> (sh - 32u)) & 0x1fffu;
+        p1 = (sh < 32u ? __funnelshift_r(a1, b1, sh) : b1 >> (sh - 32u)) & 0x1fffu;
+        if (lane >= 4) { p0 &= ~0x40u; p1 &= ~0x40u; }                        // before the move the centre was empty
     }
     uint32_t nx = T.root_off, lp = list_addr;
     if (lane < 8) {
@@ -822,15 +822,8 @@ __device__ __forceinline__ uint32_t guided_window_scan(const uint32_t* board, ui
         }
     }
     __syncwarp();
-    return lp;
-}
-
-// ... and its emissions applied: only those that cover the stone count (HasCovered, Pattern.cpp:22-25); by theorem T4 they
-// are the whole line's, by T5 nothing else changes.  A balanced scatter (ac_eval_kernel's phase 3; the owner lane names
-// direction and sign).  Returns winner bits.
-__device__ __forceinline__ uint32_t guided_window_scatter(WarpSmem& ws, const uint16_t* lists, uint32_t list_addr, uint32_t lp,
-                                                          const GuidedTables& T, int cell, int lane) {
     uint32_t win = 0;
+    // balanced scatter of the handful of emissions (ac_eval_kernel's phase 3; the owner lane names direction and sign)
     uint32_t incl = (lp - list_addr) >> 1;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -964,8 +957,7 @@ guided_kernel(EvalArgs a) {
             guided_density_add(dacc, s_lut, lane, mx, my, to_move);
             ++played;
             __syncwarp();
-            const uint32_t lp = guided_window_scan(ws.board, list_addr, T, to_move ? 1u : 2u, wc, lane);
-            win = guided_window_scatter(ws, lists, list_addr, lp, T, cell, lane);
+            win = guided_move_patterns(ws, lists, list_addr, T, cell, wc, lane);
             {   // ... and added again from the new counts and the new board
                 const int cn = compound_candidates_window(ws, lists, wc, false, lane, lt);
                 compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, 600);
@@ -986,9 +978,7 @@ guided_kernel(EvalArgs a) {
 // does (B) at the same time, then both halves of the per-cell work of the heads (each warp takes four of a lane's eight
 // cells), warp A picks the move.  Every float is produced by the operations of policy_heads_inc() and SUMMED IN ITS ORDER
 // (the a2 sum is taken from the stored per-cell values in cell order), so the games are those of guided_kernel, bit for bit.
-// After the move is chosen warp B also takes the old compounds back while warp A scans the windows (both only read the old
-// counts and the old board; integer adds commute).  Six named barriers per move (bar.sync id, 64); the loop is the same for
-// both warps, so they cannot miss each other.
+// Four named barriers per move (bar.sync id, 64); the loop is the same for both warps, so they cannot miss each other.
 constexpr int kPairMax = 15;                                       // pairs per CTA: barrier ids 1..15
 constexpr int kWnWords = 2 * kCells + 2;                           // normalised density weights, float [2][225] (16-byte multiple)
 struct PairMail { int cell; uint32_t won; int pad0, pad1; };
@@ -1143,23 +1133,18 @@ guided_pair_kernel(EvalArgs a) {
             const int my = cell / kWidth, mx = cell - my * kWidth;
             if (lane == (p ? 15 : 0) + my) mine |= 1u << mx;
             if (lane == (cell & 31)) occ8 |= 1u << (cell >> 5);
-            int wc[2];
-            window_slots(cell, lane, wc);
-            uint32_t lp = list_addr;
-            if (role == 0) {                                                 // the windows are scanned (board and counts are only read) ...
-                lp = guided_window_scan(ws.board, list_addr, T, p ? 1u : 2u, wc, lane);
-                if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
-            } else {                                                         // ... while the compounds this move can change are taken back
-                unsigned short* clist = reinterpret_cast<unsigned short*>(wn);   // (the weights' block is free until they are recomputed)
-                const int cn = compound_candidates_window(ws, clist, wc, true, lane, lt);
-                compounds_apply(ws, clist, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, -600);
-            }
-            pair_sync(bar);                                                  // (6) the old counts and the old board have been read
             if (role == 0) {
+                int wc[2];
+                window_slots(cell, lane, wc);
+                {   // the compounds this move can change are taken back while the lines still are as they were
+                    const int cn = compound_candidates_window(ws, lists, wc, true, lane, lt);
+                    compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, -600);
+                }
+                if (a.g_moves && lane == 0) a.g_moves[b * a.g_max_moves + played] = (int16_t)cell;
                 if (lane == (cell >> 4)) { bw |= (p ? 1u : 2u) << ((cell & 15) * 2); ws.board[lane] = bw; }
                 __syncwarp();
-                win = guided_window_scatter(ws, lists, list_addr, lp, T, cell, lane);
-                {   // the compounds, added again from the new counts and the new board
+                win = guided_move_patterns(ws, lists, list_addr, T, cell, wc, lane);
+                {   // ... and added again from the new counts and the new board
                     const int cn = compound_candidates_window(ws, lists, wc, false, lane, lt);
                     compounds_apply(ws, lists, cn, lane, T.next_addr, T.root_off, T.emit_thr, s_erec, s_patrec, 600);
                 }
