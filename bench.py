@@ -530,11 +530,21 @@ def run_gpu_arm(args, rank, world, local_rank):
     sp_moves = float(sp["r"]["length"].float().sum().item())
     sp_full_ms, _ = timed(lambda: gk.guided_rollout_batch(d_empty, mode="sample", key=gk.SYNTH_KEY, game_base=rank * n_games,
                                                           want_moves=True, full_rescan=True), 3, 1)
+    # the same concurrency as a STREAM of games (self-play data generation runs continuously): 8 batches' worth of games queued,
+    # at most n_games in flight per GPU -- a batch lasts as long as its longest game, a stream runs at the rate of the mean
+    d_queue = torch.zeros((8 * n_games, 16), dtype=torch.int32, device=dev)
+    sp_stream_ms, _ = timed(lambda: gk.guided_rollout_batch(d_queue, mode="sample", key=gk.SYNTH_KEY, game_base=rank * 8 * n_games,
+                                                            want_moves=True, max_in_flight=n_games), 3, 1)
+    del d_queue
     extras["selfplay"] = {"metric": "pattern-guided self-play games/sec (configs[4]: 8192 concurrent games in total, sampled moves)",
                           "games_per_gpu": n_games, "scaling": "strong",
                           "value": world * n_games / (sp_ms * 1e-3), "unit": "games/s", "ms_per_step": sp_ms,
                           "evaluated_moves_per_sec": world * sp_moves / (sp_ms * 1e-3), "mean_game_length": sp_moves / n_games,
-                          "kernel": "guided_kernel: per move only the four lines through the new stone are re-scanned (before / after)",
+                          "kernel": "guided_pair_kernel (two warps per game) up to 15 games per SM in flight, guided_kernel above: per move only the "
+                                    "four 13-symbol windows around the new stone are re-scanned (before / after)",
+                          "stream": {"value": world * 8 * n_games / (sp_stream_ms * 1e-3), "unit": "games/s", "games_per_gpu": 8 * n_games,
+                                     "in_flight_per_gpu": n_games, "ms_per_step": sp_stream_ms,
+                                     "what": "gk_guided_rollout_queue: the same number of games in flight, worked through as a queue"},
                           "full_rescan": {"value": world * n_games / (sp_full_ms * 1e-3), "unit": "games/s", "ms_per_step": sp_full_ms,
                                           "kernel": "ac_eval_kernel<true, true>: the whole board after every move (identical games)"}}
     n_enc = 1 << 18
