@@ -20,4 +20,5 @@ ncu -i $rep.ncu-rep --page raw --csv > $out/prof_${tag}_raw.csv 2>/dev/null
 ncu -i $rep.ncu-rep --page source --csv --kernel-name regex:ac_eval_kernel --launch-count 1 > $out/src_eval_$tag.csv 2>/dev/null
 ncu -i $rep.ncu-rep --page source --csv --kernel-name regex:rollout_kernel --launch-count 1 > $out/src_roll_$tag.csv 2>/dev/null
 ncu -i $rep.ncu-rep --page source --csv --kernel-name regex:guided_kernel --launch-count 1 > $out/src_guided_$tag.csv 2>/dev/null
+ncu -i $rep.ncu-rep --page source --csv --kernel-name regex:guided_pair_kernel --launch-count 1 > $out/src_guided_pair_$tag.csv 2>/dev/null
 ls -la $rep.ncu-rep $out/*_$tag*

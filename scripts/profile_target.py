@@ -20,7 +20,8 @@ if os.environ.get("GK_PROFILE_ALL"):
     m = min(n, 1 << 18)
     pol = gk.eval_policy_batch(bt[:m])
     hyb = gk.hybrid_simulate_batch(bt[:m])
-    g = gk.guided_rollout_batch(torch.zeros((8192, 16), dtype=torch.int32, device="cuda"), mode="sample")
+    g = gk.guided_rollout_batch(torch.zeros((8192, 16), dtype=torch.int32, device="cuda"), mode="sample")     # guided_kernel
+    g2 = gk.guided_rollout_batch(torch.zeros((1024, 16), dtype=torch.int32, device="cuda"), mode="sample")    # guided_pair_kernel
     last = torch.full((m, 2), -1, dtype=torch.int16, device="cuda")
     enc = gk.encode_states_batch(bt[:m], last, augment=True)
     if not once:
