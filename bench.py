@@ -379,7 +379,7 @@ def gpu_root_parallel(gk, torch, dist, dev, rank, world, barrier, moves=4):
                         "worker_wait_for_gpu_frac": statistics.mean(r["worker_wait_for_gpu_s"] for r in rows) / max(search_s, 1e-9),
                         "note": "the tree stays on the host (north_star): a move costs trees_per_gpu x playouts_per_tree host playouts / worker "
                                 "threads; the ranks of one box share its cores, so more GPUs add no host throughput"},
-            "gpu_launches_per_move": 2 * per_tree * min(4, max(1, trees // 64)), "moves": rows}
+            "gpu_launches_per_move": per_tree * min(4, max(1, trees // 16)), "moves": rows}
 
 
 def run_gpu_arm(args, rank, world, local_rank):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libgomoku_b200.so")
-SOURCES = ["gk_table.cpp", "gk_eval.cu", "gk_rollout.cu", "gk_encode.cu", "gk_peaks.cu", "gk_capi.cu"]
+SOURCES = ["gk_table.cpp", "gk_eval.cu", "gk_rollout.cu", "gk_rollout_warp.cu", "gk_encode.cu", "gk_peaks.cu", "gk_capi.cu"]
 HEADERS = ["gk_format.h", "gk_table.h", "gk_kernels.h", os.path.join("..", "..", "include", "gomoku_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall"]
@@ -15,7 +15,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # reference's IEEE float (Eigen) arithmetic: correctly rounded division and square root, no flush-to-zero, so that only
 # the summation ORDER differs from the reference (tests/test_heads.py states the tolerance); -fmad=false for the same
 # reason: the reference's x86-64 build rounds the product and the sum of `0.6 a + 0.4 b` separately.
-FAST_MATH = {"gk_rollout.cu", "gk_encode.cu", "gk_peaks.cu", "gk_capi.cu"}
+FAST_MATH = {"gk_rollout.cu", "gk_rollout_warp.cu", "gk_encode.cu", "gk_peaks.cu", "gk_capi.cu"}
 IEEE_FLAGS = ["-fmad=false"]
 
 

@@ -603,6 +603,14 @@ constexpr int kSmallBatch = 1024;
 constexpr int kFusedBatch = 16;         // up to this many positions: one fused launch (one CTA per position)
 uint32_t* g_stage_boards = nullptr;     // page-locked, kSmallBatch x 16 words
 int32_t* g_stage_wdb = nullptr;         // page-locked, kSmallBatch x 3
+
+// One-launch rollouts of a small batch: a warp per rollout while the whole batch is one resident wave of warps (the
+// latency form: a move costs ~1/2 of the thread-per-rollout chain), else a thread per rollout.  Same results either way.
+cudaError_t launch_small(const gk::RolloutArgs& a, int32_t* out, cudaStream_t stream) {
+    static const bool ab_warp = std::getenv("GK_AB_NO_WARP") == nullptr;   // TEMPORARY A/B knob
+    return ab_warp && gk::rollout_warp_fits(a.n, a.rollouts_per_pos, g_sm_count) ? gk::launch_rollout_warp(a, out, stream)
+                                                                       : gk::launch_rollout_small(a, out, stream);
+}
 }  // namespace
 
 gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_per_pos, uint64_t philox_key,
@@ -624,7 +632,7 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
             gk::RolloutArgs a{};
             a.boards = g_stage_boards; a.n = n; a.rollouts_per_pos = rollouts_per_pos;
             a.key_lo = uint32_t(philox_key); a.key_hi = uint32_t(philox_key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos_base;
-            GK_CUDA(gk::launch_rollout_small(a, g_stage_wdb, p.stream));
+            GK_CUDA(launch_small(a, g_stage_wdb, p.stream));
             GK_CUDA(cudaStreamSynchronize(p.stream));
             std::memcpy(h_wdb, g_stage_wdb, size_t(n) * 12);
             return GK_OK;
@@ -669,7 +677,7 @@ gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t 
     a.moves = g_stage_trace;
     a.lengths = g_stage_trace + size_t(256) * GK_CELLS;
     a.winners = reinterpret_cast<int8_t*>(g_stage_trace + size_t(256) * (GK_CELLS + 1));
-    GK_CUDA(gk::launch_rollout_small(a, nullptr, p.stream));
+    GK_CUDA(launch_small(a, nullptr, p.stream));
     GK_CUDA(cudaStreamSynchronize(p.stream));
     std::memcpy(h_lengths, a.lengths, size_t(rollouts));
     std::memcpy(h_winners, a.winners, size_t(rollouts));
@@ -685,8 +693,20 @@ struct AsyncSlot {
     std::mutex mutex;
     cudaStream_t stream = nullptr;
     uint32_t* d_boards = nullptr; int32_t* d_wdb = nullptr; int cap = 0;
+    // the caller's page-locked buffers of the last call and their device addresses (a search passes the same two every time)
+    const void* seen_boards = nullptr; const uint32_t* dev_boards = nullptr;
+    const void* seen_wdb = nullptr; int32_t* dev_wdb = nullptr;
 };
 AsyncSlot g_async[kAsyncSlots];
+
+// device address of a page-locked, mapped host range containing `p`, or null for pageable memory
+void* mapped_address(const void* p) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        return attr.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+}
 }  // namespace
 
 gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int rollouts_per_pos, uint64_t philox_key,
@@ -709,28 +729,20 @@ gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int 
     }
     // page-locked boards (gk_host_alloc) are read by the kernel where they lie (unified addressing): one copy less
     // on a path whose cost is launch latency; pageable boards are staged through the slot's device buffer
-    const uint32_t* boards = a.d_boards;
-    cudaPointerAttributes attr{};
-    bool boards_mapped = false;
-    if (cudaPointerGetAttributes(&attr, h_boards) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
-        boards = static_cast<const uint32_t*>(attr.devicePointer);
-        boards_mapped = true;
-    } else {
-        cudaGetLastError();
-    }
+    if (a.seen_boards != h_boards) { a.dev_boards = static_cast<const uint32_t*>(mapped_address(h_boards)); a.seen_boards = h_boards; }
+    if (a.seen_wdb != h_wdb) { a.dev_wdb = static_cast<int32_t*>(mapped_address(h_wdb)); a.seen_wdb = h_wdb; }
+    const bool boards_mapped = a.dev_boards != nullptr;
+    const uint32_t* boards = boards_mapped ? a.dev_boards : a.d_boards;
     // A leaf batch of a tree search is a few hundred positions x a handful of playouts: pure latency.  With both buffers
     // page-locked the whole round trip is ONE launch -- one CTA per position builds the slot image, plays the playouts and
     // writes the three counts straight into the caller's memory -- instead of image kernel + rollout kernel + copy-out.
-    cudaPointerAttributes wattr{};
-    if (boards_mapped && n <= kFusedAsyncMax && rollouts_per_pos <= 256 &&
-        cudaPointerGetAttributes(&wattr, h_wdb) == cudaSuccess && wattr.type == cudaMemoryTypeHost && wattr.devicePointer) {
+    if (boards_mapped && a.dev_wdb && n <= kFusedAsyncMax && rollouts_per_pos <= 256) {
         gk::RolloutArgs ra{};
         ra.boards = boards; ra.n = n; ra.rollouts_per_pos = rollouts_per_pos;
         ra.key_lo = uint32_t(philox_key); ra.key_hi = uint32_t(philox_key >> 32); ra.ctr_hi = ctr_hi; ra.pos_base = pos_base;
-        GK_CUDA(gk::launch_rollout_small(ra, static_cast<int32_t*>(wattr.devicePointer), a.stream));
+        GK_CUDA(launch_small(ra, a.dev_wdb, a.stream));
         return GK_OK;
     }
-    cudaGetLastError();
     if (!boards_mapped) GK_CUDA(cudaMemcpyAsync(a.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, a.stream));
     if (gk_status s = rollout_common(boards, n, rollouts_per_pos, philox_key, ctr_hi, pos_base, nullptr, 0, a.d_wdb, nullptr,
                                      nullptr, a.stream))
@@ -745,7 +757,8 @@ gk_status gk_rollout_wait(int slot) {
     AsyncSlot& a = g_async[slot];
     cudaStream_t stream;
     { std::lock_guard<std::mutex> lock(a.mutex); stream = a.stream; }
-    if (stream) GK_CUDA(cudaStreamSynchronize(stream));
+    if (!stream) return GK_OK;
+    GK_CUDA(cudaStreamSynchronize(stream));
     return GK_OK;
 }
 
@@ -848,7 +861,13 @@ gk_status gk_host_alloc(void** out, size_t bytes) {
 }
 
 gk_status gk_host_free(void* ptr) {
-    if (ptr) GK_CUDA(cudaFreeHost(ptr));
+    if (ptr) {
+        for (AsyncSlot& a : g_async) {                  // the slots remember device addresses of page-locked ranges
+            std::lock_guard<std::mutex> lock(a.mutex);
+            a.seen_boards = a.seen_wdb = nullptr; a.dev_boards = nullptr; a.dev_wdb = nullptr;
+        }
+        GK_CUDA(cudaFreeHost(ptr));
+    }
     return GK_OK;
 }
 
@@ -941,6 +960,7 @@ static void release_late_resources() {
         if (a.stream) { cudaStreamSynchronize(a.stream); cudaStreamDestroy(a.stream); }
         cudaFree(a.d_boards); cudaFree(a.d_wdb);
         a.stream = nullptr; a.d_boards = nullptr; a.d_wdb = nullptr; a.cap = 0;
+        a.seen_boards = a.seen_wdb = nullptr; a.dev_boards = nullptr; a.dev_wdb = nullptr;
     }
     cudaFreeHost(g_stage_boards); cudaFreeHost(g_stage_wdb); cudaFreeHost(g_policy_stage); cudaFreeHost(g_stage_trace);
     g_stage_boards = nullptr; g_stage_wdb = nullptr; g_policy_stage = nullptr; g_stage_trace = nullptr;

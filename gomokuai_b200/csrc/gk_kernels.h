@@ -51,6 +51,10 @@ cudaError_t launch_rollout(const RolloutArgs& a, int sm_count, uint32_t* images,
 // a handful of positions with at most 256 rollouts each in ONE launch: a.boards, `out` (int32[n][3], may be null) and
 // a.winners / a.lengths / a.moves may be page-locked host memory; same streams and counts as launch_rollout
 cudaError_t launch_rollout_small(const RolloutArgs& a, int32_t* out, cudaStream_t stream);
+// The latency form (gk_rollout_warp.cu): one WARP per rollout, line slots in registers, a.rollouts_per_pos <= 32.  Same
+// arguments and results as launch_rollout_small; rollout_warp_fits says whether the batch is one resident wave of it.
+bool rollout_warp_fits(int n, int rollouts_per_pos, int sm_count);
+cudaError_t launch_rollout_warp(const RolloutArgs& a, int32_t* out, cudaStream_t stream);
 // number of kernels one launch_rollout call enqueues (slot images + wdb clear, rollouts)
 int rollout_launches(const RolloutArgs& a);
 

@@ -135,7 +135,8 @@ private:
     bool stop_ = false;
 };
 
-constexpr int kMaxGroups = 4;       // leaf batches in flight (gk_rollout_submit_host slots 0..3)
+constexpr int kMaxGroups = 8;       // leaf batches in flight at most (gk_rollout_submit_host slots 0..7)
+constexpr int kAutoGroups = 4;      // ... and when the caller leaves the choice open
 
 }  // namespace
 
@@ -150,7 +151,7 @@ struct RootParallelSearch::Impl {
 RootParallelSearch::RootParallelSearch(const RootParallelConfig& cfg) : m(new Impl), m_cfg(cfg) {
     if (cfg.trees <= 0 || cfg.c_rollouts <= 0) throw std::invalid_argument("trees and c_rollouts must be positive");
     int threads = cfg.threads > 0 ? cfg.threads : static_cast<int>(std::thread::hardware_concurrency());
-    threads = std::max(2, std::min(threads, cfg.trees + 1));         // the calling thread drives the GPU, the others own trees
+    threads = std::max(1, std::min(threads, cfg.trees));             // every thread owns trees; none is set aside to drive the GPU
     m->team.reset(new Team(threads));
     m->trees.resize(cfg.trees);
 }
@@ -402,97 +403,107 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     const std::size_t root_depth = root.m_moveRecord.size();
 
     // The trees are cut into G groups whose leaf batches are in flight at the same time: while the GPU simulates the
-    // leaves of one group, the workers back up and descend the trees of the others.  "Visit" v handles round v / G of
-    // group v % G: back up the group's previous batch, select the next leaves.  The calling thread is the DRIVER: it
-    // waits for batches (publishing `ready`) and submits a visit's leaves once all of them are packed (`done`), so CUDA
-    // call latency stays off the workers' critical path; while it waits for the workers it takes chunks itself.  A tree's Philox
-    // stream is (round, global tree index), whatever G and the thread count are.
+    // leaves of one group, the threads back up and descend the trees of the others.  "Visit" v handles round v / G of
+    // group v % G: back up the group's previous batch, select the next leaves.  There is no driver thread: every thread
+    // walks the visits in order and takes trees in chunks; whoever finishes a group's LAST tree submits its batch
+    // (one launch, a few microseconds, while the others are already at the next visit), and whoever first needs a
+    // batch that is in flight waits for it on behalf of all.  A tree's Philox stream is (round, global tree index),
+    // whatever G and the thread count are.
     // (a group needs few trees to be worth a launch since a leaf batch is ONE fused launch: with 128 trees per rank -- the
     // benchmark's 1 024 trees over 8 GPUs -- four groups of 32 keep four round trips in flight instead of two)
-    const int groups = std::max(1, std::min(kMaxGroups, n_trees / 16));
+    const int groups = m_cfg.groups > 0 ? std::min({ m_cfg.groups, kMaxGroups, n_trees })
+                                        : std::max(1, std::min(kAutoGroups, n_trees / 16));
     std::array<int, kMaxGroups + 1> gs{};
     for (int g = 0; g <= groups; ++g) gs[g] = static_cast<int>(static_cast<long long>(n_trees) * g / groups);
     const long long visits_total = static_cast<long long>(playouts_per_tree + 1) * groups;
-    // Trees are handed out in chunks from a per-group counter, so a worker that loses its core for a time slice
-    // delays one chunk, not the whole group.  Both counters only grow: round r of a group owns the chunk numbers
-    // [r * chunks, (r + 1) * chunks), so a worker that arrives late can never claim work of a finished round.
+    // Trees are handed out in chunks from a per-group counter, so a thread that loses its core for a time slice
+    // delays one chunk, not the whole group.  All counters only grow: round r of a group owns the chunk numbers
+    // [r * chunks, (r + 1) * chunks), so a thread that arrives late can never claim work of a finished round.
     constexpr int kChunk = 8;
-    std::atomic<long long> ready{ -1 };          // results of every visit <= ready have arrived
-    std::array<std::atomic<long long>, kMaxGroups> claimed{}, done{};   // chunks handed out / trees finished, per group, over all rounds
-    for (int g = 0; g < kMaxGroups; ++g) { claimed[g].store(0); done[g].store(0); }
+    struct alignas(64) GroupState {
+        std::atomic<long long> claimed{ 0 }, done{ 0 };   // chunks handed out / trees finished, over all rounds
+        std::atomic<int> submitted{ 0 }, arrived{ 0 };    // batches launched / batches whose results are in m->wdb
+        std::atomic_flag waiting = ATOMIC_FLAG_INIT;      // someone is inside gk_rollout_wait for this group
+    };
+    std::array<GroupState, kMaxGroups> gst;
     std::atomic<bool> failed{ false };
+    std::mutex error_mutex;
     std::string error;
-    double idle = 0;                             // worker 1's time waiting for results
-    double t_sync = 0, t_workers = 0, t_submit = 0;   // the driver's time in gk_rollout_wait / waiting for the workers / in gk_rollout_submit_host
+    auto fail = [&](const char* what) {
+        std::lock_guard<std::mutex> lock(error_mutex);
+        if (error.empty()) error = std::string(what) + ": " + gk_last_error();
+        failed.store(true);
+    };
+    const int n_threads = m->team->size();
+    std::vector<std::array<double, 8>> clock(n_threads);   // per thread (padded): seconds waiting for results / inside gk_rollout_wait / inside gk_rollout_submit_host
+    for (auto& c : clock) c.fill(0.0);
+    auto seconds_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
 
-    // take chunks of visit v (whose results have arrived) until none is left: back up, select, pack
-    auto process = [&](long long v) {
+    // take chunks of visit v (whose results have arrived) until none is left: back up, select, pack; the thread that
+    // finishes the group's last tree sends the leaves off
+    auto process = [&](long long v, int id) {
         const int g = static_cast<int>(v % groups), round = static_cast<int>(v / groups);
+        GroupState& G = gst[g];
         const int count = gs[g + 1] - gs[g], chunks = (count + kChunk - 1) / kChunk;
         const long long first = static_cast<long long>(round) * chunks, last = first + chunks;
         for (;;) {
-            long long c = claimed[g].load(std::memory_order_relaxed);
+            long long c = G.claimed.load(std::memory_order_relaxed);
             if (c >= last) break;
-            if (!claimed[g].compare_exchange_weak(c, c + 1, std::memory_order_acq_rel)) continue;
+            if (!G.claimed.compare_exchange_weak(c, c + 1, std::memory_order_acq_rel)) continue;
             const int lo = gs[g] + static_cast<int>(c - first) * kChunk, hi = std::min(lo + kChunk, gs[g + 1]);
             for (int i = lo; i < hi; ++i) {
                 Tree& t = m->trees[i];
                 if (round > 0) backup(t, &m->wdb[static_cast<std::size_t>(i) * 3], m_cfg, root_depth);
                 if (round < playouts_per_tree) select_leaf(t, c_puct, &m->packed[static_cast<std::size_t>(i) * 16]);
             }
-            done[g].fetch_add(hi - lo, std::memory_order_acq_rel);
-        }
-    };
-    constexpr bool driver_helps = true;                              // measured: +29 % at 4 threads, +2 % at 16
-    auto driver = [&]() {
-        auto arrive = [&](long long v) {                             // results of visit v's previous batch
-            if (v >= visits_total || v / groups == 0 || failed.load()) return;
-            const auto t0 = std::chrono::steady_clock::now();
-            if (gk_rollout_wait(static_cast<int>(v % groups)) != GK_OK) { error = std::string("gk_rollout_wait: ") + gk_last_error(); failed.store(true); }
-            ready.store(v, std::memory_order_release);
-            t_sync += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        };
-        auto submit = [&](long long u) {                             // leaves selected at visit u
-            if (u < 0 || u / groups >= playouts_per_tree || failed.load()) return;
-            const auto t0 = std::chrono::steady_clock::now();
-            Backoff wait;
-            const int g = static_cast<int>(u % groups), lo = gs[g], hi = gs[g + 1];
-            const long long want = (u / groups + 1) * static_cast<long long>(hi - lo);
-            if (driver_helps) process(u);                            // lend a hand: matters when a rank has few host threads
-            while (done[g].load(std::memory_order_acquire) != want && !failed.load(std::memory_order_relaxed)) wait();
-            const auto t1 = std::chrono::steady_clock::now();
-            t_workers += std::chrono::duration<double>(t1 - t0).count();
-            if (!failed.load() &&
-                gk_rollout_submit_host(g, m->packed + static_cast<std::size_t>(lo) * 16, hi - lo, m_cfg.c_rollouts, m_cfg.seed,
-                                       static_cast<std::uint32_t>(u / groups), m_cfg.replica_base + lo,
-                                       m->wdb + static_cast<std::size_t>(lo) * 3) != GK_OK) {
-                error = std::string("gk_rollout_submit_host: ") + gk_last_error();
-                failed.store(true);
+            const long long finished = G.done.fetch_add(hi - lo, std::memory_order_acq_rel) + (hi - lo);
+            if (finished == static_cast<long long>(round + 1) * count && round < playouts_per_tree) {
+                const auto t0 = std::chrono::steady_clock::now();
+                if (gk_rollout_submit_host(g, m->packed + static_cast<std::size_t>(gs[g]) * 16, count, m_cfg.c_rollouts, m_cfg.seed,
+                                           static_cast<std::uint32_t>(round), m_cfg.replica_base + gs[g],
+                                           m->wdb + static_cast<std::size_t>(gs[g]) * 3) != GK_OK)
+                    fail("gk_rollout_submit_host");
+                G.submitted.store(round + 1, std::memory_order_release);
+                clock[id][2] += seconds_since(t0);
             }
-            t_submit += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-        };
-        for (long long v = 0; v <= visits_total; ++v) {
-            // with two or more groups the batch visit v waits for was submitted at least one iteration ago, so its
-            // arrival is published BEFORE the (slower) submit of visit v - 1
-            if (groups >= 2) { arrive(v); submit(v - 1); } else { submit(v - 1); arrive(v); }
         }
     };
-    auto worker = [&](int w) {                                       // w in [0, workers)
+    auto worker = [&](int id) {
         for (long long v = 0; v < visits_total && !failed.load(std::memory_order_relaxed); ++v) {
-            if (v / groups > 0 && ready.load(std::memory_order_acquire) < v) {
+            const int g = static_cast<int>(v % groups), round = static_cast<int>(v / groups);
+            GroupState& G = gst[g];
+            if (round > 0 && G.arrived.load(std::memory_order_acquire) < round) {      // the batch of round - 1 is still out
                 const auto t0 = std::chrono::steady_clock::now();
                 Backoff wait;
-                while (ready.load(std::memory_order_acquire) < v && !failed.load(std::memory_order_relaxed)) wait();
-                if (w == 0) idle += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                while (G.arrived.load(std::memory_order_acquire) < round && !failed.load(std::memory_order_relaxed)) {
+                    if (G.submitted.load(std::memory_order_acquire) >= round && !G.waiting.test_and_set(std::memory_order_acquire)) {
+                        if (G.arrived.load(std::memory_order_acquire) < round) {
+                            const auto t1 = std::chrono::steady_clock::now();
+                            if (gk_rollout_wait(g) != GK_OK) fail("gk_rollout_wait");
+                            G.arrived.store(round, std::memory_order_release);
+                            clock[id][1] += seconds_since(t1);
+                        }
+                        G.waiting.clear(std::memory_order_release);
+                    } else {
+                        wait();
+                    }
+                }
+                clock[id][0] += seconds_since(t0);
             }
-            process(v);
+            process(v, id);
         }
     };
-    m->team->run([&](int id) { if (id == 0) driver(); else worker(id - 1); });
+    m->team->run([&](int id) { worker(id); });
     if (failed.load()) {
         for (int g = 0; g < groups; ++g) gk_rollout_wait(g);
         throw std::runtime_error(error);
     }
+    double idle = 0, t_sync = 0, t_submit = 0;
+    for (const auto& c : clock) { idle += c[0]; t_sync += c[1]; t_submit += c[2]; }
+    idle /= n_threads;                           // mean over the threads: time spent waiting for results
+    const double t_workers = 0;
     seconds_gpu = idle;
     driver_seconds = { t_sync, t_workers, t_submit };
     leaves = static_cast<std::int64_t>(n_trees) * playouts_per_tree;

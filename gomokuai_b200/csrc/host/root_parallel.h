@@ -21,11 +21,12 @@ struct RootParallelConfig {
     double c_puct = 5.0;
     std::uint64_t seed = 1;     // Philox key
     int replica_base = 0;       // first global tree index of this rank (keeps streams disjoint across ranks)
-    int threads = 0;            // host threads: one drives the GPU, the rest do tree work (0 = hardware concurrency; at least 2)
+    int threads = 0;            // host threads, all doing tree work; whoever finishes a group's last tree launches its batch (0 = hardware concurrency)
     // Dirichlet noise on the priors of the root's fresh children.  An EXTENSION, off by default: the reference's
     // Default::AddNoise runs before the playouts and only touches children that already exist (MonteCarlo.hpp:97-108,
     // MCTS.cpp:182), so a search from a fresh tree -- which is what every root-parallel move is -- draws none.
     bool noise = false;
+    int groups = 0;             // leaf batches in flight, 1..8 (0 = chosen from the tree count); never changes a result
     bool eager = false;         // materialise every child at expansion like the reference (slow; kept to test the lazy tree against)
 };
 
@@ -48,8 +49,8 @@ public:
     std::vector<DumpNode> dumpTree(int tree) const;
     static Position bestMove(const Stats& stats);             // most visited root child, ties -> lowest cell (MCTS.cpp:129-134)
 
-    double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / of it, time the first worker waited for GPU results
-    std::array<double, 3> driver_seconds{};                   // the GPU driver thread: in gk_rollout_wait, waiting for the workers, in gk_rollout_submit_host
+    double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / of it, the time a thread waited for GPU results (mean over threads)
+    std::array<double, 3> driver_seconds{};                   // summed over threads: inside gk_rollout_wait, (unused, 0), inside gk_rollout_submit_host
     std::int64_t leaves = 0, nodes = 0;
 
 private:
