@@ -323,7 +323,7 @@ def gpu_root_parallel(gk, torch, dist, dev, rank, world, barrier, moves=4):
     share = cores[rank * len(cores) // world:(rank + 1) * len(cores) // world] or cores
     if world > 1 and hasattr(os, "sched_setaffinity"):
         os.sched_setaffinity(0, share)                                   # the ranks' worker threads get disjoint cores
-    threads = max(2, len(share))
+    threads = max(1, len(share))
     s = core.RootParallelSearch(trees=trees, c_rollouts=5, seed=1, replica_base=rank * trees, threads=threads)
     if world > 1:
         rp._ensure_gk_comm()
@@ -375,11 +375,12 @@ def gpu_root_parallel(gk, torch, dist, dev, rank, world, barrier, moves=4):
             "exchange": "5.4 KB H2D + gk_root_allreduce (ncclAllReduce int64[675], sum) + 5.4 KB D2H, inside the timed region" if world > 1
                         else "5.4 KB H2D + D2H (one rank: no collective)",
             "merged_equals_single_rank_search": equal,
-            "limiter": {"host_us_per_playout_per_worker_thread": search_s * (threads - 1) / (trees * per_tree) * 1e6,
+            "limiter": {"host_us_per_playout_per_thread": search_s * threads / (trees * per_tree) * 1e6,
                         "worker_wait_for_gpu_frac": statistics.mean(r["worker_wait_for_gpu_s"] for r in rows) / max(search_s, 1e-9),
-                        "note": "the tree stays on the host (north_star): a move costs trees_per_gpu x playouts_per_tree host playouts / worker "
-                                "threads; the ranks of one box share its cores, so more GPUs add no host throughput"},
-            "gpu_launches_per_move": per_tree * min(4, max(1, trees // 16)), "moves": rows}
+                        "note": "the tree stays on the host (north_star): a move costs trees_per_gpu x playouts_per_tree host playouts / "
+                                "threads (every thread does tree work; whoever finishes a group's last tree launches its leaf batch); the ranks "
+                                "of one box share its cores, so more GPUs add no host throughput"},
+            "gpu_launches_per_move": per_tree * max(1, min(4 if trees >= 4096 else 6, trees // 16)), "moves": rows}
 
 
 def run_gpu_arm(args, rank, world, local_rank):

@@ -607,8 +607,7 @@ int32_t* g_stage_wdb = nullptr;         // page-locked, kSmallBatch x 3
 // One-launch rollouts of a small batch: a warp per rollout while the whole batch is one resident wave of warps (the
 // latency form: a move costs ~1/2 of the thread-per-rollout chain), else a thread per rollout.  Same results either way.
 cudaError_t launch_small(const gk::RolloutArgs& a, int32_t* out, cudaStream_t stream) {
-    static const bool ab_warp = std::getenv("GK_AB_NO_WARP") == nullptr;   // TEMPORARY A/B knob
-    return ab_warp && gk::rollout_warp_fits(a.n, a.rollouts_per_pos, g_sm_count) ? gk::launch_rollout_warp(a, out, stream)
+    return gk::rollout_warp_fits(a.n, a.rollouts_per_pos, g_sm_count) ? gk::launch_rollout_warp(a, out, stream)
                                                                        : gk::launch_rollout_small(a, out, stream);
 }
 }  // namespace

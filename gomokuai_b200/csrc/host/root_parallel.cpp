@@ -136,7 +136,8 @@ private:
 };
 
 constexpr int kMaxGroups = 8;       // leaf batches in flight at most (gk_rollout_submit_host slots 0..7)
-constexpr int kAutoGroups = 4;      // ... and when the caller leaves the choice open
+constexpr int kAutoGroups = 6;      // ... and when the caller leaves the choice open (measured: scripts/ab_root_parallel.py,
+                                    // profiles/r03c_root_parallel_groups.json; 4 from 4 096 trees on, where the batches are large)
 
 }  // namespace
 
@@ -412,14 +413,19 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     // (a group needs few trees to be worth a launch since a leaf batch is ONE fused launch: with 128 trees per rank -- the
     // benchmark's 1 024 trees over 8 GPUs -- four groups of 32 keep four round trips in flight instead of two)
     const int groups = m_cfg.groups > 0 ? std::min({ m_cfg.groups, kMaxGroups, n_trees })
-                                        : std::max(1, std::min(kAutoGroups, n_trees / 16));
+                                        : std::max(1, std::min(n_trees >= 4096 ? 4 : kAutoGroups, n_trees / 16));
     std::array<int, kMaxGroups + 1> gs{};
     for (int g = 0; g <= groups; ++g) gs[g] = static_cast<int>(static_cast<long long>(n_trees) * g / groups);
     const long long visits_total = static_cast<long long>(playouts_per_tree + 1) * groups;
     // Trees are handed out in chunks from a per-group counter, so a thread that loses its core for a time slice
     // delays one chunk, not the whole group.  All counters only grow: round r of a group owns the chunk numbers
     // [r * chunks, (r + 1) * chunks), so a thread that arrives late can never claim work of a finished round.
-    constexpr int kChunk = 8;
+    // A visit ends when its LAST chunk does, so a small group is cut into one chunk per thread (170 trees over 16 threads
+    // in chunks of 8 would be 16 + 6 chunks: two waves for the work of 1.3); measured, finer chunks than that lose more
+    // to the shared counter than they gain in balance.
+    const int n_threads = m->team->size();
+    const int share = (n_trees / groups + n_threads - 1) / n_threads;
+    const int kChunk = share <= 16 ? std::max(1, share) : 8;
     struct alignas(64) GroupState {
         std::atomic<long long> claimed{ 0 }, done{ 0 };   // chunks handed out / trees finished, over all rounds
         std::atomic<int> submitted{ 0 }, arrived{ 0 };    // batches launched / batches whose results are in m->wdb
@@ -434,7 +440,6 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         if (error.empty()) error = std::string(what) + ": " + gk_last_error();
         failed.store(true);
     };
-    const int n_threads = m->team->size();
     std::vector<std::array<double, 8>> clock(n_threads);   // per thread (padded): seconds waiting for results / inside gk_rollout_wait / inside gk_rollout_submit_host
     for (auto& c : clock) c.fill(0.0);
     auto seconds_since = [](std::chrono::steady_clock::time_point t0) {

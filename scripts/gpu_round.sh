@@ -3,6 +3,8 @@
 #   tests    python -m pytest tests -m gpu  (rebuilds the library on the box first, see tests/conftest.py)
 #   bench    the default bench command, 1 GPU
 #   profile  scripts/profile_round.sh <tag>: ncu launch list + one `--set full` capture with source pages
+#   small    one-leaf rollout launches under ncu (cycles per move of rollout_warp_kernel / rollout_small_kernel) + call latency
+#   groups   root-parallel search against the number of leaf batches in flight
 set -u
 tag=${1:-rXX}; shift
 what=${*:-tests bench profile}
@@ -26,6 +28,13 @@ for w in $what; do
     fuzz)    python tests/tools/fuzz_guided.py > $out/fuzz_guided_$tag.json 2> $out/fuzz_guided_$tag.err; r=$?; cat $out/fuzz_guided_$tag.json; tail -3 $out/fuzz_guided_$tag.err; [ $r -ne 0 ] && rc=$r
              python tests/tools/fuzz_eval.py 100000 > $out/fuzz_eval_$tag.txt 2>&1; r=$?; tail -1 $out/fuzz_eval_$tag.txt; [ $r -ne 0 ] && rc=$r ;;
     sweep)   python scripts/sweep_root_parallel.py > $out/rp_sweep_$tag.json 2> $out/rp_sweep_$tag.err; r=$?; tail -6 $out/rp_sweep_$tag.err | cut -c1-300; [ $r -ne 0 ] && rc=$r ;;
+    small)   python scripts/profile_small_rollout.py > $out/small_plain_$tag.json 2> $out/small_$tag.err && \
+             ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max,smsp__inst_executed.sum --clock-control none --csv --log-file $out/small_launches_$tag.csv python scripts/profile_small_rollout.py > $out/small_lengths_$tag.json 2>> $out/small_$tag.err; \
+             python scripts/small_rollout_summary.py $out/small_launches_$tag.csv $out/small_lengths_$tag.json > $out/small_rollout_$tag.json 2>> $out/small_$tag.err; head -c 900 $out/small_rollout_$tag.json; echo; \
+             ncu --set full --import-source on --clock-control none -k regex:rollout_warp -c 1 -f -o /tmp/small_$tag python scripts/profile_small_rollout.py > /dev/null 2>> $out/small_$tag.err; \
+             ncu -i /tmp/small_$tag.ncu-rep --page source --csv > $out/src_rollout_warp_$tag.csv 2>/dev/null; \
+             python scripts/bench_small_rollout.py > $out/small_latency_$tag.json 2>> $out/small_$tag.err ;;
+    groups)  python scripts/ab_root_parallel.py 8192 1024 512 128 > $out/rp_groups_$tag.json 2> $out/rp_groups_$tag.err; r=$?; tail -2 $out/rp_groups_$tag.err; [ $r -ne 0 ] && rc=$r ;;
     *)       echo "unknown step $w" ;;
   esac
 done

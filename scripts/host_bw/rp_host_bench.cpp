@@ -40,7 +40,7 @@ gk_status gk_rollout_batch_host(const uint32_t* b, int n, int r, uint64_t key, u
     return GK_OK;
 }
 // asynchronous pair: the stub "GPU" finishes g_latency_us after the submit
-struct Slot { std::chrono::steady_clock::time_point ready; } g_slots[4];
+struct Slot { std::chrono::steady_clock::time_point ready; } g_slots[8];
 gk_status gk_rollout_submit_host(int slot, const uint32_t* b, int n, int r, uint64_t key, uint32_t ctr, int base, int32_t* wdb) {
     fake(b, n, r, key, ctr, base, wdb);
     g_slots[slot].ready = std::chrono::steady_clock::now() + std::chrono::microseconds(g_latency_us);
