@@ -606,8 +606,8 @@ int32_t* g_stage_wdb = nullptr;         // page-locked, kSmallBatch x 3
 
 // One-launch rollouts of a small batch: a warp per rollout while the whole batch is one resident wave of warps (the
 // latency form: a move costs ~1/2 of the thread-per-rollout chain), else a thread per rollout.  Same results either way.
-cudaError_t launch_small(const gk::RolloutArgs& a, int32_t* out, cudaStream_t stream) {
-    return gk::rollout_warp_fits(a.n, a.rollouts_per_pos, g_sm_count) ? gk::launch_rollout_warp(a, out, stream)
+cudaError_t launch_small(const gk::RolloutArgs& a, int32_t* out, cudaStream_t stream, const uint32_t* h_boards) {
+    return gk::rollout_warp_fits(a.n, a.rollouts_per_pos, g_sm_count) ? gk::launch_rollout_warp(a, out, stream, h_boards)
                                                                        : gk::launch_rollout_small(a, out, stream);
 }
 }  // namespace
@@ -631,7 +631,7 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
             gk::RolloutArgs a{};
             a.boards = g_stage_boards; a.n = n; a.rollouts_per_pos = rollouts_per_pos;
             a.key_lo = uint32_t(philox_key); a.key_hi = uint32_t(philox_key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos_base;
-            GK_CUDA(launch_small(a, g_stage_wdb, p.stream));
+            GK_CUDA(launch_small(a, g_stage_wdb, p.stream, g_stage_boards));
             GK_CUDA(cudaStreamSynchronize(p.stream));
             std::memcpy(h_wdb, g_stage_wdb, size_t(n) * 12);
             return GK_OK;
@@ -676,7 +676,7 @@ gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t 
     a.moves = g_stage_trace;
     a.lengths = g_stage_trace + size_t(256) * GK_CELLS;
     a.winners = reinterpret_cast<int8_t*>(g_stage_trace + size_t(256) * (GK_CELLS + 1));
-    GK_CUDA(launch_small(a, nullptr, p.stream));
+    GK_CUDA(launch_small(a, nullptr, p.stream, g_stage_boards));
     GK_CUDA(cudaStreamSynchronize(p.stream));
     std::memcpy(h_lengths, a.lengths, size_t(rollouts));
     std::memcpy(h_winners, a.winners, size_t(rollouts));
@@ -686,7 +686,7 @@ gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t 
 
 // ---- asynchronous host entry points: several small batches in flight (root-parallel search) ----------------
 namespace {
-constexpr int kAsyncSlots = 8;
+constexpr int kAsyncSlots = 16;
 constexpr int kFusedAsyncMax = 4096;     // positions per asynchronous batch that still go through the one-launch path
 struct AsyncSlot {
     std::mutex mutex;
@@ -739,7 +739,7 @@ gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int 
         gk::RolloutArgs ra{};
         ra.boards = boards; ra.n = n; ra.rollouts_per_pos = rollouts_per_pos;
         ra.key_lo = uint32_t(philox_key); ra.key_hi = uint32_t(philox_key >> 32); ra.ctr_hi = ctr_hi; ra.pos_base = pos_base;
-        GK_CUDA(launch_small(ra, a.dev_wdb, a.stream));
+        GK_CUDA(launch_small(ra, a.dev_wdb, a.stream, h_boards));
         return GK_OK;
     }
     if (!boards_mapped) GK_CUDA(cudaMemcpyAsync(a.d_boards, h_boards, size_t(n) * 64, cudaMemcpyHostToDevice, a.stream));

@@ -54,7 +54,8 @@ cudaError_t launch_rollout_small(const RolloutArgs& a, int32_t* out, cudaStream_
 // The latency form (gk_rollout_warp.cu): one WARP per rollout, line slots in registers, a.rollouts_per_pos <= 32.  Same
 // arguments and results as launch_rollout_small; rollout_warp_fits says whether the batch is one resident wave of it.
 bool rollout_warp_fits(int n, int rollouts_per_pos, int sm_count);
-cudaError_t launch_rollout_warp(const RolloutArgs& a, int32_t* out, cudaStream_t stream);
+// h_board0: when a.n == 1, a HOST-readable copy of the one board (may be null): it is passed in the kernel parameters.
+cudaError_t launch_rollout_warp(const RolloutArgs& a, int32_t* out, cudaStream_t stream, const uint32_t* h_board0 = nullptr);
 // number of kernels one launch_rollout call enqueues (slot images + wdb clear, rollouts)
 int rollout_launches(const RolloutArgs& a);
 

@@ -73,11 +73,15 @@ __device__ __forceinline__ Line line_of(int slot) {
 
 // kMaxThreads: 256 for up to 8 rollouts per position (the search's 5), 1024 otherwise -- the tighter bound lets ptxas use
 // more registers, i.e. interleave the three slot updates of a move instead of running them one after the other.
+// A single leaf (the single-tree search: one launch per playout) rides in the kernel's parameters, which arrive with the
+// launch: reading it through the pointer would be a round trip over PCIe to the caller's page-locked memory first.
+struct InlineBoard { uint32_t w[kBoardWords]; int valid; };
+
 template <bool kMoves, int kMaxThreads>
-__global__ void __launch_bounds__(kMaxThreads) rollout_warp_kernel(RolloutArgs a, int32_t* __restrict__ out) {
+__global__ void __launch_bounds__(kMaxThreads) rollout_warp_kernel(RolloutArgs a, int32_t* __restrict__ out, const InlineBoard b0) {
     __shared__ uint32_t s_board[kBoardWords], s_cnt[3], s_slot[kLineSlots];
     const int pos = blockIdx.x, tid = threadIdx.x, lane = tid & 31, roll = tid >> 5;
-    if (tid < kBoardWords) s_board[tid] = a.boards[(size_t)pos * kBoardWords + tid];
+    if (tid < kBoardWords) s_board[tid] = b0.valid ? b0.w[tid] : a.boards[(size_t)pos * kBoardWords + tid];
     if (tid < 3) s_cnt[tid] = 0;
     for (int i = tid; i < kLineSlots; i += blockDim.x) s_slot[i] = 0;
     __syncthreads();
@@ -219,17 +223,22 @@ bool rollout_warp_fits(int n, int rollouts_per_pos, int sm_count) {
            (long long)n * rollouts_per_pos <= (long long)sm_count * 10;
 }
 
-cudaError_t launch_rollout_warp(const RolloutArgs& a, int32_t* out, cudaStream_t stream) {
+cudaError_t launch_rollout_warp(const RolloutArgs& a, int32_t* out, cudaStream_t stream, const uint32_t* h_board0) {
     if (a.n <= 0 || a.rollouts_per_pos <= 0) return cudaSuccess;
     if (a.rollouts_per_pos > 32) return cudaErrorInvalidValue;
     const int threads = a.rollouts_per_pos * 32;
+    InlineBoard b0{};
+    if (h_board0 && a.n == 1) {
+        for (int i = 0; i < kBoardWords; ++i) b0.w[i] = h_board0[i];
+        b0.valid = 1;
+    }
     const bool trace = a.moves || a.winners || a.lengths;
     if (threads <= 256) {
-        if (trace) rollout_warp_kernel<true, 256><<<a.n, threads, 0, stream>>>(a, out);
-        else rollout_warp_kernel<false, 256><<<a.n, threads, 0, stream>>>(a, out);
+        if (trace) rollout_warp_kernel<true, 256><<<a.n, threads, 0, stream>>>(a, out, b0);
+        else rollout_warp_kernel<false, 256><<<a.n, threads, 0, stream>>>(a, out, b0);
     } else {
-        if (trace) rollout_warp_kernel<true, 1024><<<a.n, threads, 0, stream>>>(a, out);
-        else rollout_warp_kernel<false, 1024><<<a.n, threads, 0, stream>>>(a, out);
+        if (trace) rollout_warp_kernel<true, 1024><<<a.n, threads, 0, stream>>>(a, out, b0);
+        else rollout_warp_kernel<false, 1024><<<a.n, threads, 0, stream>>>(a, out, b0);
     }
     return cudaGetLastError();
 }

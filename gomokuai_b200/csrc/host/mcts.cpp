@@ -192,12 +192,53 @@ void Default::AddNoise(Node* node, float alpha, float epsilon) {
     for (auto& child : node->children) child->action_prob = prior[child->position];
 }
 
+Probs Policy::simulateBegin(Board&) { throw std::logic_error("this policy has no split simulate"); }
+float Policy::simulateEnd() { throw std::logic_error("this policy has no split simulate"); }
+
 // ---- RandomPolicy (policies/Random.h) --------------------------------------------------------------------
 RandomPolicy::RandomPolicy(double c_puct, std::size_t c_rollouts)
-    : Policy(nullptr, nullptr, [this](Board& board) { return averagedSimulate(board); }, nullptr, c_puct), c_rollouts(c_rollouts) {}
+    : Policy(nullptr, nullptr, [this](Board& board) { return averagedSimulate(board); }, nullptr, c_puct), c_rollouts(c_rollouts) {
+    static std::atomic<int> next_slot{ 0 };
+    m_slot = 8 + next_slot.fetch_add(1) % 8;             // slots 8..15: 0..7 belong to the root-parallel search
+    m_ownSimulate = &simulate.target_type();
+}
+
+RandomPolicy::~RandomPolicy() {
+    if (m_pendingPlayer != Player::None) gk_rollout_wait(m_slot);
+    if (m_pinned) gk_host_free(m_pinned);
+}
 
 Policy::EvalResult RandomPolicy::averagedSimulate(Board& board) {                      // Random.h:22-35; the board is left untouched
     return { Default::GpuRolloutValue(board, static_cast<int>(c_rollouts)), Default::UniformProbs(board) };
+}
+
+// averagedSimulate in two halves: same Philox stream per call as GpuRolloutValue, so the same value; the probabilities
+// are uniform over the empty cells and need no device, which lets the search expand the leaf while the playouts run.
+Probs RandomPolicy::simulateBegin(Board& board) {
+    ensure_gpu();
+    if (m_pendingPlayer != Player::None) { gk_rollout_wait(m_slot); m_pendingPlayer = Player::None; }   // a begin whose end never came
+    if (!m_pinned) {
+        void* p = nullptr;
+        if (gk_host_alloc(&p, 128) != GK_OK) throw std::runtime_error(std::string("gk_host_alloc: ") + gk_last_error());
+        m_pinned = static_cast<std::uint32_t*>(p);
+    }
+    board.pack(m_pinned);
+    const std::uint64_t call = g_rollout_calls.fetch_add(1);
+    if (gk_rollout_submit_host(m_slot, m_pinned, 1, static_cast<int>(c_rollouts), rollout_key(), static_cast<std::uint32_t>(call >> 30),
+                               static_cast<int>(call & 0x3fffffff), reinterpret_cast<std::int32_t*>(m_pinned + 16)) != GK_OK)
+        throw std::runtime_error(std::string("gk_rollout_submit_host: ") + gk_last_error());
+    m_pendingPlayer = board.m_curPlayer;
+    return Default::UniformProbs(board);
+}
+
+float RandomPolicy::simulateEnd() {
+    if (m_pendingPlayer == Player::None) throw std::logic_error("simulateEnd without simulateBegin");
+    const Player player = m_pendingPlayer;
+    m_pendingPlayer = Player::None;
+    if (gk_rollout_wait(m_slot) != GK_OK) throw std::runtime_error(std::string("gk_rollout_wait: ") + gk_last_error());
+    const std::int32_t* wdb = reinterpret_cast<const std::int32_t*>(m_pinned + 16);
+    const float black_value = static_cast<float>(wdb[2] - wdb[0]) / static_cast<float>(c_rollouts);
+    return CalcScore(player, black_value);
 }
 
 // ---- RAVE (MonteCarlo.hpp:112-186) ------------------------------------------------------------------------------
@@ -378,9 +419,15 @@ std::size_t MCTS::playout(Board& board) {                                       
     double node_value;
     std::size_t expand_size;
     if (!m_policy->checkGameEnd(board)) {
-        auto [state_value, action_probs] = m_policy->simulate(board);   // value for the player to move
-        expand_size = m_policy->expand(node, board, action_probs);
-        node_value = -state_value;                                       // the node stores the view of who moved INTO it
+        if (m_policy->splitSimulate()) {                                 // expand while the GPU plays the leaf's rollouts
+            const Probs action_probs = m_policy->simulateBegin(board);
+            expand_size = m_policy->expand(node, board, action_probs);
+            node_value = -m_policy->simulateEnd();
+        } else {
+            auto [state_value, action_probs] = m_policy->simulate(board);   // value for the player to move
+            expand_size = m_policy->expand(node, board, action_probs);
+            node_value = -state_value;                                   // the node stores the view of who moved INTO it
+        }
     } else {
         expand_size = 0;
         node_value = CalcScore(node->player, board.m_winner);

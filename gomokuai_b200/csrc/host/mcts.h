@@ -9,6 +9,7 @@
 #include <functional>
 #include <memory>
 #include <tuple>
+#include <typeinfo>
 #include <vector>
 
 #include "game.h"
@@ -76,8 +77,19 @@ public:
     virtual bool checkGameEnd(Board& board);
     virtual void reset() {}
 
+    // Split form of the policy's OWN simulate, for policies whose move probabilities do not need the device (new; the
+    // reference's simulate is synchronous CPU code): simulateBegin sends the leaf to the GPU and returns the
+    // probabilities, simulateEnd waits for the value, and MCTS::playout expands the leaf in between.  Same numbers as
+    // `simulate`.  Only used while the `simulate` slot still holds what the policy's constructor put there.
+    bool splitSimulate() const { return m_ownSimulate != nullptr && simulate.target_type() == *m_ownSimulate; }
+    virtual Probs simulateBegin(Board& board);
+    virtual float simulateEnd();
+
     double c_puct;
     std::size_t m_initActs = 0;
+
+protected:
+    const std::type_info* m_ownSimulate = nullptr;   // type of the callable the constructor stored in `simulate`, if it has a split form
 };
 
 // The default algorithms (MonteCarlo.hpp:13-110).  Simulate plays its random game on the GPU.
@@ -98,8 +110,16 @@ struct Default {
 class RandomPolicy : public Policy {
 public:
     explicit RandomPolicy(double c_puct = C_PUCT, std::size_t c_rollouts = 5);
+    ~RandomPolicy() override;
     EvalResult averagedSimulate(Board& board);
+    Probs simulateBegin(Board& board) override;      // the c_rollouts playouts of averagedSimulate, in flight on the GPU
+    float simulateEnd() override;
     std::size_t c_rollouts;
+
+private:
+    std::uint32_t* m_pinned = nullptr;               // page-locked: 16 board words + 3 counts
+    Player m_pendingPlayer = Player::None;           // side to move of the leaf in flight (None: nothing in flight)
+    int m_slot = 8;
 };
 
 // RAVE (algorithms/MonteCarlo.hpp:112-186): back-propagation keeps the best-scoring child at index 0 of every node on

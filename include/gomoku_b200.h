@@ -193,7 +193,7 @@ gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t 
                                 int8_t* h_winners, uint8_t* h_lengths, uint8_t* h_moves);
 /* Asynchronous form of gk_rollout_batch_host for callers that keep several small batches in flight (the
  * root-parallel search: while one group of leaves is simulated, the host descends the trees of the next one).
- * `slot` in [0, 8) names an independent stream with its own device buffers.  submit enqueues copy-in, rollouts and
+ * `slot` in [0, 16) names an independent stream with its own device buffers.  submit enqueues copy-in, rollouts and
  * copy-out and returns; h_boards and h_wdb must stay valid and untouched until gk_rollout_wait(slot) has returned.
  * Page-locked buffers (gk_host_alloc) make the call truly asynchronous and let the kernel read the boards in place.
  * One thread at a time per slot. */

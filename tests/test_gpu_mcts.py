@@ -28,6 +28,29 @@ def test_random_policy_mcts_plays_a_legal_move_and_restores_the_board(core):
     assert m.size > 400
 
 
+def test_split_simulate_builds_the_same_tree_as_the_synchronous_slot(core):
+    """MCTS::playout expands the leaf while RandomPolicy's rollouts are in flight (simulateBegin / simulateEnd); a policy
+    whose eval_state slot is a user function takes the synchronous path.  Same seed -> same Philox stream per call ->
+    the same tree."""
+    b = core.Board()
+    for c in (112, 113, 97, 98):
+        b.apply_move(c)
+
+    def search(policy):
+        core.seed(123)
+        m = core.MCTS(c_iterations=600, policy=policy)
+        move = m.get_action(b)
+        kids = sorted((int(ch.position), int(ch.node_visits), float(ch.state_value)) for ch in m.root.children)
+        return int(move), int(m.size), kids
+
+    rp = core.RandomPolicy(5.0, 5)
+    split = search(rp)
+    inner = core.RandomPolicy(5.0, 5)
+    sync = search(core.Policy(eval_state=lambda board: inner.eval_state(board), c_puct=5.0))
+    assert split == sync
+    assert split == search(rp)                          # and the split path is repeatable under the seed
+
+
 def test_random_policy_value_tracks_the_rollout_kernel(core, gpu):
     b = core.Board()
     for c in (112, 0, 113, 1, 114, 2, 115, 30):        # black to move with an open four: black wins most rollouts

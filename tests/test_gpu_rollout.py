@@ -157,7 +157,7 @@ def test_async_slots_equal_the_synchronous_call(gpu):
         assert np.array_equal(np.concatenate(outs), want)
         assert (want.sum(1) == 24).all()
     with pytest.raises(gpu.GomokuB200Error):
-        gpu.rollout_submit_host(8, parts[0], 24, outs[0])
+        gpu.rollout_submit_host(16, parts[0], 24, outs[0])
     gpu.rollout_wait(5)                                     # a slot never used: nothing to wait for
 
 
