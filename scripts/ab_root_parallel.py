@@ -1,16 +1,17 @@
 """Root-parallel search, one GPU: seconds per 10^6-playout move against the number of leaf batches in flight.
-    python scripts/ab_root_parallel.py [trees ...]       (prints one JSON line per tree count)"""
+    python scripts/ab_root_parallel.py [trees[:threads] ...]       (prints one JSON line per tree count)"""
 import json, os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gomokuai_b200 as gk
 from gomokuai_b200 import core
 
 gk.init(0)
-threads = os.cpu_count() or 8
+all_threads = os.cpu_count() or 8
 b = core.Board()
 for c in (112, 113, 97, 98):
     b.apply_move(c)
-for trees in [int(x) for x in sys.argv[1:]] or [1024, 128]:
+for spec in sys.argv[1:] or ["1024", "128"]:
+    trees, threads = (int(x) for x in spec.split(":")) if ":" in spec else (int(spec), all_threads)
     per_tree = max(1, 1_000_000 // trees)
     row = {"trees": trees, "playouts_per_tree": per_tree, "threads": threads, "groups": {}}
     ref = None                                                # the statistics do not depend on the group count
