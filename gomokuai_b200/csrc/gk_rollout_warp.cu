@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(kMaxThreads) rollout_warp_kernel(RolloutArgs a
     const bool is_row = lane < 15;
     const uint32_t blk = __reduce_add_sync(kFull, is_row ? __popc(sw[0] & 0x7fffu) : 0);
     const uint32_t wht = __reduce_add_sync(kFull, is_row ? __popc(sw[0] >> 16) : 0);
-    uint32_t rowmask = __ballot_sync(kFull, is_row && ((sw[0] | (sw[0] >> 16)) & 0x7fffu) != 0x7fffu);
     uint32_t left = uint32_t(kCells) - blk - wht;
     uint32_t colour = blk == wht ? 0u : 1u;                      // black moves first, Game.h:128; Game.cpp:52
     uint32_t played = 0;
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(kMaxThreads) rollout_warp_kernel(RolloutArgs a
         //    the top of iteration m, BEFORE move m's stone is on the board, and patched with that stone if it is the same
         //    row; the index itself (one byte of some lane's Philox block) is fetched an iteration before that;
         //  * the fallback row -- the next row that still has an empty cell, when the start index lies behind the last
-        //    empty cell of its row -- is looked up only when needed (a uniform branch);
+        //    empty cell of its row -- is looked up only when needed (a uniform branch: one ballot of the row owners);
         //  * the win vote of move m is looked at one iteration later: move m+1 is played speculatively and thrown away
         //    when move m turns out to have ended the game (registers only, nothing to undo).
         auto draw_block = [&](uint32_t first_move) {              // lane j: the four start indices of Philox block first_move / 4 + j, one byte each
@@ -162,19 +161,19 @@ __global__ void __launch_bounds__(kMaxThreads) rollout_warp_kernel(RolloutArgs a
                 uint32_t wn = __shfl_sync(kFull, sw[0], yn);
                 rn = start_index(played + 2u);
                 // ---- move m: Board::getRandomMove = the first empty cell at or after the start index, cyclically --------
-                uint32_t empty = ~(w | (w >> 16)) & 0x7fffu;
-                uint32_t avail = empty & xmask;
+                uint32_t avail = ~(w | (w >> 16)) & 0x7fffu & xmask;
                 if (avail == 0) {                                 // nothing left in row y from there on: all of the next row that has a cell
+                    const uint32_t occ0 = (sw[0] | (sw[0] >> 16)) & 0x7fffu;   // (the rows that still have one: asked of their owners now)
+                    const uint32_t rowmask = __ballot_sync(kFull, lane < 15 && occ0 != 0x7fffu);
                     uint32_t m = rowmask & ~((2u << y) - 1u);
                     if (m == 0) m = rowmask;
                     y = 31u - __clz(m & (0u - m));
                     w = __shfl_sync(kFull, sw[0], y);
-                    avail = empty = ~(w | (w >> 16)) & 0x7fffu;
+                    avail = ~(w | (w >> 16)) & 0x7fffu;
                 }
                 const uint32_t xbit = avail & (0u - avail);
                 const uint32_t stone = 1u + 0xffffu * colour;
                 if (yn == y) wn |= xbit * stone;
-                if ((empty & (empty - 1u)) == 0) rowmask ^= 1u << y;            // that was the row's last empty cell
                 const uint32_t x = 31u - __clz(xbit);
                 if (kMoves && trace && lane == 0) trace[played] = uint8_t(y * 15u + x);
                 // ---- Board::applyMove + checkGameEnd: every lane puts the stone on the slots it owns that pass through (x, y)

@@ -2,7 +2,8 @@
 // against a STUB of the C-ABI: rollouts are replaced by hash-derived outcomes after a modelled GPU latency, so the
 // host-side selection / backup cost can be profiled without a GPU.  Development tool, not part of the product.
 //   g++ -O2 -std=c++17 -I include scripts/host_bw/rp_host_bench.cpp gomokuai_b200/csrc/host/root_parallel.cpp \
-//       gomokuai_b200/csrc/host/mcts.cpp -lpthread -o /tmp/rp_host_bench && /tmp/rp_host_bench 2048 245 8 100
+//       gomokuai_b200/csrc/host/mcts.cpp -lpthread -o /tmp/rp_host_bench && /tmp/rp_host_bench 2048 245 8 100 [groups [reps]]
+// tests/test_root_parallel_host.py builds it (also with -fsanitize=thread) to check the scheduler without a GPU.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -59,11 +60,13 @@ int main(int argc, char** argv) {
     const int per_tree = argc > 2 ? std::atoi(argv[2]) : 245;
     cfg.threads = argc > 3 ? std::atoi(argv[3]) : 8;
     g_latency_us = argc > 4 ? std::atoi(argv[4]) : 100;
+    cfg.groups = argc > 5 ? std::atoi(argv[5]) : 0;
+    const int reps = argc > 6 ? std::atoi(argv[6]) : 3;
     cfg.seed = 11;
     Board b;
     for (int c : { 112, 113, 97, 98 }) b.applyMove(Position(c));
     RootParallelSearch s(cfg);
-    for (int rep = 0; rep < 3; ++rep) {
+    for (int rep = 0; rep < reps; ++rep) {
         s.run(b, per_tree);
         long long visits = 0, chk = 0;
         for (int c = 0; c < BOARD_SIZE; ++c) { visits += s.stats()[c]; chk = chk * 31 + s.stats()[c]; }
