@@ -27,7 +27,8 @@ for w in $what; do
     benchN)  n=$(nvidia-smi -L | wc -l); python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 > $out/bench_n${n}_$tag.json 2> $out/bench_n${n}_$tag.err; r=$?; head -c 400 $out/bench_n${n}_$tag.json; echo; [ $r -ne 0 ] && { tail -8 $out/bench_n${n}_$tag.err; rc=$r; } ;;
     fuzz)    python tests/tools/fuzz_guided.py > $out/fuzz_guided_$tag.json 2> $out/fuzz_guided_$tag.err; r=$?; cat $out/fuzz_guided_$tag.json; tail -3 $out/fuzz_guided_$tag.err; [ $r -ne 0 ] && rc=$r
              python tests/tools/fuzz_eval.py 100000 > $out/fuzz_eval_$tag.txt 2>&1; r=$?; tail -1 $out/fuzz_eval_$tag.txt; [ $r -ne 0 ] && rc=$r
-             python tests/tools/fuzz_rollout.py 20000 > $out/fuzz_rollout_$tag.txt 2>&1; r=$?; tail -1 $out/fuzz_rollout_$tag.txt; [ $r -ne 0 ] && rc=$r ;;
+             python tests/tools/fuzz_rollout.py 20000 > $out/fuzz_rollout_$tag.txt 2>&1; r=$?; tail -1 $out/fuzz_rollout_$tag.txt; [ $r -ne 0 ] && rc=$r
+             python tests/tools/fuzz_search.py 600 > $out/fuzz_search_$tag.json 2> $out/fuzz_search_$tag.err; r=$?; tail -1 $out/fuzz_search_$tag.json; tail -3 $out/fuzz_search_$tag.err; [ $r -ne 0 ] && rc=$r ;;
     sweep)   python scripts/sweep_root_parallel.py > $out/rp_sweep_$tag.json 2> $out/rp_sweep_$tag.err; r=$?; tail -6 $out/rp_sweep_$tag.err | cut -c1-300; [ $r -ne 0 ] && rc=$r ;;
     small)   python scripts/profile_small_rollout.py > $out/small_plain_$tag.json 2> $out/small_$tag.err && \
              ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max,smsp__inst_executed.sum --clock-control none --csv --log-file $out/small_launches_$tag.csv python scripts/profile_small_rollout.py > $out/small_lengths_$tag.json 2>> $out/small_$tag.err; \
