@@ -11,8 +11,9 @@
 // slot is "a x + b y == c", the stone's bit is "min(p, q)"), and the win test is one vote.  No shared memory in the loop,
 // one Philox block per LANE gives the random numbers of 128 moves at once.
 //
-// One CTA per position, one warp per rollout (rollouts_per_pos <= 32).  Used while the whole batch is one resident wave
-// of warps (rollout_warp_fits); above that K2's thread-per-rollout forms win on throughput.
+// One CTA per position, one warp per rollout (rollouts_per_pos <= 32).  Used for batches of up to ten warps per SM
+// (rollout_warp_fits): a move costs ~90 warp instructions PER ROLLOUT here, so beyond that the warps wait for issue slots and
+// K2's thread-per-rollout forms win.
 #include <cuda_runtime.h>
 
 #include <cstdint>

@@ -111,6 +111,8 @@ class RandomPolicy : public Policy {
 public:
     explicit RandomPolicy(double c_puct = C_PUCT, std::size_t c_rollouts = 5);
     ~RandomPolicy() override;
+    RandomPolicy(const RandomPolicy&) = delete;      // the slots capture `this`, and the page-locked block has one owner
+    RandomPolicy& operator=(const RandomPolicy&) = delete;
     EvalResult averagedSimulate(Board& board);
     Probs simulateBegin(Board& board) override;      // the c_rollouts playouts of averagedSimulate, in flight on the GPU
     float simulateEnd() override;
