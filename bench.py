@@ -380,7 +380,7 @@ def gpu_root_parallel(gk, torch, dist, dev, rank, world, barrier, moves=4):
                         "note": "the tree stays on the host (north_star): a move costs trees_per_gpu x playouts_per_tree host playouts / "
                                 "threads (every thread does tree work; whoever finishes a group's last tree launches its leaf batch); the ranks "
                                 "of one box share its cores, so more GPUs add no host throughput"},
-            "gpu_launches_per_move": per_tree * max(1, min(4 if trees >= 4096 else 6, trees // 16)), "moves": rows}
+            "gpu_launches_per_move": per_tree * max(1, min(8, trees // 16)), "moves": rows}
 
 
 def run_gpu_arm(args, rank, world, local_rank):

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -631,8 +632,21 @@ gk_status gk_rollout_batch_host(const uint32_t* h_boards, int n, int rollouts_pe
             gk::RolloutArgs a{};
             a.boards = g_stage_boards; a.n = n; a.rollouts_per_pos = rollouts_per_pos;
             a.key_lo = uint32_t(philox_key); a.key_hi = uint32_t(philox_key >> 32); a.ctr_hi = ctr_hi; a.pos_base = pos_base;
+            // the kernel stores a position's three counts (never negative) as that position's block retires: watching them
+            // arrive in the page-locked block saves the stream synchronisation's own latency, ~3 us of a ~27 us call
+            volatile int32_t* counts = g_stage_wdb;
+            for (int k = 0; k < 3 * n; ++k) counts[k] = INT32_MIN;
             GK_CUDA(launch_small(a, g_stage_wdb, p.stream, g_stage_boards));
-            GK_CUDA(cudaStreamSynchronize(p.stream));
+            int seen = 0;
+            for (int spins = 0; spins < (1 << 22); ++spins) {
+                while (seen < 3 * n && counts[seen] != INT32_MIN) ++seen;
+                if (seen == 3 * n) break;
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            if (seen < 3 * n) GK_CUDA(cudaStreamSynchronize(p.stream));      // nothing arrived: the stream knows why
             std::memcpy(h_wdb, g_stage_wdb, size_t(n) * 12);
             return GK_OK;
         }

@@ -192,6 +192,8 @@ void Default::AddNoise(Node* node, float alpha, float epsilon) {
     for (auto& child : node->children) child->action_prob = prior[child->position];
 }
 
+namespace { constexpr std::int32_t kCountPending = INT32_MIN; }   // no count is negative
+
 Probs Policy::simulateBegin(Board&) { throw std::logic_error("this policy has no split simulate"); }
 float Policy::simulateEnd() { throw std::logic_error("this policy has no split simulate"); }
 
@@ -223,6 +225,8 @@ Probs RandomPolicy::simulateBegin(Board& board) {
         m_pinned = static_cast<std::uint32_t*>(p);
     }
     board.pack(m_pinned);
+    volatile std::int32_t* counts = reinterpret_cast<volatile std::int32_t*>(m_pinned + 16);
+    counts[0] = counts[1] = counts[2] = kCountPending;
     const std::uint64_t call = g_rollout_calls.fetch_add(1);
     if (gk_rollout_submit_host(m_slot, m_pinned, 1, static_cast<int>(c_rollouts), rollout_key(), static_cast<std::uint32_t>(call >> 30),
                                static_cast<int>(call & 0x3fffffff), reinterpret_cast<std::int32_t*>(m_pinned + 16)) != GK_OK)
@@ -235,7 +239,19 @@ float RandomPolicy::simulateEnd() {
     if (m_pendingPlayer == Player::None) throw std::logic_error("simulateEnd without simulateBegin");
     const Player player = m_pendingPlayer;
     m_pendingPlayer = Player::None;
-    if (gk_rollout_wait(m_slot) != GK_OK) throw std::runtime_error(std::string("gk_rollout_wait: ") + gk_last_error());
+    // The kernel stores the three counts into this page-locked block as its last act: watching them arrive saves the
+    // stream synchronisation's own latency (2-3 us of a ~27 us playout).  Not there after a while (or a launch that
+    // failed): ask the stream, which also reports the error.
+    volatile std::int32_t* counts = reinterpret_cast<volatile std::int32_t*>(m_pinned + 16);
+    bool arrived = false;
+    for (int spins = 0; spins < (1 << 22) && !arrived; ++spins) {
+        arrived = counts[0] != kCountPending && counts[1] != kCountPending && counts[2] != kCountPending;
+#if defined(__x86_64__)
+        if (!arrived) __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (!arrived && gk_rollout_wait(m_slot) != GK_OK) throw std::runtime_error(std::string("gk_rollout_wait: ") + gk_last_error());
     const std::int32_t* wdb = reinterpret_cast<const std::int32_t*>(m_pinned + 16);
     const float black_value = static_cast<float>(wdb[2] - wdb[0]) / static_cast<float>(c_rollouts);
     return CalcScore(player, black_value);

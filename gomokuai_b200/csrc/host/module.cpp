@@ -189,13 +189,13 @@ PYBIND11_MODULE(CorePyExt, mod) {
 
     // ---- new: root-parallel search -------------------------------------------------------------------------------
     py::class_<RootParallelSearch>(mod, "RootParallelSearch", "Root-parallel MCTS: many trees, leaves simulated in one GPU batch per round")
-        .def(py::init([](int trees, int c_rollouts, double c_puct, std::uint64_t seed, int replica_base, int threads, bool noise, bool eager, int groups) {
+        .def(py::init([](int trees, int c_rollouts, double c_puct, std::uint64_t seed, int replica_base, int threads, bool noise, bool eager, int groups, bool watch) {
                  RootParallelConfig cfg;
                  cfg.trees = trees; cfg.c_rollouts = c_rollouts; cfg.c_puct = c_puct; cfg.seed = seed;
-                 cfg.replica_base = replica_base; cfg.threads = threads; cfg.noise = noise; cfg.eager = eager; cfg.groups = groups;
+                 cfg.replica_base = replica_base; cfg.threads = threads; cfg.noise = noise; cfg.eager = eager; cfg.groups = groups; cfg.watch = watch;
                  return new RootParallelSearch(cfg);
              }), "trees"_a = 256, "c_rollouts"_a = 5, "c_puct"_a = C_PUCT, "seed"_a = 1, "replica_base"_a = 0, "threads"_a = 0, "noise"_a = false,
-             "eager"_a = false, "groups"_a = 0)
+             "eager"_a = false, "groups"_a = 0, "watch"_a = true)
         .def("run", [](RootParallelSearch& s, const Board& b, int playouts_per_tree, py::object seed) {
             const bool reseed = !seed.is_none();
             const std::uint64_t key = reseed ? seed.cast<std::uint64_t>() : 0;

@@ -135,9 +135,10 @@ private:
     bool stop_ = false;
 };
 
+constexpr std::int32_t kCountPending = INT32_MIN;   // no count is negative
 constexpr int kMaxGroups = 8;       // leaf batches in flight at most (gk_rollout_submit_host slots 0..7)
-constexpr int kAutoGroups = 6;      // ... and when the caller leaves the choice open (measured: scripts/ab_root_parallel.py,
-                                    // profiles/r03c_root_parallel_groups.json; 4 from 4 096 trees on, where the batches are large)
+constexpr int kAutoGroups = 8;      // ... and when the caller leaves the choice open (measured: scripts/ab_root_parallel.py,
+                                    // profiles/r03q_root_parallel_groups.json)
 
 }  // namespace
 
@@ -413,7 +414,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     // (a group needs few trees to be worth a launch since a leaf batch is ONE fused launch: with 128 trees per rank -- the
     // benchmark's 1 024 trees over 8 GPUs -- four groups of 32 keep four round trips in flight instead of two)
     const int groups = m_cfg.groups > 0 ? std::min({ m_cfg.groups, kMaxGroups, n_trees })
-                                        : std::max(1, std::min(n_trees >= 4096 ? 4 : kAutoGroups, n_trees / 16));
+                                        : std::max(1, std::min(kAutoGroups, n_trees / 16));
     std::array<int, kMaxGroups + 1> gs{};
     for (int g = 0; g <= groups; ++g) gs[g] = static_cast<int>(static_cast<long long>(n_trees) * g / groups);
     const long long visits_total = static_cast<long long>(playouts_per_tree + 1) * groups;
@@ -466,6 +467,8 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
             const long long finished = G.done.fetch_add(hi - lo, std::memory_order_acq_rel) + (hi - lo);
             if (finished == static_cast<long long>(round + 1) * count && round < playouts_per_tree) {
                 const auto t0 = std::chrono::steady_clock::now();
+                volatile std::int32_t* counts = m->wdb + static_cast<std::size_t>(gs[g]) * 3;      // every backup of the round has read them
+                for (int k = 0; k < 3 * count; ++k) counts[k] = kCountPending;
                 if (gk_rollout_submit_host(g, m->packed + static_cast<std::size_t>(gs[g]) * 16, count, m_cfg.c_rollouts, m_cfg.seed,
                                            static_cast<std::uint32_t>(round), m_cfg.replica_base + gs[g],
                                            m->wdb + static_cast<std::size_t>(gs[g]) * 3) != GK_OK)
@@ -485,8 +488,20 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
                 while (G.arrived.load(std::memory_order_acquire) < round && !failed.load(std::memory_order_relaxed)) {
                     if (G.submitted.load(std::memory_order_acquire) >= round && !G.waiting.test_and_set(std::memory_order_acquire)) {
                         if (G.arrived.load(std::memory_order_acquire) < round) {
+                            // The kernel stores a leaf's three counts into the page-locked block as that leaf's CTA retires:
+                            // watching them arrive saves the stream synchronisation's own latency (~3 us of a ~33 us round
+                            // trip).  No progress for a while (or a failed launch): ask the stream, which reports the error.
                             const auto t1 = std::chrono::steady_clock::now();
-                            if (gk_rollout_wait(g) != GK_OK) fail("gk_rollout_wait");
+                            volatile const std::int32_t* counts = m->wdb + static_cast<std::size_t>(gs[g]) * 3;
+                            const int total = 3 * (gs[g + 1] - gs[g]);
+                            int seen = 0;
+                            for (int spins = 0; m_cfg.watch && spins < (1 << 22); ++spins) {
+                                while (seen < total && counts[seen] != kCountPending) ++seen;
+                                if (seen == total) break;
+                                cpu_relax();
+                            }
+                            std::atomic_thread_fence(std::memory_order_acquire);
+                            if (seen < total && gk_rollout_wait(g) != GK_OK) fail("gk_rollout_wait");
                             G.arrived.store(round, std::memory_order_release);
                             clock[id][1] += seconds_since(t1);
                         }
@@ -501,10 +516,9 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         }
     };
     m->team->run([&](int id) { worker(id); });
-    if (failed.load()) {
-        for (int g = 0; g < groups; ++g) gk_rollout_wait(g);
-        throw std::runtime_error(error);
-    }
+    for (int g = 0; g < groups; ++g)                              // the streams are idle by now; a launch error surfaces here at the latest
+        if (gk_rollout_wait(g) != GK_OK && !failed.load()) fail("gk_rollout_wait");
+    if (failed.load()) throw std::runtime_error(error);
     double idle = 0, t_sync = 0, t_submit = 0;
     for (const auto& c : clock) { idle += c[0]; t_sync += c[1]; t_submit += c[2]; }
     idle /= n_threads;                           // mean over the threads: time spent waiting for results

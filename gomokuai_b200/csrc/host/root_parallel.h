@@ -27,6 +27,7 @@ struct RootParallelConfig {
     // MCTS.cpp:182), so a search from a fresh tree -- which is what every root-parallel move is -- draws none.
     bool noise = false;
     int groups = 0;             // leaf batches in flight, 1..8 (0 = chosen from the tree count); never changes a result
+    bool watch = true;          // see a batch's counts arrive in the page-locked block instead of synchronising its stream
     bool eager = false;         // materialise every child at expansion like the reference (slow; kept to test the lazy tree against)
 };
 

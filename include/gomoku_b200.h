@@ -196,7 +196,10 @@ gk_status gk_rollout_trace_host(const uint32_t* h_board, int rollouts, uint64_t 
  * `slot` in [0, 16) names an independent stream with its own device buffers.  submit enqueues copy-in, rollouts and
  * copy-out and returns; h_boards and h_wdb must stay valid and untouched until gk_rollout_wait(slot) has returned.
  * Page-locked buffers (gk_host_alloc) make the call truly asynchronous and let the kernel read the boards in place.
- * One thread at a time per slot. */
+ * With both buffers page-locked and n <= 4096 the batch is one launch that stores a position's three counts into h_wdb
+ * as that position's block retires; counts are never negative, so a caller that fills h_wdb with a negative value before
+ * the submit may WATCH them arrive (volatile reads) instead of paying gk_rollout_wait's stream synchronisation -- the
+ * root-parallel search and the MCTS mirror do.  One thread at a time per slot. */
 gk_status gk_rollout_submit_host(int slot, const uint32_t* h_boards, int n, int rollouts_per_pos,
                                  uint64_t philox_key, uint32_t ctr_hi, int pos_base, int32_t* h_wdb);
 gk_status gk_rollout_wait(int slot);

@@ -18,7 +18,7 @@ for spec in sys.argv[1:] or ["1024", "128"]:
     for groups in (1, 2, 3, 4, 6, 8):
         if groups > trees:
             continue
-        s = core.RootParallelSearch(trees=trees, c_rollouts=5, seed=5, threads=threads, groups=groups)
+        s = core.RootParallelSearch(trees=trees, c_rollouts=5, seed=5, threads=threads, groups=groups, watch=os.environ.get("RP_WATCH", "1") != "0")
         secs, drv, idle = [], [], []
         for rep in range(4):
             st = s.run(b, per_tree)

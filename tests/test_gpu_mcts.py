@@ -167,15 +167,17 @@ def test_root_allreduce_through_the_c_abi(gpu):
 
 
 def test_root_parallel_pipeline_is_invisible_in_the_statistics(core):
-    """Four tree groups in flight, chunked work distribution, a helping driver thread: none of it may show in the
-    result -- a tree's Philox stream is (round, global tree index), its noise stream is seeded per tree."""
+    """Several tree groups in flight, chunked work distribution, whichever thread launching and awaiting the batches,
+    counts watched as they arrive or streams synchronised: none of it may show in the result -- a tree's Philox stream
+    is (round, global tree index), its noise stream is seeded per tree."""
     b = core.Board()
     for c in (112, 113, 97):
         b.apply_move(c)
-    ref = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=2).run(b, 60)      # 4 groups of 75 trees
+    ref = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=2).run(b, 60)      # 8 groups of 37 / 38 trees
     assert ref[0].sum() == 300 * 59
-    for threads in (3, 7):
-        assert np.array_equal(core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=threads).run(b, 60), ref)
+    for threads, groups, watch in ((3, 0, True), (7, 0, False), (1, 1, True), (5, 3, False), (16, 8, True)):
+        s = core.RootParallelSearch(trees=300, c_rollouts=5, seed=21, threads=threads, groups=groups, watch=watch)
+        assert np.array_equal(s.run(b, 60), ref), (threads, groups, watch)
     s = core.RootParallelSearch(trees=300, c_rollouts=5, seed=5, threads=4)
     first = s.run(b, 30)
     assert np.array_equal(s.run(b, 60, 21), ref)                    # the searcher is reusable and reseedable

@@ -41,7 +41,8 @@ for i, moves in enumerate(lists):
     groups = int(rng.choice([0, 1, 3, 8]))
     base = int(rng.integers(0, 1 << 20))
     key = int(rng.integers(1, 1 << 40))
-    s = core.RootParallelSearch(trees=trees, c_rollouts=5, seed=key, threads=threads, noise=False, replica_base=base, groups=groups)
+    s = core.RootParallelSearch(trees=trees, c_rollouts=5, seed=key, threads=threads, noise=False, replica_base=base, groups=groups,
+                                watch=bool(rng.integers(0, 2)))
     s.run(b, playouts)
     for t in sorted(set(rng.integers(0, trees, size=min(trees, 4)).tolist())):
         want = ref.mcts_injected(moves, playouts, n_searches=0, sim_kind=1, key=key, tree=base + t, c_rollouts=5)
