@@ -409,10 +409,10 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     // group v % G: back up the group's previous batch, select the next leaves.  There is no driver thread: every thread
     // walks the visits in order and takes trees in chunks; whoever finishes a group's LAST tree submits its batch
     // (one launch, a few microseconds, while the others are already at the next visit), and whoever first needs a
-    // batch that is in flight waits for it on behalf of all.  A tree's Philox stream is (round, global tree index),
-    // whatever G and the thread count are.
+    // batch that is in flight watches its counts arrive on behalf of all.  A tree's Philox stream is (round, global
+    // tree index), whatever G and the thread count are.
     // (a group needs few trees to be worth a launch since a leaf batch is ONE fused launch: with 128 trees per rank -- the
-    // benchmark's 1 024 trees over 8 GPUs -- four groups of 32 keep four round trips in flight instead of two)
+    // benchmark's 1 024 trees over 8 GPUs -- eight groups of 16 keep eight round trips in flight)
     const int groups = m_cfg.groups > 0 ? std::min({ m_cfg.groups, kMaxGroups, n_trees })
                                         : std::max(1, std::min(kAutoGroups, n_trees / 16));
     std::array<int, kMaxGroups + 1> gs{};
@@ -430,7 +430,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     struct alignas(64) GroupState {
         std::atomic<long long> claimed{ 0 }, done{ 0 };   // chunks handed out / trees finished, over all rounds
         std::atomic<int> submitted{ 0 }, arrived{ 0 };    // batches launched / batches whose results are in m->wdb
-        std::atomic_flag waiting = ATOMIC_FLAG_INIT;      // someone is inside gk_rollout_wait for this group
+        std::atomic_flag waiting = ATOMIC_FLAG_INIT;      // someone is watching / waiting for this group's batch
     };
     std::array<GroupState, kMaxGroups> gst;
     std::atomic<bool> failed{ false };
@@ -441,7 +441,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
         if (error.empty()) error = std::string(what) + ": " + gk_last_error();
         failed.store(true);
     };
-    std::vector<std::array<double, 8>> clock(n_threads);   // per thread (padded): seconds waiting for results / inside gk_rollout_wait / inside gk_rollout_submit_host
+    std::vector<std::array<double, 8>> clock(n_threads);   // per thread (padded): seconds waiting for results / of it, as the group's watcher / inside gk_rollout_submit_host
     for (auto& c : clock) c.fill(0.0);
     auto seconds_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

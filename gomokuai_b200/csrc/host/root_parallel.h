@@ -51,7 +51,7 @@ public:
     static Position bestMove(const Stats& stats);             // most visited root child, ties -> lowest cell (MCTS.cpp:129-134)
 
     double seconds_total = 0, seconds_gpu = 0;                // wall clock of the last run / of it, the time a thread waited for GPU results (mean over threads)
-    std::array<double, 3> driver_seconds{};                   // summed over threads: inside gk_rollout_wait, (unused, 0), inside gk_rollout_submit_host
+    std::array<double, 3> driver_seconds{};                   // summed over threads: watching / waiting for a batch as its group's watcher, (unused, 0), inside gk_rollout_submit_host
     std::int64_t leaves = 0, nodes = 0;
 
 private:
