@@ -35,6 +35,7 @@ for w in $what; do
              python scripts/small_rollout_summary.py $out/small_launches_$tag.csv $out/small_lengths_$tag.json > $out/small_rollout_$tag.json 2>> $out/small_$tag.err; head -c 900 $out/small_rollout_$tag.json; echo; \
              ncu --set full --import-source on --clock-control none -k regex:rollout_warp -c 1 -f -o /tmp/small_$tag python scripts/profile_small_rollout.py > /dev/null 2>> $out/small_$tag.err; \
              ncu -i /tmp/small_$tag.ncu-rep --page source --csv > $out/src_rollout_warp_$tag.csv 2>/dev/null; \
+             ncu -i /tmp/small_$tag.ncu-rep --page raw --csv > $out/small_raw_$tag.csv 2>/dev/null; \
              python scripts/bench_small_rollout.py > $out/small_latency_$tag.json 2>> $out/small_$tag.err ;;
     groups)  python scripts/ab_root_parallel.py 8192 1024 512 128 > $out/rp_groups_$tag.json 2> $out/rp_groups_$tag.err; r=$?; tail -2 $out/rp_groups_$tag.err; [ $r -ne 0 ] && rc=$r ;;
     *)       echo "unknown step $w" ;;
