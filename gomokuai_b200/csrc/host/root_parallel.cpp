@@ -58,7 +58,8 @@ struct Tree {
     std::int16_t root_child = -1;   // root move of the current path (-1: the leaf is the root itself)
     bool terminal = false;
     std::mt19937 rng;
-    std::array<std::int32_t, BOARD_SIZE> black_wins{}, white_wins{};   // rollouts below each root child
+    struct Wins { std::int32_t black, white; };
+    std::array<Wins, BOARD_SIZE> wins{};                             // rollouts won below each root child (one cache line per update)
 
     std::int32_t add(std::int32_t parent, int position, float pr, int player) {
         ANode n{};
@@ -324,7 +325,7 @@ static void backup(Tree& t, const std::int32_t* r, const RootParallelConfig& cfg
             }
         }
     }
-    if (t.root_child >= 0) { t.black_wins[t.root_child] += r[2]; t.white_wins[t.root_child] += r[0]; }
+    if (t.root_child >= 0) { t.wins[t.root_child].black += r[2]; t.wins[t.root_child].white += r[0]; }
     float v = static_cast<float>(t.nodes[t.leaf].player) * black_value;   // value for who moved into the leaf
     for (std::int32_t n = t.leaf; n >= 0; n = t.nodes[n].parent, v = -v) {
         if (t.in_root_block(n)) {
@@ -385,8 +386,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
                 t.clear(reserve);
                 t.add(-1, root.m_moveRecord.empty() ? -1 : static_cast<int>(root.m_moveRecord.back()), 1.0f, static_cast<int>(root_last));   // MCTS.h:138-151
                 t.board = root;
-                t.black_wins.fill(0);
-                t.white_wins.fill(0);
+                t.wins.fill({ 0, 0 });
                 t.rng.seed(static_cast<std::uint32_t>(m_cfg.seed * 2654435761u + static_cast<std::uint32_t>(m_cfg.replica_base + i)));
             }
         });
@@ -537,8 +537,8 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
             for (std::int32_t c = rt.first_child; c >= 0; c = t.nodes[c].next_sibling) m_stats[t.nodes[c].position] += t.nodes[c].visits;
         }
         for (int c = 0; c < BOARD_SIZE; ++c) {
-            m_stats[BOARD_SIZE + c] += t.black_wins[c];
-            m_stats[2 * BOARD_SIZE + c] += t.white_wins[c];
+            m_stats[BOARD_SIZE + c] += t.wins[c].black;
+            m_stats[2 * BOARD_SIZE + c] += t.wins[c].white;
         }
     }
     seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
