@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -18,6 +19,9 @@
 
 #if defined(__x86_64__)
 #include <immintrin.h>
+#endif
+#if defined(__linux__)
+#include <sys/mman.h>
 #endif
 
 #include "../../../include/gomoku_b200.h"
@@ -48,10 +52,52 @@ struct ANode {
     std::int8_t eager;              // children are one contiguous block [first_child, first_child + n_children)
 };
 
+// A tree's nodes: the little of std::vector the search uses, over storage that normally is a slice of one slab shared by
+// all trees of the searcher (huge pages: ~100 MB of nodes touched at random otherwise miss the TLB on every access) and
+// only falls back to its own heap block when a tree outgrows its slice.
+class NodeArray {
+public:
+    NodeArray() = default;
+    NodeArray(const NodeArray&) = delete;
+    NodeArray& operator=(const NodeArray&) = delete;
+    NodeArray(NodeArray&& o) noexcept { *this = std::move(o); }
+    NodeArray& operator=(NodeArray&& o) noexcept {
+        std::swap(m_data, o.m_data); std::swap(m_size, o.m_size); std::swap(m_cap, o.m_cap); std::swap(m_own, o.m_own);
+        return *this;
+    }
+    ~NodeArray() { if (m_own) std::free(m_data); }
+    ANode& operator[](std::size_t i) { return m_data[i]; }
+    const ANode& operator[](std::size_t i) const { return m_data[i]; }
+    std::size_t size() const { return m_size; }
+    bool empty() const { return m_size == 0; }
+    void clear() { m_size = 0; }
+    void adopt(ANode* storage, std::size_t capacity) {            // empty array over caller-owned storage
+        if (m_own) std::free(m_data);
+        m_data = storage; m_size = 0; m_cap = capacity; m_own = false;
+    }
+    void reserve(std::size_t n) { if (n > m_cap) grow(n); }
+    void push_back(const ANode& n) {
+        if (m_size == m_cap) grow(m_cap ? 2 * m_cap : 256);
+        m_data[m_size++] = n;
+    }
+
+private:
+    void grow(std::size_t n) {
+        ANode* fresh = static_cast<ANode*>(std::malloc(n * sizeof(ANode)));
+        if (!fresh) throw std::bad_alloc();
+        if (m_size) std::memcpy(fresh, m_data, m_size * sizeof(ANode));
+        if (m_own) std::free(m_data);
+        m_data = fresh; m_cap = n; m_own = true;
+    }
+    ANode* m_data = nullptr;
+    std::size_t m_size = 0, m_cap = 0;
+    bool m_own = false;
+};
+
 struct Tree {
-    std::vector<ANode> nodes;
-    std::vector<float> rvalue, rprior;  // statistics of the root's eager block, nodes [rfirst, rfirst + rn)
-    std::vector<std::int32_t> rvisits;
+    NodeArray nodes;
+    std::array<float, BOARD_SIZE> rvalue, rprior;   // statistics of the root's eager block, nodes [rfirst, rfirst + rn)
+    std::array<std::int32_t, BOARD_SIZE> rvisits;
     std::int32_t rfirst = 0, rn = 0;
     Board board;
     std::int32_t leaf = 0;          // selected this round
@@ -70,10 +116,10 @@ struct Tree {
         nodes.push_back(n);
         return static_cast<std::int32_t>(nodes.size()) - 1;
     }
-    void clear(std::size_t reserve) {
-        nodes.clear(); rvalue.clear(); rprior.clear(); rvisits.clear();
+    void clear(std::size_t reserve, ANode* slice) {               // slice: `reserve` nodes of the searcher's slab, or null
         rfirst = rn = 0;
-        nodes.reserve(reserve);
+        if (slice) nodes.adopt(slice, reserve);
+        else { nodes.clear(); nodes.reserve(reserve); }
     }
     bool in_root_block(std::int32_t i) const { return static_cast<std::uint32_t>(i - rfirst) < static_cast<std::uint32_t>(rn); }
     std::int32_t visits_of(std::int32_t i) const { return in_root_block(i) ? rvisits[i - rfirst] : nodes[i].visits; }
@@ -144,11 +190,33 @@ constexpr int kAutoGroups = 8;      // ... and when the caller leaves the choice
 }  // namespace
 
 struct RootParallelSearch::Impl {
-    std::vector<Tree> trees;
+    std::vector<Tree> trees;                // declared before the slab's owner below: the trees' slices die first
     std::uint32_t* packed = nullptr;        // trees x 16, page-locked (allocated on first run, when the GPU is bound)
     std::int32_t* wdb = nullptr;            // trees x 3, page-locked
     std::unique_ptr<Team> team;
-    ~Impl() { gk_host_free(packed); gk_host_free(wdb); }
+    void* slab = nullptr;                   // node storage of all trees, 2 MB aligned, MADV_HUGEPAGE
+    std::size_t slab_bytes = 0;
+    // `nodes_per_tree` nodes for each of `n` trees, or null when that is too much to hold in one piece
+    ANode* node_slab(std::size_t n, std::size_t nodes_per_tree) {
+        constexpr std::size_t kHuge = std::size_t(2) << 20, kMost = std::size_t(1) << 30;
+        const std::size_t want = (n * nodes_per_tree * sizeof(ANode) + kHuge - 1) / kHuge * kHuge;
+        if (want > kMost) return nullptr;
+        if (want > slab_bytes) {
+            for (Tree& t : trees) t.nodes.adopt(nullptr, 0);
+            std::free(slab);
+            slab = std::aligned_alloc(kHuge, want);
+            slab_bytes = slab ? want : 0;
+#if defined(__linux__)
+            if (slab) madvise(slab, want, MADV_HUGEPAGE);            // advisory: 4 KB pages work too, just slower
+#endif
+        }
+        return static_cast<ANode*>(slab);
+    }
+    ~Impl() {
+        for (Tree& t : trees) t.nodes.adopt(nullptr, 0);
+        std::free(slab);
+        gk_host_free(packed); gk_host_free(wdb);
+    }
 };
 
 RootParallelSearch::RootParallelSearch(const RootParallelConfig& cfg) : m(new Impl), m_cfg(cfg) {
@@ -186,7 +254,7 @@ static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
     t.nodes[node].eager = 1;
     if (node == 0) {                                                 // the root's block: statistics in parallel arrays
         t.rfirst = first; t.rn = empties;
-        t.rvalue.assign(empties, 0.0f); t.rprior.assign(empties, prior); t.rvisits.assign(empties, 0);
+        std::fill_n(t.rvalue.begin(), empties, 0.0f); std::fill_n(t.rprior.begin(), empties, prior); std::fill_n(t.rvisits.begin(), empties, 0);
     }
 }
 
@@ -379,11 +447,12 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
     const std::size_t reserve = m_cfg.eager ? static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 64 + 256
                                             : static_cast<std::size_t>(std::max(playouts_per_tree, 0)) * 2 + 256;
     {
+        ANode* const slab = m->node_slab(static_cast<std::size_t>(n_trees), reserve);
         std::atomic<int> next{ 0 };                                  // fresh trees, set up by the whole team (first-touch allocation)
         m->team->run([&](int) {
             for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < n_trees;) {
                 Tree& t = m->trees[i];
-                t.clear(reserve);
+                t.clear(reserve, slab ? slab + static_cast<std::size_t>(i) * reserve : nullptr);
                 t.add(-1, root.m_moveRecord.empty() ? -1 : static_cast<int>(root.m_moveRecord.back()), 1.0f, static_cast<int>(root_last));   // MCTS.h:138-151
                 t.board = root;
                 t.wins.fill({ 0, 0 });
