@@ -24,6 +24,8 @@ def _build(tmp, name, flags):
 def _run(exe, trees, per_tree, threads, latency_us, groups, reps=1):
     r = subprocess.run([exe, str(trees), str(per_tree), str(threads), str(latency_us), str(groups), str(reps)],
                        capture_output=True, text=True, timeout=300)
+    if "FATAL: ThreadSanitizer" in r.stderr:            # the runtime could not set up its shadow memory on this kernel
+        pytest.skip(r.stderr.strip().splitlines()[0])
     assert r.returncode == 0, r.stderr
     return r.stdout + r.stderr, re.findall(r"(\d+) playouts .* nodes (\d+), best (\d+), chk ([0-9a-f]+)", r.stdout)
 
