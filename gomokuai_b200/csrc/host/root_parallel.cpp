@@ -41,16 +41,19 @@ namespace {
 // A node carries its statistics inline (one cache line per child when a sibling list is walked: the search is bound
 // by memory latency, ~110 MB of trees per rank).  Only the root's materialised block of 200+ children keeps them in
 // three parallel arrays instead, so that its scan streams 2.6 KB and vectorises.
-struct ANode {
+struct ANode {                      // 32 bytes: two per cache line, none across a line boundary
     std::int32_t parent, first_child, last_child, next_sibling;
-    std::int16_t n_children;        // children that exist as nodes
-    std::int16_t n_moves;           // legal moves here (empty cells); > 0 once the node has been expanded
-    std::int16_t position, cursor;  // the move into this node; highest cell materialised so far (-1 none)
-    float value, prior;             // running mean from the view of who moved into the node; prior of the move
+    float value;                    // running mean from the view of who moved into the node
     std::int32_t visits;
+    std::int16_t position, cursor;  // the move into this node; highest cell materialised so far (-1 none)
+    std::uint8_t n_children;        // children that exist as nodes (<= 225)
+    std::uint8_t n_moves;           // legal moves here (empty cells); > 0 once the node has been expanded
     std::int8_t player;             // who played `position`
     std::int8_t eager;              // children are one contiguous block [first_child, first_child + n_children)
+    // (no prior: every child of a node has the prior 1 / n_moves of its parent -- Default::UniformProbs -- except the
+    //  root's block, whose priors Dirichlet noise may change and which live in Tree::rprior; the root itself has 1)
 };
+static_assert(sizeof(ANode) == 32, "two nodes per cache line");
 
 // A tree's nodes: the little of std::vector the search uses, over storage that normally is a slice of one slab shared by
 // all trees of the searcher (huge pages: ~100 MB of nodes touched at random otherwise miss the TLB on every access) and
@@ -107,11 +110,10 @@ struct Tree {
     struct Wins { std::int32_t black, white; };
     std::array<Wins, BOARD_SIZE> wins{};                             // rollouts won below each root child (one cache line per update)
 
-    std::int32_t add(std::int32_t parent, int position, float pr, int player) {
+    std::int32_t add(std::int32_t parent, int position, int player) {
         ANode n{};
         n.parent = parent; n.first_child = n.last_child = n.next_sibling = -1;
         n.position = static_cast<std::int16_t>(position); n.cursor = -1;
-        n.prior = pr;
         n.player = static_cast<std::int8_t>(player);
         nodes.push_back(n);
         return static_cast<std::int32_t>(nodes.size()) - 1;
@@ -242,15 +244,15 @@ Position RootParallelSearch::bestMove(const Stats& stats) {
 static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
     const int empties = static_cast<int>(board.moveCounts(Player::None));
     if (empties == 0) return;
-    t.nodes[node].n_moves = static_cast<std::int16_t>(empties);
+    t.nodes[node].n_moves = static_cast<std::uint8_t>(empties);
     if (!eager) return;
     const float prior = 1.0f / static_cast<float>(empties);
     const std::int32_t first = static_cast<std::int32_t>(t.nodes.size());
     const int player = -t.nodes[node].player;
     for (int c = 0; c < BOARD_SIZE; ++c)
-        if (board.cell(c) == 0) t.add(node, c, prior, player);
+        if (board.cell(c) == 0) t.add(node, c, player);
     t.nodes[node].first_child = first;
-    t.nodes[node].n_children = static_cast<std::int16_t>(empties);
+    t.nodes[node].n_children = static_cast<std::uint8_t>(empties);
     t.nodes[node].eager = 1;
     if (node == 0) {                                                 // the root's block: statistics in parallel arrays
         t.rfirst = first; t.rn = empties;
@@ -260,8 +262,8 @@ static void expand(Tree& t, std::int32_t node, const Board& board, bool eager) {
 
 // PUCB score of node c under a parent with sqrt(visits) = sq: state_value + c_puct * P * sqrt(N) / (n + 1), the
 // product evaluated left to right in double like the reference (MonteCarlo.hpp:23-28,62)
-static inline double pucb(const ANode& ch, double c_puct, double sq) {
-    return ch.value + c_puct * ch.prior * sq / static_cast<double>(ch.visits + 1);
+static inline double pucb(const ANode& ch, float prior, double c_puct, double sq) {
+    return ch.value + c_puct * prior * sq / static_cast<double>(ch.visits + 1);
 }
 
 // Default::Select (MonteCarlo.hpp:57-68) over a contiguous block of children: the first child with the highest score.
@@ -317,8 +319,9 @@ static std::int32_t select_block(const Tree& t, std::int32_t first, int n, doubl
     if (first != t.rfirst || n != t.rn) {                            // a block below the root (eager mode only): plain loop
         std::int32_t best = first;
         double best_score = -1.0;
+        const float prior = 1.0f / static_cast<float>(n);              // an eager block holds every legal move: n = n_moves
         for (std::int32_t c = first; c < first + n; ++c) {
-            const double score = pucb(t.nodes[c], c_puct, sq);
+            const double score = pucb(t.nodes[c], prior, c_puct, sq);
             if (score > best_score) { best_score = score; best = c; }
         }
         return best;
@@ -339,7 +342,7 @@ static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
     std::int32_t best = parent.first_child;                          // as the reference: the first child unless one scores above -1
     double best_score = -1.0;
     for (std::int32_t c = parent.first_child; c >= 0; c = t.nodes[c].next_sibling) {   // increasing cell order
-        const double score = pucb(t.nodes[c], c_puct, sq);
+        const double score = pucb(t.nodes[c], prior, c_puct, sq);
         if (score > best_score) { best_score = score; best = c; }
     }
     if (parent.n_children < parent.n_moves) {                       // someone has never been visited: value 0, visits 0
@@ -347,7 +350,7 @@ static std::int32_t select_lazy(Tree& t, std::int32_t node, double c_puct) {
         if (best < 0 || fresh > best_score) {
             int cell = parent.cursor + 1;
             while (t.board.cell(cell) != 0) ++cell;                 // the lowest empty cell above the cursor
-            const std::int32_t created = t.add(node, cell, prior, -parent.player);
+            const std::int32_t created = t.add(node, cell, -parent.player);
             ANode& p = t.nodes[node];
             if (p.last_child >= 0) t.nodes[p.last_child].next_sibling = created; else p.first_child = created;
             p.last_child = created;
@@ -421,8 +424,9 @@ std::vector<RootParallelSearch::DumpNode> RootParallelSearch::dumpTree(int tree)
         stack.pop_back();
         const ANode& nd = t.nodes[n];
         const bool in_block = t.in_root_block(n);
-        out.push_back({ nd.position, t.visits_of(n), in_block ? t.rvalue[n - t.rfirst] : nd.value, in_block ? t.rprior[n - t.rfirst] : nd.prior,
-                        static_cast<std::int16_t>(depth), nd.n_moves });
+        const float prior = in_block ? t.rprior[n - t.rfirst] : nd.parent < 0 ? 1.0f : 1.0f / static_cast<float>(t.nodes[nd.parent].n_moves);
+        out.push_back({ nd.position, t.visits_of(n), in_block ? t.rvalue[n - t.rfirst] : nd.value, prior,
+                        static_cast<std::int16_t>(depth), static_cast<std::int16_t>(nd.n_moves) });
         kids.clear();
         if (nd.eager) for (std::int32_t c = nd.first_child; c < nd.first_child + nd.n_children; ++c) kids.push_back(c);
         else for (std::int32_t c = nd.first_child; c >= 0; c = t.nodes[c].next_sibling) kids.push_back(c);
@@ -453,7 +457,7 @@ void RootParallelSearch::run(const Board& root, int playouts_per_tree) {
             for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < n_trees;) {
                 Tree& t = m->trees[i];
                 t.clear(reserve, slab ? slab + static_cast<std::size_t>(i) * reserve : nullptr);
-                t.add(-1, root.m_moveRecord.empty() ? -1 : static_cast<int>(root.m_moveRecord.back()), 1.0f, static_cast<int>(root_last));   // MCTS.h:138-151
+                t.add(-1, root.m_moveRecord.empty() ? -1 : static_cast<int>(root.m_moveRecord.back()), static_cast<int>(root_last));   // MCTS.h:138-151
                 t.board = root;
                 t.wins.fill({ 0, 0 });
                 t.rng.seed(static_cast<std::uint32_t>(m_cfg.seed * 2654435761u + static_cast<std::uint32_t>(m_cfg.replica_base + i)));
