@@ -39,7 +39,7 @@ namespace {
 // cursor.  Selection visits exactly the nodes the eager tree would (tests/test_gpu_mcts.py compares the two).
 // The root keeps a materialised block of children when Dirichlet noise makes their priors differ.
 // A node carries its statistics inline (one cache line per child when a sibling list is walked: the search is bound
-// by memory latency, ~110 MB of trees per rank).  Only the root's materialised block of 200+ children keeps them in
+// by memory latency, ~80 MB of trees per rank).  Only the root's materialised block of 200+ children keeps them in
 // three parallel arrays instead, so that its scan streams 2.6 KB and vectorises.
 struct ANode {                      // 32 bytes: two per cache line, none across a line boundary
     std::int32_t parent, first_child, last_child, next_sibling;
@@ -56,7 +56,7 @@ struct ANode {                      // 32 bytes: two per cache line, none across
 static_assert(sizeof(ANode) == 32, "two nodes per cache line");
 
 // A tree's nodes: the little of std::vector the search uses, over storage that normally is a slice of one slab shared by
-// all trees of the searcher (huge pages: ~100 MB of nodes touched at random otherwise miss the TLB on every access) and
+// all trees of the searcher (huge pages: ~70 MB of nodes touched at random otherwise miss the TLB on every access) and
 // only falls back to its own heap block when a tree outgrows its slice.
 class NodeArray {
 public:
